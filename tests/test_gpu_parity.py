@@ -1,0 +1,209 @@
+"""GPU parity: the CUDA path, called through the public API / C ABI, against the oracle.
+
+FP32 gate: rtol 1e-5 relative to max|g| or twice the oracle's own Float32
+rounding error, both measured against the Float64 oracle.  Index / scatter pullbacks and
+fused-vs-unfused runs: bit-exact."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import cases
+import gpu_util as U
+import yota_b200 as Y
+from oracle import c_oracle
+from oracle import yota_oracle as O
+from yota_b200 import ffi, jl
+
+pytestmark = pytest.mark.gpu
+F32 = np.float32
+
+
+def f32(args):
+    return [a.astype(F32) if isinstance(a, np.ndarray) and a.dtype.kind == "f" else a for a in args]
+
+
+# ---- the reference's own test cases, on the device ---------------------------------------
+@pytest.mark.parametrize("name,f,args", cases.gradcheck_cases(), ids=lambda v: v if isinstance(v, str) else "")
+def test_reference_cases(name, f, args):
+    U.check_parity(f, f32(args))
+
+
+@pytest.mark.parametrize("flags", [ffi.FLAG_NO_FUSE, ffi.FLAG_NO_GRAPH, ffi.FLAG_NO_STATIC])
+def test_reference_cases_other_plans(flags):
+    for name, f, args in cases.gradcheck_cases():
+        U.check_parity(f, f32(args), flags=flags)
+
+
+def test_getindex_pullbacks_exact():  # test/test_grad.jl:87-95
+    x = cases.rng(0).random((3, 4, 5)).astype(F32)
+    dx = Y.cu(x)
+    for f, sel in ((lambda x: x[1], (0, 0, 0)), (lambda x: x[1, 2, 1], (0, 1, 0))):
+        val, g = Y.grad(f, dx)
+        e = np.zeros_like(x)
+        e[sel] = 1
+        assert np.array_equal(g[1].to_host(), e) and val == float(x[sel])
+    _, g = Y.grad(lambda x: jl.sum(x[jl.colon, 1, jl.colon]), dx)
+    e = np.zeros_like(x)
+    e[:, 0, :] = 1
+    assert np.array_equal(g[1].to_host(), e)
+
+
+def test_ungetindex_known_answers_on_device():  # test/test_helpers.jl:11-25,74-86
+    ctx = Y.context()
+    dy = Y.cu(np.ones((4, 3), F32))
+    idx = Y.cu(np.array([1, 3, 1], np.int64))
+    dx = Y.B200Array((4, 5))
+    ffi.check(ffi.lib().yota_scatter_add_cols(ctx.h, dx.ptr, 4, 5, dy.ptr, idx.ptr, 3))
+    assert np.array_equal(dx.to_host(), np.array([[2, 0, 1, 0, 0]] * 4, F32))
+    _, g = Y.grad(lambda x: jl.sum(x[[1, 3, 1]]), Y.cu(np.zeros(4, F32)))
+    assert np.array_equal(g[1].to_host(), [2, 0, 1, 0])
+
+
+def test_seed_forms():  # test/test_grad.jl:253-268
+    x = Y.cu(np.array([1, 2, 3], F32))
+    for seed in (Y.cu(np.ones(3, F32)), "auto"):
+        val, g = Y.grad(lambda x: 2 * x, x, seed=seed)
+        assert np.array_equal(val.to_host(), [2, 4, 6]) and np.array_equal(g[1].to_host(), [2, 2, 2])
+    a = f32(cases.gradcheck_cases()[1][2])
+    v1, g1 = Y.grad(cases.loss_tanh, *map(Y.cu, a))
+    v2, g2 = Y.grad(cases.loss_tanh, *map(Y.cu, a), seed=2.0)
+    assert v1 == v2 and np.allclose(2 * g1[1].to_host(), g2[1].to_host(), rtol=1e-6)
+
+
+def test_cached_equals_fresh_and_host_arrays():  # test/test_grad.jl:271-289
+    a = f32(cases.gradcheck_cases()[2][2])
+    Y.reset()
+    r1 = Y.grad(cases.loss_abs2, *map(Y.cu, a))
+    r2 = Y.grad(cases.loss_abs2, *map(Y.cu, a))  # cached compiled tape (graph replay)
+    r3 = Y.grad(cases.loss_abs2, *map(Y.cu, a))
+    rh = Y.grad(cases.loss_abs2, *a)  # host arrays in -> host arrays out
+    assert r1[0] == r2[0] == r3[0] == rh[0]
+    for x, y, z, h in zip(r1[1][1:], r2[1][1:], r3[1][1:], rh[1][1:]):
+        assert np.array_equal(U.bits(x.to_host()), U.bits(y.to_host()))
+        assert np.array_equal(U.bits(x.to_host()), U.bits(z.to_host()))
+        assert np.array_equal(U.bits(x.to_host()), U.bits(h))
+
+
+def test_update():  # src/update.jl:42-49
+    x, g = Y.cu(np.array([1, 2, 3, 4], F32)), Y.cu(np.array([0.5, 0.5, 1, 1], F32))
+    Y.update(x, g)
+    assert np.array_equal(x.to_host(), [0.5, 1.5, 2, 3])
+
+
+def test_transpose_cat():  # test/test_grad.jl:98-104,175-182
+    r = cases.rng(5)
+    U.check_parity(lambda a, b: jl.sum(jl.vcat(a, b) ** 2), [r.random((2, 3)).astype(F32), r.random((3, 3)).astype(F32)])
+    U.check_parity(lambda a, b: jl.sum(jl.hcat(a, b) ** 2), [r.random((2, 3)).astype(F32), r.random((2, 4)).astype(F32)])
+    U.check_parity(lambda a: jl.sum(jl.transpose(a) * jl.transpose(a)), [r.random((5, 7)).astype(F32)])
+
+
+def test_unary_rules():
+    r = cases.rng(6)
+    x = (r.random((8, 6)) + 0.5).astype(F32)
+    for fn in (jl.exp, jl.log, jl.sin, jl.cos, jl.sqrt, jl.relu, jl.sigmoid, jl.abs2, jl.tanh):
+        U.check_parity(lambda a: jl.sum(fn(a - 0.7) if fn in (jl.relu,) else fn(a)), [x])
+    U.check_parity(lambda a, b: jl.sum(a / b), [x, (r.random((8, 1)) + 1).astype(F32)])
+
+
+# ---- GEMM --------------------------------------------------------------------------------
+@pytest.mark.parametrize("tA,tB", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_gemm_ffma(tA, tB):
+    r = cases.rng(8)
+    for m, n, k in [(128, 128, 64), (200, 77, 33), (10, 64, 128), (1, 5, 3), (257, 130, 300)]:
+        A = r.standard_normal((k, m) if tA else (m, k)).astype(F32)
+        B = r.standard_normal((n, k) if tB else (k, n)).astype(F32)
+        ref = (A.T if tA else A).astype(np.float64) @ (B.T if tB else B).astype(np.float64)
+        got = U.gemm(0, tA, tB, np.asfortranarray(A), np.asfortranarray(B))
+        assert np.allclose(got, ref, rtol=1e-5, atol=1e-5 * np.abs(ref).max()), (m, n, k)
+        C0 = np.asfortranarray(r.standard_normal((m, n)).astype(F32))
+        got = U.gemm(0, tA, tB, np.asfortranarray(A), np.asfortranarray(B), C0)
+        assert np.allclose(got, ref + C0, rtol=1e-5, atol=1e-5 * np.abs(ref).max())
+
+
+# ---- the benchmark configs, scaled so the oracle finishes in seconds --------------------
+def test_c1_mlp_full_size():
+    U.check_parity(cases.c1_mlp, cases.c1_args())
+
+
+def test_c2_chain_scaled_and_ragged():
+    for n, m in [(512, 384), (1024, 1024), (250, 33), (4, 3), (1030, 7)]:
+        U.check_parity(cases.c2_chain, cases.c2_args(n, m))
+
+
+def test_c2_fused_equals_unfused_bitwise():
+    a = [Y.cu(x) for x in cases.c2_args(1024, 512)]
+    ref = None
+    for flags in (0, ffi.FLAG_NO_FUSE, ffi.FLAG_NO_STATIC, ffi.FLAG_NO_GRAPH):
+        val, g = Y.grad(cases.c2_chain, *a, flags=flags)
+        got = [U.bits(x.to_host()) for x in g[1:3]]  # dx, dW: elementwise, order-independent
+        if ref is None:
+            ref = got
+        for x, y in zip(ref, got):
+            assert np.array_equal(x, y), flags
+
+
+def test_c3_mlp_scaled():
+    U.check_parity(cases.make_c3(3, 96), cases.c3_args(3, 64, 96))
+    U.check_parity(cases.make_c3(8, 256), cases.c3_args(8, 256, 256))
+
+
+def test_c4_rnn_scaled():
+    U.check_parity(cases.make_c4(5), cases.c4_args(32, 16, 5))
+    U.check_parity(cases.make_c4(16), cases.c4_args(128, 32, 16))
+
+
+def test_c5_embedding_bit_exact():
+    for rows, nt, ni, zipf in [(8, 16, 100, False), (256, 1024, 8192, False), (256, 512, 20000, True), (3, 7, 50, False),
+                               (64, 5000, 100, False)]:
+        E, idx, V = cases.c5_args(rows, nt, ni, zipf=zipf)
+        val, g = Y.grad(cases.c5_embed, Y.cu(E), Y.cu(idx), Y.cu(V))
+        dE = c_oracle.scatter_add_cols(V, idx, nt)  # dy == V (seed 1): the sequential fold
+        assert np.array_equal(U.bits(g[1].to_host()), U.bits(dE)), (rows, nt, ni, zipf)
+        assert g[2] is Y.NoTangent
+        assert np.array_equal(U.bits(g[3].to_host()), U.bits(c_oracle.gather_cols(E, idx)))  # dV = E[:, idx] exactly
+        ref = c_oracle.gather_dot(E, V, idx)
+        assert abs(val - ref) <= 1e-5 * abs(ref) + 1e-3
+
+
+def test_scatter_negative_zero_and_empty_destinations():
+    ctx = Y.context()
+    dy = np.asfortranarray(np.array([[-0.0, 1.0, -0.0], [-0.0, -1.0, 2.0]], F32))
+    idx = np.array([2, 4, 2], np.int64)
+    dx = Y.B200Array((2, 5))
+    ffi.check(ffi.lib().yota_scatter_add_cols(ctx.h, dx.ptr, 2, 5, Y.cu(dy).ptr, Y.cu(idx).ptr, 3))
+    got = dx.to_host()
+    assert np.array_equal(U.bits(got), U.bits(c_oracle.scatter_add_cols(dy, idx, 5)))
+    assert not np.signbit(got).any() or got[1, 3] == -1.0  # 0.0f + (-0.0f) = +0.0f; untouched columns are +0.0f
+
+
+def test_scatter_standalone_large_bit_exact():
+    r = cases.rng(9)
+    rows, nd, ns = 256, 1 << 14, 1 << 17
+    dy = r.standard_normal((rows, ns), dtype=F32)
+    idx = r.integers(1, nd + 1, size=ns).astype(np.int64)
+    ctx = Y.context()
+    dx = Y.B200Array((rows, nd))
+    ffi.check(ffi.lib().yota_scatter_add_cols(ctx.h, dx.ptr, rows, nd, Y.cu(dy).ptr, Y.cu(idx).ptr, ns))
+    assert np.array_equal(U.bits(dx.to_host()), U.bits(c_oracle.scatter_add_cols(dy, idx, nd)))
+
+
+def test_general_getindex_forms():  # test/test_helpers.jl:29-71 index forms, now value-checked
+    r = cases.rng(10)
+    x = r.random((3, 4)).astype(F32)
+    forms = [(jl.range_(1, 2), jl.range_(2, 3)), (1, jl.range_(2, 3)), (1, jl.colon), (1, [1, 3]), ([3, 1, 3], jl.colon)]
+    for I in forms:
+        U.check_parity(lambda a: jl.sum(a[I] * a[I]), [x])
+    U.check_parity(lambda a: a[1, 2] * a[5], [x])
+    x3 = r.random((4, 3, 5)).astype(F32)
+    U.check_parity(lambda a: jl.sum(a[jl.colon, 2, jl.colon] ** 2) + jl.sum(a[jl.colon, jl.colon, 5]), [x3])
+
+
+def test_deterministic_run_to_run():
+    a = [Y.cu(x) for x in cases.c3_args(3, 128, 200)]
+    f = cases.make_c3(3, 200)
+    r1 = Y.grad(f, *a)
+    r2 = Y.grad(f, *a)
+    assert r1[0] == r2[0]
+    for x, y in zip(r1[1][1:], r2[1][1:]):
+        assert np.array_equal(U.bits(x.to_host()), U.bits(y.to_host()))

@@ -1,0 +1,179 @@
+"""CPU tests of the host side: tape form (vs the worked tape in SURVEY §8(a)), the tape ->
+op-program lowering (checked against the oracle through a test-only NumPy interpreter of the
+op program), the planner (fusion decisions) and the C ABI surface.  No device work."""
+import ctypes as C
+import re
+
+import numpy as np
+import pytest
+
+import cases
+import ir_interp
+import yota_b200 as Y
+from oracle import yota_oracle as O
+from yota_b200 import ffi, ir, jl
+from yota_b200.grad import lower
+from yota_b200.tape import Call
+
+A = Y.AVal
+
+
+def _lowered_vs_oracle(f, args, seed=1, rtol=1e-11):
+    tape = Y.gradtape(f, *args, seed=seed)
+    L = lower(tape)
+    ins = [None] * L.prog.n_inputs
+    for a, s in zip(args, L.arg_slots):
+        ins[s] = a
+    for s, a in L.captured:
+        ins[s] = a
+    if L.seed_slot is not None:
+        ins[L.seed_slot] = np.asarray(seed, dtype=np.float64)
+    outs = ir_interp.run(L.prog, ins, seed=float(seed) if isinstance(seed, (int, float)) else 1.0, dtype=np.float64)
+    val, g = O.grad(f, *args, seed=seed, dtype=np.float64)
+    assert np.allclose(outs[L.val[1]], val, rtol=rtol)
+    for spec, gg in zip(L.grads, g[1:]):
+        if isinstance(spec, tuple):
+            assert outs[spec[1]].shape == np.shape(gg)
+            assert np.allclose(outs[spec[1]], gg, rtol=rtol, atol=1e-13)
+        else:
+            assert repr(spec) == repr(gg)
+    return L
+
+
+def test_tape_has_reference_form():
+    """sum(tanh.(W*x .+ b)) -- statement for statement the worked tape of SURVEY §8(a)."""
+    tape = Y.gradtape(cases.loss_tanh, A((4, 3)), A((4,)), A((3,)))
+    fns = [(op.fn if isinstance(op.fn, str) else "pb") for op in tape.ops if isinstance(op, Call)]
+    assert fns == ["rrule", "_getfield", "_getfield"] * 5 + ["pb", "getfield"] * 3 + ["pb", "getfield", "getfield"] * 2 \
+        + ["tuple", "map", "tuple"]
+    rr = [op.args[1:3] for op in tape.ops if isinstance(op, Call) and op.fn == "rrule"]
+    assert [a[0] if a[0] != "broadcasted" else a[1] for a in rr] == ["matmul", "add", "tanh", "materialize", "sum"]
+    # getfield indices count f as position 1 (src/grad.jl:176,182-186)
+    gf = [op.args[1] for op in tape.ops if isinstance(op, Call) and op.fn == "getfield"]
+    assert gf == [2, 2, 3, 3, 4, 2, 3]
+
+
+def test_accumulation_ops_on_tape():
+    """multipath: y used twice -> one broadcast(+, dx, old_dx) per extra use (src/grad.jl:91)."""
+    f = lambda x: jl.sum(jl.tanh(x) * x)  # noqa: E731
+    tape = Y.gradtape(f, A((3, 4)))
+    adds = [op for op in tape.ops if isinstance(op, Call) and op.fn == "broadcast"]
+    assert len(adds) == 1 and adds[0].args[0] == "+"
+
+
+@pytest.mark.parametrize("name,f,args", cases.gradcheck_cases(), ids=lambda v: v if isinstance(v, str) else "")
+def test_lowering_matches_oracle(name, f, args):
+    _lowered_vs_oracle(f, args)
+
+
+def test_lowering_configs_small():
+    f64 = lambda xs: [x.astype(np.float64) if x.dtype.kind == "f" else x for x in xs]  # noqa: E731
+    _lowered_vs_oracle(cases.c1_mlp, f64(cases.c1_args(6, 5, 3, 4)))
+    _lowered_vs_oracle(cases.c2_chain, f64(cases.c2_args(4, 5)))
+    _lowered_vs_oracle(cases.make_c3(3, 4), f64(cases.c3_args(3, 5, 4)))
+    L = _lowered_vs_oracle(cases.make_c4(3), f64(cases.c4_args(4, 3, 3)))
+    assert sum(o.opcode == ir.EW_ADD for o in L.prog.ops) >= 3 * 2  # accumulation adds survive lowering
+    L = _lowered_vs_oracle(cases.c5_embed, f64(cases.c5_args(3, 5, 8)))
+    assert L.grads[1] is Y.NoTangent  # index argument
+
+
+def test_lowering_seed_forms():
+    x = np.array([1.0, 2, 3])
+    _lowered_vs_oracle(lambda x: 2 * x, (x,), seed=np.ones(3))
+    _lowered_vs_oracle(lambda x: 2 * x, (x,), seed="auto")
+    _lowered_vs_oracle(cases.loss_tanh, (np.ones((4, 3)), np.ones(4), np.ones(3)), seed=2.5)
+    with pytest.raises(ValueError):
+        Y.gradtape(lambda x: 2 * x, A((3,)))
+
+
+def test_trivial_grads_need_no_device():
+    _, g = Y.grad(lambda x, y: x, 42.0, 54.0)
+    assert g == (Y.ZeroTangent, 1, Y.ZeroTangent)
+    _, g = Y.grad(lambda x: 1, 42.0)
+    assert g == (Y.ZeroTangent, Y.ZeroTangent)
+
+
+def test_no_rule_error():
+    with pytest.raises(Y.NoRuleError):
+        Y.gradtape(lambda x: jl.logsoftmax(x, dims=2), A((3, 4)))
+
+
+# ---- the C ABI -------------------------------------------------------------------------
+def test_library_exports_every_declared_symbol(built):
+    hdr = open(ffi.LIB_PATH.replace("yota.jl_b200/lib/libyota_cuda.so", "include/yota_cuda.h")).read()
+    declared = set(re.findall(r"\b(yota_[a-z0-9_]+)\s*\(", hdr)) - {"yota_ctx", "yota_program"}
+    assert declared == set(ffi.SYMBOLS), declared ^ set(ffi.SYMBOLS)
+    for name in declared:
+        assert getattr(built, name) is not None
+    assert built.yota_abi_version() == 1
+
+
+def _plan(f, *avals, flags=0, seed=1):
+    lib = ffi.lib()
+    ctx = C.c_void_p()
+    ffi.check(lib.yota_init(0, C.byref(ctx)))
+    L = lower(Y.gradtape(f, *avals, seed=seed))
+    ops, tens = ffi.pack_program(L.prog)
+    h = C.c_void_p()
+    ffi.check(lib.yota_program_build(ctx, ops, len(L.prog.ops), tens, len(L.prog.tensors), flags, C.byref(h)))
+    n = lib.yota_program_describe(h, None, 0)
+    buf = C.create_string_buffer(n + 1)
+    lib.yota_program_describe(h, buf, n + 1)
+    st = [C.c_int64() for _ in range(5)]
+    ffi.check(lib.yota_program_stats(h, *[C.byref(s) for s in st]))
+    lib.yota_program_destroy(h)
+    lib.yota_shutdown(ctx)
+    return buf.value.decode(), [s.value for s in st]
+
+
+def test_planner_fuses_c2_into_one_pass(built):
+    """C2 forward + pullback = ONE region: 2 full reads (x, W), 2 full writes (dx, dW), the
+    loss and db as fused sinks -- the 4-pass contract of SURVEY §8(d)."""
+    desc, (steps, launches, ws, regions, _) = _plan(cases.c2_chain, A((8192, 8192)), A((8192, 8192)), A((8192,)))
+    assert regions == 1 and steps == 3, desc
+    assert "+sum+sum" in desc and "scalar_finish" in desc and "rowsum_finish" in desc
+    assert ws < 16 << 20  # no 256 MiB temporaries
+    unf, (steps_u, *_rest) = _plan(cases.c2_chain, A((8192, 8192)), A((8192, 8192)), A((8192,)), flags=ffi.FLAG_NO_FUSE)
+    assert steps_u > 10
+
+
+def test_planner_never_materialises_pullback_temporaries(built):
+    desc, st = _plan(cases.make_c3(2, 64), *[A(a.shape) for a in cases.c3_args(2, 32, 64)])
+    assert "region[exp,mul,sub]+sum" in desc, desc  # exp.(logp) is recomputed inside the dz pass, not stored
+
+
+def test_build_rejects_unsupported_and_bad_programs(built):
+    lib = ffi.lib()
+    ctx = C.c_void_p()
+    ffi.check(lib.yota_init(0, C.byref(ctx)))
+    p = ir.IRProgram()
+    x = p.tensor((4, 4), kind=ir.T_INPUT, slot=0)
+    y = p.op(999, (x,), (4, 4))
+    p.mark_output(y, 0)
+    ops, tens = ffi.pack_program(p)
+    h = C.c_void_p()
+    rc = lib.yota_program_build(ctx, ops, len(p.ops), tens, len(p.tensors), 0, C.byref(h))
+    assert rc == -4 and b"no CPU fallback" in lib.yota_last_error()
+    p = ir.IRProgram()
+    a = p.tensor((4, 3), kind=ir.T_INPUT, slot=0)
+    b = p.tensor((5,), kind=ir.T_INPUT, slot=1)
+    p.mark_output(p.op(ir.EW_ADD, (a, b), (4, 3)), 0)
+    ops, tens = ffi.pack_program(p)
+    rc = lib.yota_program_build(ctx, ops, len(p.ops), tens, len(p.tensors), 0, C.byref(h))
+    assert rc == -3 and b"DimensionMismatch" in lib.yota_last_error()
+    lib.yota_shutdown(ctx)
+
+
+def test_compute_entry_fails_loudly_without_gpu(built):
+    import shutil
+
+    if shutil.which("nvidia-smi"):
+        pytest.skip("a GPU is present")
+    lib = ffi.lib()
+    ctx = C.c_void_p()
+    ffi.check(lib.yota_init(0, C.byref(ctx)))
+    p = C.c_void_p()
+    assert lib.yota_alloc(ctx, 1024, C.byref(p)) == -1
+    assert b"no CPU fallback" in lib.yota_last_error()
+    with pytest.raises(Y.YotaError):
+        Y.grad(cases.loss_tanh, np.ones((4, 3), np.float32), np.ones(4, np.float32), np.ones(3, np.float32))

@@ -1,0 +1,254 @@
+// C ABI: context, caller-owned device buffers, events, stand-alone operators.
+#include <stdarg.h>
+
+#include "common.h"
+
+namespace yota {
+
+static thread_local char g_err[1024] = "";
+thread_local int g_last_status = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int ctx_ensure_device(yota_ctx* ctx) {
+  if (ctx->device_ready) {
+    YOTA_CUDA(cudaSetDevice(ctx->device));
+    return YOTA_OK;
+  }
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    YOTA_FAIL(YOTA_E_CUDA, "no CUDA device available (%s): libyota_cuda has no CPU fallback",
+              e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  if (ctx->device >= n) YOTA_FAIL(YOTA_E_ARG, "device %d requested but only %d present", ctx->device, n);
+  YOTA_CUDA(cudaSetDevice(ctx->device));
+  cudaDeviceProp pr;
+  YOTA_CUDA(cudaGetDeviceProperties(&pr, ctx->device));
+  ctx->sm_count = pr.multiProcessorCount;
+  ctx->cc_major = pr.major;
+  ctx->cc_minor = pr.minor;
+  ctx->total_mem = pr.totalGlobalMem;
+  if (pr.major != 10)
+    YOTA_FAIL(YOTA_E_CUDA, "device %d is sm_%d%d; libyota_cuda is built for sm_100a (B200) only", ctx->device, pr.major,
+              pr.minor);
+  YOTA_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  YOTA_CUDA(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+  ctx->device_ready = true;
+  return YOTA_OK;
+}
+
+int ctx_scratch(yota_ctx* ctx, size_t bytes, void** out) {
+  if (ctx->scratch_bytes < bytes) {
+    if (ctx->scratch) {
+      YOTA_CUDA(cudaStreamSynchronize(ctx->stream));
+      cudaFree(ctx->scratch);
+      ctx->scratch = nullptr;
+      ctx->scratch_bytes = 0;
+    }
+    cudaError_t e = cudaMalloc(&ctx->scratch, bytes);
+    if (e != cudaSuccess) YOTA_FAIL(YOTA_E_NOMEM, "cannot allocate %zu bytes of scratch: %s", bytes, cudaGetErrorString(e));
+    ctx->scratch_bytes = bytes;
+  }
+  *out = ctx->scratch;
+  return YOTA_OK;
+}
+
+}  // namespace yota
+
+using namespace yota;
+
+extern "C" {
+
+int yota_abi_version(void) { return YOTA_ABI_VERSION; }
+const char* yota_last_error(void) { return g_err; }
+
+int yota_init(int device, yota_ctx** out) {
+  if (!out || device < 0) YOTA_FAIL(YOTA_E_ARG, "yota_init: bad arguments");
+  yota_ctx* c = new yota_ctx();
+  c->device = device;
+  // The device itself is attached on first use so that planning (yota_program_build /
+  // describe) also works on a host without a GPU; every compute entry fails loudly there.
+  *out = c;
+  return YOTA_OK;
+}
+
+int yota_shutdown(yota_ctx* ctx) {
+  if (!ctx) return YOTA_OK;
+  if (ctx->device_ready) {
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    yota_comm_destroy(ctx);
+    for (auto& kv : ctx->free_blocks) cudaFree(kv.second);
+    for (auto& kv : ctx->live_blocks) cudaFree(kv.first);
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->comm_stream);
+  }
+  delete ctx;
+  return YOTA_OK;
+}
+
+int yota_device_info(yota_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem) {
+  if (!ctx) YOTA_FAIL(YOTA_E_ARG, "null ctx");
+  YOTA_TRY(ctx_ensure_device(ctx));
+  if (sm_count) *sm_count = ctx->sm_count;
+  if (cc_major) *cc_major = ctx->cc_major;
+  if (cc_minor) *cc_minor = ctx->cc_minor;
+  if (total_mem) *total_mem = ctx->total_mem;
+  return YOTA_OK;
+}
+
+// Pooled allocation: grad() hands out fresh result arrays every call (Julia semantics), so
+// freed blocks are kept in exact-size buckets and reused without touching cudaMalloc.
+int yota_alloc(yota_ctx* ctx, size_t bytes, void** dptr) {
+  if (!ctx || !dptr) YOTA_FAIL(YOTA_E_ARG, "yota_alloc: bad arguments");
+  YOTA_TRY(ctx_ensure_device(ctx));
+  bytes = (bytes + 511) & ~(size_t)511;
+  if (bytes == 0) bytes = 512;
+  auto it = ctx->free_blocks.find(bytes);
+  if (it != ctx->free_blocks.end()) {
+    *dptr = it->second;
+    ctx->free_blocks.erase(it);
+  } else {
+    cudaError_t e = cudaMalloc(dptr, bytes);
+    if (e != cudaSuccess) {
+      // drop the cache and retry once
+      for (auto& kv : ctx->free_blocks) cudaFree(kv.second);
+      ctx->free_blocks.clear();
+      e = cudaMalloc(dptr, bytes);
+      if (e != cudaSuccess) YOTA_FAIL(YOTA_E_NOMEM, "yota_alloc(%zu bytes): %s", bytes, cudaGetErrorString(e));
+    }
+  }
+  ctx->live_blocks[*dptr] = bytes;
+  return YOTA_OK;
+}
+
+int yota_free(yota_ctx* ctx, void* dptr) {
+  if (!ctx || !dptr) return YOTA_OK;
+  auto it = ctx->live_blocks.find(dptr);
+  if (it == ctx->live_blocks.end()) YOTA_FAIL(YOTA_E_ARG, "yota_free: pointer was not allocated by yota_alloc");
+  // stream-ordered reuse: every consumer runs on ctx->stream, so a recycled block is only
+  // touched after the work already queued on it
+  ctx->free_blocks.insert({it->second, dptr});
+  ctx->live_blocks.erase(it);
+  return YOTA_OK;
+}
+
+int yota_h2d(yota_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (!ctx) YOTA_FAIL(YOTA_E_ARG, "null ctx");
+  YOTA_TRY(ctx_ensure_device(ctx));
+  YOTA_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  YOTA_CUDA(cudaStreamSynchronize(ctx->stream));
+  return YOTA_OK;
+}
+
+int yota_d2h(yota_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (!ctx) YOTA_FAIL(YOTA_E_ARG, "null ctx");
+  YOTA_TRY(ctx_ensure_device(ctx));
+  YOTA_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  YOTA_CUDA(cudaStreamSynchronize(ctx->stream));
+  return YOTA_OK;
+}
+
+int yota_host_alloc(yota_ctx* ctx, size_t bytes, void** hptr) {
+  if (!ctx || !hptr) YOTA_FAIL(YOTA_E_ARG, "yota_host_alloc: bad arguments");
+  YOTA_TRY(ctx_ensure_device(ctx));
+  YOTA_CUDA(cudaMallocHost(hptr, bytes ? bytes : 1));
+  return YOTA_OK;
+}
+
+int yota_host_free(yota_ctx* ctx, void* hptr) {
+  if (!ctx) YOTA_FAIL(YOTA_E_ARG, "null ctx");
+  if (hptr) YOTA_CUDA(cudaFreeHost(hptr));
+  return YOTA_OK;
+}
+
+int yota_h2d_async(yota_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (!ctx) YOTA_FAIL(YOTA_E_ARG, "null ctx");
+  YOTA_TRY(ctx_ensure_device(ctx));
+  YOTA_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return YOTA_OK;
+}
+
+int yota_memset(yota_ctx* ctx, void* dptr, int byte, size_t bytes) {
+  if (!ctx) YOTA_FAIL(YOTA_E_ARG, "null ctx");
+  YOTA_TRY(ctx_ensure_device(ctx));
+  YOTA_CUDA(cudaMemsetAsync(dptr, byte, bytes, ctx->stream));
+  return YOTA_OK;
+}
+
+int yota_sync(yota_ctx* ctx) {
+  if (!ctx) YOTA_FAIL(YOTA_E_ARG, "null ctx");
+  YOTA_TRY(ctx_ensure_device(ctx));
+  YOTA_CUDA(cudaStreamSynchronize(ctx->stream));
+  YOTA_CUDA(cudaStreamSynchronize(ctx->comm_stream));
+  return YOTA_OK;
+}
+
+int yota_event_create(yota_ctx* ctx, void** ev) {
+  if (!ctx || !ev) YOTA_FAIL(YOTA_E_ARG, "bad arguments");
+  YOTA_TRY(ctx_ensure_device(ctx));
+  cudaEvent_t e;
+  YOTA_CUDA(cudaEventCreate(&e));
+  *ev = e;
+  return YOTA_OK;
+}
+int yota_event_record(yota_ctx* ctx, void* ev) {
+  YOTA_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ev), ctx->stream));
+  return YOTA_OK;
+}
+int yota_event_elapsed_ms(yota_ctx* ctx, void* a, void* b, float* ms) {
+  (void)ctx;
+  YOTA_CUDA(cudaEventSynchronize(static_cast<cudaEvent_t>(b)));
+  YOTA_CUDA(cudaEventElapsedTime(ms, static_cast<cudaEvent_t>(a), static_cast<cudaEvent_t>(b)));
+  return YOTA_OK;
+}
+int yota_event_destroy(yota_ctx* ctx, void* ev) {
+  (void)ctx;
+  if (ev) YOTA_CUDA(cudaEventDestroy(static_cast<cudaEvent_t>(ev)));
+  return YOTA_OK;
+}
+
+int yota_gemm(yota_ctx* ctx, int mode, int transA, int transB, int64_t m, int64_t n, int64_t k, const float* A,
+              int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int accumulate) {
+  if (!ctx) YOTA_FAIL(YOTA_E_ARG, "null ctx");
+  YOTA_TRY(ctx_ensure_device(ctx));
+  GemmArgs g{mode, transA, transB, m, n, k, A, lda, B, ldb, C, ldc, accumulate};
+  if (mode != 0) {
+    if (!gemm_tc_eligible(g))
+      YOTA_FAIL(YOTA_E_UNSUPPORTED_OP, "yota_gemm: shape %lldx%lldx%lld is not eligible for the tensor-core kernel",
+                (long long)m, (long long)n, (long long)k);
+    return launch_gemm_tc(ctx, g, ctx->stream);
+  }
+  return launch_gemm_ffma(g, ctx->stream);
+}
+
+int yota_scatter_add_cols(yota_ctx* ctx, float* dx, int64_t rows, int64_t n_dst, const float* dy, const int64_t* idx,
+                          int64_t n_src) {
+  if (!ctx) YOTA_FAIL(YOTA_E_ARG, "null ctx");
+  YOTA_TRY(ctx_ensure_device(ctx));
+  const size_t ws = scatter_cols_workspace_bytes(n_dst, n_src);
+  void* w = nullptr;
+  YOTA_TRY(ctx_scratch(ctx, ws, &w));
+  return launch_scatter_add_cols(dx, rows, n_dst, dy, idx, n_src, w, ws, ctx->stream);
+}
+
+int yota_gather_cols(yota_ctx* ctx, float* y, const float* x, int64_t rows, int64_t n_dst, const int64_t* idx,
+                     int64_t n_src) {
+  if (!ctx) YOTA_FAIL(YOTA_E_ARG, "null ctx");
+  YOTA_TRY(ctx_ensure_device(ctx));
+  return launch_gather_cols(y, x, rows, n_dst, idx, n_src, ctx->stream);
+}
+
+int yota_update_sgd(yota_ctx* ctx, float* x, const float* gx, int64_t n, float lr) {
+  if (!ctx) YOTA_FAIL(YOTA_E_ARG, "null ctx");
+  YOTA_TRY(ctx_ensure_device(ctx));
+  return launch_axpy(x, gx, n, lr, ctx->stream);
+}
+
+}  // extern "C"

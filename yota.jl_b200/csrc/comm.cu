@@ -1,0 +1,120 @@
+// Multi-GPU: batch-sharded data parallelism.  The tape is replicated, each GPU runs its
+// column shard of the batch, and parameter gradients are summed with ncclAllReduce over
+// NVLink 5 / NVSwitch on a dedicated stream while the pullback sweep continues (program.cu).
+// The reference has no multi-device code at all.
+// NCCL is loaded with dlopen so the library also loads where NCCL is absent; any
+// communication entry then fails loudly.
+#include <dlfcn.h>
+
+#include "common.h"
+
+namespace yota {
+
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclFloat32 = 7, ncclSum = 0 };
+
+struct NcclApi {
+  void* h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static NcclApi g_nccl;
+
+static int nccl_load() {
+  if (g_nccl.h) return YOTA_OK;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    g_nccl.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.h) break;
+  }
+  if (!g_nccl.h) YOTA_FAIL(YOTA_E_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+#define SYM(field, name)                                                         \
+  *(void**)(&g_nccl.field) = dlsym(g_nccl.h, name);                              \
+  if (!g_nccl.field) YOTA_FAIL(YOTA_E_NCCL, "libnccl is missing symbol %s", name)
+  SYM(GetUniqueId, "ncclGetUniqueId");
+  SYM(CommInitRank, "ncclCommInitRank");
+  SYM(CommDestroy, "ncclCommDestroy");
+  SYM(AllReduce, "ncclAllReduce");
+  SYM(GroupStart, "ncclGroupStart");
+  SYM(GroupEnd, "ncclGroupEnd");
+  SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+  return YOTA_OK;
+}
+
+#define YOTA_NCCL(expr)                                                                            \
+  do {                                                                                             \
+    ncclResult_t _r = (expr);                                                                      \
+    if (_r != 0) YOTA_FAIL(YOTA_E_NCCL, "NCCL error at %s:%d: %s", __FILE__, __LINE__, g_nccl.GetErrorString(_r)); \
+  } while (0)
+
+int comm_allreduce(yota_ctx* ctx, float* buf, long long n, cudaStream_t s) {
+  if (!ctx->nccl_comm) YOTA_FAIL(YOTA_E_NCCL, "yota_comm_init has not been called");
+  if (n == 0) return YOTA_OK;
+  YOTA_NCCL(g_nccl.AllReduce(buf, buf, (size_t)n, ncclFloat32, ncclSum, (ncclComm_t)ctx->nccl_comm, s));
+  return YOTA_OK;
+}
+int comm_group_start(yota_ctx* ctx) {
+  (void)ctx;
+  YOTA_TRY(nccl_load());
+  YOTA_NCCL(g_nccl.GroupStart());
+  return YOTA_OK;
+}
+int comm_group_end(yota_ctx* ctx) {
+  (void)ctx;
+  YOTA_NCCL(g_nccl.GroupEnd());
+  return YOTA_OK;
+}
+
+}  // namespace yota
+
+using namespace yota;
+
+extern "C" {
+
+int yota_comm_unique_id(void* id128) {
+  if (!id128) YOTA_FAIL(YOTA_E_ARG, "null id buffer");
+  YOTA_TRY(nccl_load());
+  ncclUniqueId id;
+  YOTA_NCCL(g_nccl.GetUniqueId(&id));
+  memcpy(id128, &id, sizeof(id));
+  return YOTA_OK;
+}
+
+int yota_comm_init(yota_ctx* ctx, int rank, int nranks, const void* id128) {
+  if (!ctx || !id128 || rank < 0 || rank >= nranks) YOTA_FAIL(YOTA_E_ARG, "yota_comm_init: bad arguments");
+  YOTA_TRY(ctx_ensure_device(ctx));
+  YOTA_TRY(nccl_load());
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  ncclComm_t comm;
+  YOTA_NCCL(g_nccl.CommInitRank(&comm, nranks, id, rank));
+  ctx->nccl_comm = comm;
+  ctx->rank = rank;
+  ctx->nranks = nranks;
+  return YOTA_OK;
+}
+
+int yota_comm_destroy(yota_ctx* ctx) {
+  if (ctx && ctx->nccl_comm) {
+    g_nccl.CommDestroy((ncclComm_t)ctx->nccl_comm);
+    ctx->nccl_comm = nullptr;
+  }
+  return YOTA_OK;
+}
+
+int yota_allreduce_f32(yota_ctx* ctx, float* buf, int64_t n) {
+  if (!ctx) YOTA_FAIL(YOTA_E_ARG, "null ctx");
+  YOTA_TRY(ctx_ensure_device(ctx));
+  return comm_allreduce(ctx, buf, n, ctx->stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,194 @@
+// Internal declarations shared by the translation units of libyota_cuda.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/yota_cuda.h"
+
+namespace yota {
+
+void set_error(const char* fmt, ...);
+extern thread_local int g_last_status;
+
+#define YOTA_FAIL(code, ...)            \
+  do {                                  \
+    ::yota::set_error(__VA_ARGS__);     \
+    return (code);                      \
+  } while (0)
+
+#define YOTA_CUDA(expr)                                                                   \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      ::yota::set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__,     \
+                        __LINE__, cudaGetErrorString(_e));                                \
+      return YOTA_E_CUDA;                                                                 \
+    }                                                                                     \
+  } while (0)
+
+#define YOTA_TRY(expr)            \
+  do {                            \
+    int _s = (expr);              \
+    if (_s != YOTA_OK) return _s; \
+  } while (0)
+
+struct NcclApi;  // comm.cu
+
+}  // namespace yota
+
+struct yota_ctx {
+  int device = 0;
+  int sm_count = 148;
+  int cc_major = 0, cc_minor = 0;
+  size_t total_mem = 0;
+  bool device_ready = false;  // lazily initialised so that plan-only use works without a GPU
+  cudaStream_t stream = nullptr;
+  cudaStream_t comm_stream = nullptr;
+  // size-bucketed free lists (caller-owned buffers come and go every grad() call)
+  std::multimap<size_t, void*> free_blocks;
+  std::map<void*, size_t> live_blocks;
+  // NCCL
+  void* nccl_comm = nullptr;
+  int rank = 0, nranks = 1;
+  // scratch for standalone ops
+  void* scratch = nullptr;
+  size_t scratch_bytes = 0;
+};
+
+namespace yota {
+
+int ctx_ensure_device(yota_ctx* ctx);
+int ctx_scratch(yota_ctx* ctx, size_t bytes, void** out);
+
+// ---- elementwise region (ew_kernels.cu) ------------------------------------------------
+enum : int { CLS_FULL = 0, CLS_ROWVEC = 1, CLS_COLVEC = 2, CLS_SCALAR = 3 };
+enum : int { OUT_STORE = 0, OUT_ROWSUM = 1, OUT_SCALARSUM = 2 };
+constexpr int RG_MAX_IN = 12;
+constexpr int RG_MAX_OUT = 12;
+constexpr int RG_MAX_OPS = 64;
+constexpr int RG_MAX_SLOTS = 28;
+constexpr int RG_THREADS = 256;
+constexpr uint8_t RG_ACC = 0xFF;   // operand: the previous micro-op's result
+constexpr uint8_t RG_NONE = 0xFF;  // dst: keep only in the accumulator register
+
+struct RegionIn {
+  const float* ptr;
+  int cls;
+  int slot;
+};
+struct RegionOut {
+  float* ptr;  // STORE: destination; ROWSUM / SCALARSUM: partials workspace
+  int kind;
+  int src;  // slot holding the value
+  int acc;  // slot used as accumulator (sums)
+  int _pad;
+};
+struct MicroOp {
+  uint8_t op, dst, a, b;
+  float imm;
+};
+struct RegionParams {
+  long long R, C;
+  int TRG, TCC, rowblocks, colchunks;
+  long long cols_per_chunk;
+  int n_in, n_out, n_ops, n_slots;
+  RegionIn in[RG_MAX_IN];
+  RegionOut out[RG_MAX_OUT];
+  MicroOp ops[RG_MAX_OPS];
+};
+
+struct RegionLaunch {
+  RegionParams p;
+  int V;        // 4 or 1
+  int grid;
+  size_t smem;
+  int static_id;  // >= 0: precompiled chain kernel
+};
+
+// geometry from (R, C, V): fills TRG, TCC, rowblocks, colchunks, cols_per_chunk, grid
+void region_geometry(RegionLaunch& L, int sm_count);
+int launch_region(const RegionLaunch& L, cudaStream_t s);
+// out[r] = scale * sum_p partial[p*R + r], p ascending (deterministic)
+int launch_rowsum_finish(float* out, const float* partial, long long R, int P, float scale, cudaStream_t s);
+// out[0] = scale * tree(partial[0..n))
+int launch_scalar_finish(float* out, const float* partial, int n, float scale, cudaStream_t s);
+// out[c] = scale * sum_r x[r + c*R]
+int launch_colsum(float* out, const float* x, long long R, long long C, float scale, cudaStream_t s);
+
+// generic N-d fallbacks (any broadcast pattern / any reduced-dims mask)
+struct GenericEw {
+  int opcode;
+  int nd;
+  long long dims[4];        // output dims
+  long long sa[4], sb[4];   // element strides of the operands (0 = broadcast)
+  float imm;
+};
+int launch_generic_ew(const GenericEw& g, float* out, const float* a, const float* b, cudaStream_t s);
+struct GenericSum {
+  int nd;
+  long long dims[4];
+  unsigned mask;
+  float scale;
+};
+int launch_generic_sum(const GenericSum& g, float* out, const float* x, cudaStream_t s);
+int launch_fill_const(float* out, float v, cudaStream_t s);
+
+// static (precompiled) chain registry
+int static_chain_lookup(const RegionParams& p, int V);
+const char* static_chain_name(int id);
+
+// ---- GEMM (gemm_ffma.cu / gemm_tc.cu) ---------------------------------------------------
+struct GemmArgs {
+  int mode;  // 0 fp32 ffma, 1 tf32 tcgen05, 2 bf16 tcgen05
+  int transA, transB;
+  long long M, N, K;
+  const float* A;
+  long long lda;
+  const float* B;
+  long long ldb;
+  float* C;
+  long long ldc;
+  int accumulate;
+};
+int launch_gemm_ffma(const GemmArgs& g, cudaStream_t s);
+int launch_gemm_tc(yota_ctx* ctx, const GemmArgs& g, cudaStream_t s);  // returns YOTA_E_UNSUPPORTED_OP if shape not eligible
+bool gemm_tc_eligible(const GemmArgs& g);
+
+// ---- indexing (index_kernels.cu) --------------------------------------------------------
+struct IndexSpec {
+  int n;                 // number of indices
+  int kind[4];
+  long long a[4], b[4];
+  const int64_t* vec[4];  // device pointer for IDX_VEC
+  long long vlen[4];
+  int nd_x;
+  long long xdims[4];     // dims of x as indexed (flattened when n == 1)
+};
+int launch_getindex(const IndexSpec& sp, float* y, const float* x, long long n_out, cudaStream_t s);
+size_t ungetindex_workspace_bytes(const IndexSpec& sp);
+int launch_ungetindex(const IndexSpec& sp, float* dx, const float* dy, void* workspace, size_t ws_bytes,
+                      int sm_count, cudaStream_t s);
+size_t scatter_cols_workspace_bytes(long long n_dst, long long n_src);
+int launch_scatter_add_cols(float* dx, long long rows, long long n_dst, const float* dy, const int64_t* idx,
+                            long long n_src, void* workspace, size_t ws_bytes, cudaStream_t s);
+int launch_gather_cols(float* y, const float* x, long long rows, long long n_dst, const int64_t* idx,
+                       long long n_src, cudaStream_t s);
+
+// ---- misc kernels (misc_kernels.cu) -----------------------------------------------------
+int launch_logsoftmax(float* y, const float* x, long long R, long long C, cudaStream_t s);
+int launch_transpose(float* y, const float* x, long long R, long long C, cudaStream_t s);
+int launch_copy_strided(float* dst, const float* src, int nd, const long long* dims, const long long* dst_stride,
+                        const long long* src_stride, cudaStream_t s);
+int launch_axpy(float* x, const float* g, long long n, float lr, cudaStream_t s);
+
+// ---- NCCL (comm.cu) ---------------------------------------------------------------------
+int comm_allreduce(yota_ctx* ctx, float* buf, long long n, cudaStream_t s);
+int comm_group_start(yota_ctx* ctx);
+int comm_group_end(yota_ctx* ctx);
+
+}  // namespace yota

@@ -1,0 +1,164 @@
+// Strict-FP32 GEMM (FFMA pipe): the exactness variant of the matmul rrule
+// (ChainRules rrule(*, A, B): C = A*B, dA = Ȳ*B', dB = A'*Ȳ -- dispatched at
+// /root/reference/src/grad.jl:147 and forced by map(unthunk, .) at src/grad.jl:235;
+// SURVEY.md §8(a) row 10).  Column-major operands, any of NN / NT / TN / TT through element
+// strides, optional accumulate (C += ...) which absorbs the tape's broadcast(+, dW, old)
+// (src/grad.jl:91).  128x128x16 CTA tile, 8x8 register tile per thread, double-buffered
+// shared memory.  Deterministic: fixed k order per output element.
+#include "common.h"
+
+namespace yota {
+
+constexpr int BM = 128, BN = 128, BK = 16, GT = 256;
+
+// AM: A is contiguous along m (non-transposed column-major); else contiguous along k.
+// BNc: B is contiguous along n (transposed B); else contiguous along k (non-transposed).
+template <bool AM, bool BNc>
+__global__ void __launch_bounds__(GT) gemm_ffma_kernel(long long M, long long N, long long K,
+                                                        const float* __restrict__ A, long long sam, long long sak,
+                                                        const float* __restrict__ B, long long sbk, long long sbn,
+                                                        float* __restrict__ C, long long ldc, int accumulate) {
+  __shared__ __align__(16) float As[2][BK][BM + 4];
+  __shared__ __align__(16) float Bs[2][BK][BN + 4];
+  const int t = threadIdx.x;
+  const long long m0 = (long long)blockIdx.x * BM, n0 = (long long)blockIdx.y * BN;
+  const int tx = t & 15, ty = t >> 4;
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[i][j] = 0.f;
+
+  float ra[8], rb[8];
+  auto load_tile = [&](long long k0) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      int m, k;
+      if (AM) {
+        m = t & 127;
+        k = (t >> 7) + 2 * i;
+      } else {
+        k = t & 15;
+        m = (t >> 4) + 16 * i;
+      }
+      const long long gm = m0 + m, gk = k0 + k;
+      ra[i] = (gm < M && gk < K) ? __ldg(A + gm * sam + gk * sak) : 0.f;
+      int n, kb;
+      if (BNc) {
+        n = t & 127;
+        kb = (t >> 7) + 2 * i;
+      } else {
+        kb = t & 15;
+        n = (t >> 4) + 16 * i;
+      }
+      const long long gn = n0 + n, gkb = k0 + kb;
+      rb[i] = (gn < N && gkb < K) ? __ldg(B + gkb * sbk + gn * sbn) : 0.f;
+    }
+  };
+  auto store_tile = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      int m, k;
+      if (AM) {
+        m = t & 127;
+        k = (t >> 7) + 2 * i;
+      } else {
+        k = t & 15;
+        m = (t >> 4) + 16 * i;
+      }
+      As[buf][k][m] = ra[i];
+      int n, kb;
+      if (BNc) {
+        n = t & 127;
+        kb = (t >> 7) + 2 * i;
+      } else {
+        kb = t & 15;
+        n = (t >> 4) + 16 * i;
+      }
+      Bs[buf][kb][n] = rb[i];
+    }
+  };
+
+  const long long nk = (K + BK - 1) / BK;
+  load_tile(0);
+  store_tile(0);
+  __syncthreads();
+  for (long long kt = 0; kt < nk; kt++) {
+    const int buf = (int)(kt & 1);
+    if (kt + 1 < nk) load_tile((kt + 1) * BK);
+#pragma unroll
+    for (int k = 0; k < BK; k++) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][tx * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + tx * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][ty * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + ty * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) {
+      store_tile(buf ^ 1);
+      __syncthreads();
+    }
+  }
+
+  // epilogue: thread owns rows {tx*4..+3, 64+tx*4..+3} x cols {ty*4..+3, 64+ty*4..+3}
+  const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+#pragma unroll
+  for (int jh = 0; jh < 2; jh++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const long long n = n0 + jh * 64 + ty * 4 + j;
+      if (n >= N) continue;
+#pragma unroll
+      for (int ih = 0; ih < 2; ih++) {
+        const long long m = m0 + ih * 64 + tx * 4;
+        float* dst = C + m + n * ldc;
+        float v[4] = {acc[ih * 4 + 0][jh * 4 + j], acc[ih * 4 + 1][jh * 4 + j], acc[ih * 4 + 2][jh * 4 + j],
+                      acc[ih * 4 + 3][jh * 4 + j]};
+        if (vec_ok && m + 3 < M) {
+          if (accumulate) {
+            const float4 o = *reinterpret_cast<const float4*>(dst);
+            v[0] += o.x;
+            v[1] += o.y;
+            v[2] += o.z;
+            v[3] += o.w;
+          }
+          *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; q++)
+            if (m + q < M) dst[q] = accumulate ? dst[q] + v[q] : v[q];
+        }
+      }
+    }
+}
+
+int launch_gemm_ffma(const GemmArgs& g, cudaStream_t s) {
+  if (g.M <= 0 || g.N <= 0) return YOTA_OK;
+  // element strides: op(A)(m,k), op(B)(k,n)
+  const long long sam = g.transA ? g.lda : 1, sak = g.transA ? 1 : g.lda;
+  const long long sbk = g.transB ? g.ldb : 1, sbn = g.transB ? 1 : g.ldb;
+  dim3 grid((unsigned)((g.M + BM - 1) / BM), (unsigned)((g.N + BN - 1) / BN));
+  if (grid.y > 65535) YOTA_FAIL(YOTA_E_SHAPE, "gemm: N too large for the FFMA kernel grid");
+  const bool AM = !g.transA, BNc = g.transB != 0;
+#define LAUNCH(a, b) \
+  gemm_ffma_kernel<a, b><<<grid, GT, 0, s>>>(g.M, g.N, g.K, g.A, sam, sak, g.B, sbk, sbn, g.C, g.ldc, g.accumulate)
+  if (AM && BNc)
+    LAUNCH(true, true);
+  else if (AM && !BNc)
+    LAUNCH(true, false);
+  else if (!AM && BNc)
+    LAUNCH(false, true);
+  else
+    LAUNCH(false, false);
+#undef LAUNCH
+  YOTA_CUDA(cudaGetLastError());
+  return YOTA_OK;
+}
+
+}  // namespace yota

@@ -1,0 +1,602 @@
+// getindex (gather) and its pullback: a DETERMINISTIC, bit-exact scatter-add.
+//
+// Reference semantics: ungetindex! ->
+// NNlib.scatter!(+, dx, dy, idx) at /root/reference/src/helpers.jl:7-11 and ChainRules'
+// ∇getindex! both run   dx = zero(x); for k in eachindex(dy) (column-major): dx[I_k] += dy[k]
+// i.e. per destination a LEFT FOLD IN SOURCE ORDER starting from +0.0f.  Atomics (what
+// NNlibCUDA does) or tree reductions change the rounding, so instead:
+//   1. stable LSD radix sort of (destination, source position) pairs  -> per destination the
+//      source positions in increasing order (warp match-any multi-split, no atomics on data)
+//   2. segment starts per destination
+//   3. one thread per destination ELEMENT folds its contributions sequentially and writes the
+//      element exactly once (so dx needs no memset and every byte of dx is written once).
+// HBM traffic for dx[:, idx] += dy: read dy once (full 128-byte lines per gathered column),
+// read idx, write dx once -- the algorithmic minimum of SURVEY §8(d) C5.
+#include "common.h"
+
+namespace yota {
+
+// ------------------------------------------------------------------------------------------
+// gather
+// ------------------------------------------------------------------------------------------
+__global__ void gather_cols_v4_kernel(float4* __restrict__ y, const float4* __restrict__ x, int R4, long long n_dst,
+                                      const int64_t* __restrict__ idx, long long n_src) {
+  const long long total = n_src * R4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long k = i / R4;
+    const int r = (int)(i - k * R4);
+    long long j = __ldg(idx + k) - 1;
+    j = j < 0 ? 0 : (j >= n_dst ? n_dst - 1 : j);
+    y[i] = __ldg(x + j * R4 + r);
+  }
+}
+__global__ void gather_cols_v1_kernel(float* __restrict__ y, const float* __restrict__ x, long long R, long long n_dst,
+                                      const int64_t* __restrict__ idx, long long n_src) {
+  const long long total = n_src * R;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long k = i / R;
+    const long long r = i - k * R;
+    long long j = __ldg(idx + k) - 1;
+    j = j < 0 ? 0 : (j >= n_dst ? n_dst - 1 : j);
+    y[i] = __ldg(x + j * R + r);
+  }
+}
+
+static unsigned grid_for(long long total, int threads, int cap_blocks = 148 * 16) {
+  long long b = (total + threads - 1) / threads;
+  if (b > cap_blocks) b = cap_blocks;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+int launch_gather_cols(float* y, const float* x, long long rows, long long n_dst, const int64_t* idx, long long n_src,
+                       cudaStream_t s) {
+  if (rows * n_src == 0) return YOTA_OK;
+  const bool v4 = (rows % 4 == 0) && ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(x)) % 16 == 0);
+  if (v4)
+    gather_cols_v4_kernel<<<grid_for(n_src * (rows / 4), 256), 256, 0, s>>>(
+        reinterpret_cast<float4*>(y), reinterpret_cast<const float4*>(x), (int)(rows / 4), n_dst, idx, n_src);
+  else
+    gather_cols_v1_kernel<<<grid_for(n_src * rows, 256), 256, 0, s>>>(y, x, rows, n_dst, idx, n_src);
+  YOTA_CUDA(cudaGetLastError());
+  return YOTA_OK;
+}
+
+struct GetIdxParams {
+  int n;  // number of indices
+  int kind[4];
+  long long a[4];
+  const int64_t* vec[4];
+  long long xdim[4];     // extent of x along index d
+  long long xstride[4];  // element stride of x along index d
+  long long odim[4];     // extent of the (unsqueezed) output along index d (1 for INT)
+};
+
+__global__ void getindex_generic_kernel(GetIdxParams p, float* __restrict__ y, const float* __restrict__ x,
+                                        long long n_out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_out;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long rem = i, off = 0;
+#pragma unroll
+    for (int d = 0; d < 4; d++) {
+      if (d < p.n) {
+        const long long c = rem % p.odim[d];
+        rem /= p.odim[d];
+        long long xi;
+        if (p.kind[d] == YOTA_IDX_COLON)
+          xi = c;
+        else if (p.kind[d] == YOTA_IDX_VEC) {
+          xi = __ldg(p.vec[d] + c) - 1;
+          xi = xi < 0 ? 0 : (xi >= p.xdim[d] ? p.xdim[d] - 1 : xi);
+        } else
+          xi = p.a[d] - 1 + c;  // INT (c == 0) or RANGE
+        off += xi * p.xstride[d];
+      }
+    }
+    y[i] = __ldg(x + off);
+  }
+}
+
+static void fill_getidx(const IndexSpec& sp, GetIdxParams& p) {
+  p.n = sp.n;
+  long long st = 1;
+  for (int d = 0; d < 4; d++) {
+    p.kind[d] = 0;
+    p.a[d] = 0;
+    p.vec[d] = nullptr;
+    p.xdim[d] = p.odim[d] = 1;
+    p.xstride[d] = 0;
+  }
+  for (int d = 0; d < sp.n; d++) {
+    p.kind[d] = sp.kind[d];
+    p.a[d] = sp.a[d];
+    p.vec[d] = sp.vec[d];
+    p.xdim[d] = sp.xdims[d];
+    p.xstride[d] = st;
+    st *= sp.xdims[d];
+    switch (sp.kind[d]) {
+      case YOTA_IDX_COLON: p.odim[d] = sp.xdims[d]; break;
+      case YOTA_IDX_INT: p.odim[d] = 1; break;
+      case YOTA_IDX_RANGE: p.odim[d] = sp.b[d] - sp.a[d] + 1; break;
+      default: p.odim[d] = sp.vlen[d]; break;
+    }
+  }
+}
+
+int launch_getindex(const IndexSpec& sp, float* y, const float* x, long long n_out, cudaStream_t s) {
+  if (n_out == 0) return YOTA_OK;
+  // fast path: x[:, idx] on a matrix
+  if (sp.n == 2 && sp.kind[0] == YOTA_IDX_COLON && sp.kind[1] == YOTA_IDX_VEC)
+    return launch_gather_cols(y, x, sp.xdims[0], sp.xdims[1], sp.vec[1], sp.vlen[1], s);
+  GetIdxParams p;
+  fill_getidx(sp, p);
+  getindex_generic_kernel<<<grid_for(n_out, 256), 256, 0, s>>>(p, y, x, n_out);
+  YOTA_CUDA(cudaGetLastError());
+  return YOTA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// exclusive scan of u32 (in place), any length; deterministic
+// ------------------------------------------------------------------------------------------
+constexpr int SCAN_T = 256, SCAN_ITEMS = 8, SCAN_TILE = SCAN_T * SCAN_ITEMS;
+
+__device__ __forceinline__ unsigned block_excl_scan_u32(unsigned v, unsigned* total, unsigned* sm /*>=8*/) {
+  // exclusive scan of one value per thread across a 256-thread block
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  unsigned inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) sm[w] = inc;
+  __syncthreads();
+  unsigned wbase = 0, tot = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_T / 32; i++) {
+    const unsigned t = sm[i];
+    if (i < w) wbase += t;
+    tot += t;
+  }
+  __syncthreads();
+  *total = tot;
+  return wbase + inc - v;
+}
+
+__global__ void __launch_bounds__(SCAN_T) scan_tile_kernel(unsigned* __restrict__ data, long long n,
+                                                           unsigned* __restrict__ bsum) {
+  __shared__ unsigned sm[8];
+  const long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
+  unsigned v[SCAN_ITEMS], t = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++) {
+    v[i] = (base + i < n) ? data[base + i] : 0u;
+    t += v[i];
+  }
+  unsigned total;
+  unsigned ex = block_excl_scan_u32(t, &total, sm);
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++) {
+    if (base + i < n) data[base + i] = ex;
+    ex += v[i];
+  }
+  if (bsum && threadIdx.x == 0) bsum[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(SCAN_T) scan_add_kernel(unsigned* __restrict__ data, long long n,
+                                                          const unsigned* __restrict__ bsum) {
+  const unsigned add = bsum[blockIdx.x];
+  const long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++)
+    if (base + i < n) data[base + i] += add;
+}
+
+static size_t scan_ws_elems(long long n) {
+  size_t tot = 0;
+  while (n > SCAN_TILE) {
+    n = (n + SCAN_TILE - 1) / SCAN_TILE;
+    tot += (size_t)n;
+  }
+  return tot + 1;
+}
+
+static int exclusive_scan_u32(unsigned* data, long long n, unsigned* ws, cudaStream_t s) {
+  if (n <= 0) return YOTA_OK;
+  const long long nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+  if (nb == 1) {
+    scan_tile_kernel<<<1, SCAN_T, 0, s>>>(data, n, nullptr);
+    YOTA_CUDA(cudaGetLastError());
+    return YOTA_OK;
+  }
+  scan_tile_kernel<<<(unsigned)nb, SCAN_T, 0, s>>>(data, n, ws);
+  YOTA_CUDA(cudaGetLastError());
+  YOTA_TRY(exclusive_scan_u32(ws, nb, ws + nb, s));
+  scan_add_kernel<<<(unsigned)nb, SCAN_T, 0, s>>>(data, n, ws);
+  YOTA_CUDA(cudaGetLastError());
+  return YOTA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// stable LSD radix sort of (key = destination, value = source position)
+// ------------------------------------------------------------------------------------------
+constexpr int RS_T = 256, RS_WARPS = 8, RS_ROUNDS = 16, RS_TILE = RS_T * RS_ROUNDS;  // 4096 keys per CTA
+
+__global__ void keys_from_idx_kernel(unsigned* __restrict__ keys, unsigned* __restrict__ vals,
+                                     const int64_t* __restrict__ idx, long long n, long long n_dst) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    long long j = __ldg(idx + i) - 1;
+    // out-of-range indices (a BoundsError in Julia) go to an overflow bucket that is never read
+    keys[i] = (j < 0 || j >= n_dst) ? (unsigned)n_dst : (unsigned)j;
+    vals[i] = (unsigned)i;
+  }
+}
+
+template <int BITS>
+__global__ void __launch_bounds__(RS_T) radix_hist_kernel(const unsigned* __restrict__ keys, long long n, int shift,
+                                                          unsigned* __restrict__ hist, int nblocks) {
+  constexpr int ND = 1 << BITS;
+  extern __shared__ unsigned sh[];  // ND
+  for (int i = threadIdx.x; i < ND; i += RS_T) sh[i] = 0;
+  __syncthreads();
+  const long long base = (long long)blockIdx.x * RS_TILE;
+  for (int r = 0; r < RS_ROUNDS; r++) {
+    const long long i = base + r * RS_T + threadIdx.x;
+    if (i < n) atomicAdd(&sh[(keys[i] >> shift) & (ND - 1)], 1u);  // integer counts: order-independent
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < ND; i += RS_T) hist[(long long)i * nblocks + blockIdx.x] = sh[i];
+}
+
+// Each warp owns a contiguous 512-key segment of the CTA's tile and walks it in order, 32
+// keys at a time; match-any gives the rank among equal digits inside a round.  Position =
+// global digit base (scan of hist) + earlier warps' count + this warp's running count + rank
+// => a stable split.
+template <int BITS>
+__global__ void __launch_bounds__(RS_T) radix_scatter_kernel(const unsigned* __restrict__ keys_in,
+                                                             const unsigned* __restrict__ vals_in,
+                                                             unsigned* __restrict__ keys_out,
+                                                             unsigned* __restrict__ vals_out, long long n, int shift,
+                                                             const unsigned* __restrict__ hist, int nblocks) {
+  constexpr int ND = 1 << BITS;
+  extern __shared__ unsigned sh[];  // [RS_WARPS][ND] counts, then running offsets
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  unsigned* mine = sh + w * ND;
+  for (int i = threadIdx.x; i < RS_WARPS * ND; i += RS_T) sh[i] = 0;
+  __syncthreads();
+  const long long wbase = (long long)blockIdx.x * RS_TILE + (long long)w * (RS_TILE / RS_WARPS);
+  unsigned k[RS_ROUNDS];
+  // pass 1: per-warp digit counts
+#pragma unroll
+  for (int r = 0; r < RS_ROUNDS; r++) {
+    const long long i = wbase + r * 32 + lane;
+    const bool ok = i < n;
+    k[r] = ok ? keys_in[i] : 0xffffffffu;
+    const unsigned d = (k[r] >> shift) & (ND - 1);
+    const unsigned act = __ballot_sync(0xffffffffu, ok);
+    if (ok) {
+      const unsigned peers = __match_any_sync(act, d);
+      if (lane == __ffs(peers) - 1) mine[d] += __popc(peers);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  // exclusive prefix over warps per digit, plus the global base of this (digit, block)
+  for (int d = threadIdx.x; d < ND; d += RS_T) {
+    unsigned run = hist[(long long)d * nblocks + blockIdx.x];
+#pragma unroll
+    for (int ww = 0; ww < RS_WARPS; ww++) {
+      const unsigned c = sh[ww * ND + d];
+      sh[ww * ND + d] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+  // pass 2: stable scatter
+#pragma unroll
+  for (int r = 0; r < RS_ROUNDS; r++) {
+    const long long i = wbase + r * 32 + lane;
+    const bool ok = i < n;
+    const unsigned d = (k[r] >> shift) & (ND - 1);
+    const unsigned act = __ballot_sync(0xffffffffu, ok);
+    unsigned peers = 0;
+    if (ok) {
+      peers = __match_any_sync(act, d);
+      const unsigned rank = __popc(peers & ((1u << lane) - 1u));
+      const unsigned pos = mine[d] + rank;
+      keys_out[pos] = k[r];
+      vals_out[pos] = vals_in[i];
+    }
+    __syncwarp();
+    if (ok && lane == __ffs(peers) - 1) mine[d] += __popc(peers);
+    __syncwarp();
+  }
+}
+
+// seg[j] = first sorted position whose key >= j, for j in [0, n_dst]; keys sorted ascending
+__global__ void seg_start_kernel(const unsigned* __restrict__ keys, long long n, unsigned* __restrict__ seg,
+                                 long long n_dst) {
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p <= n; p += (long long)gridDim.x * blockDim.x) {
+    const long long lo = (p == 0) ? 0 : (long long)keys[p - 1] + 1;
+    long long hi = (p == n) ? n_dst : (long long)keys[p];
+    if (hi > n_dst) hi = n_dst;
+    for (long long j = lo; j <= hi; j++) seg[j] = (unsigned)p;
+  }
+}
+
+struct SortPlan {
+  int bits, passes;
+  long long nblocks;
+  size_t off_keys[2], off_vals[2], off_hist, off_seg, off_scan, total;
+};
+
+static SortPlan sort_plan(long long n_dst, long long n_src) {
+  SortPlan sp{};
+  int keybits = 1;
+  while ((1ll << keybits) <= n_dst) keybits++;  // keys in [0, n_dst] (n_dst = overflow bucket)
+  sp.passes = (keybits + 10) / 11;
+  sp.bits = (keybits + sp.passes - 1) / sp.passes;
+  if (sp.bits < 4) sp.bits = 4;
+  sp.nblocks = (n_src + RS_TILE - 1) / RS_TILE;
+  if (sp.nblocks < 1) sp.nblocks = 1;
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  size_t o = 0;
+  for (int i = 0; i < 2; i++) {
+    sp.off_keys[i] = o;
+    o += al((size_t)n_src * 4 + 4);
+    sp.off_vals[i] = o;
+    o += al((size_t)n_src * 4 + 4);
+  }
+  sp.off_hist = o;
+  const size_t hist_elems = ((size_t)1 << sp.bits) * (size_t)sp.nblocks;
+  o += al(hist_elems * 4);
+  sp.off_seg = o;
+  o += al(((size_t)n_dst + 2) * 4);
+  sp.off_scan = o;
+  o += al(scan_ws_elems((long long)hist_elems) * 4 + 1024);
+  sp.total = o;
+  return sp;
+}
+
+template <int BITS>
+static int radix_pass(const unsigned* kin, const unsigned* vin, unsigned* kout, unsigned* vout, long long n, int shift,
+                      unsigned* hist, int nblocks, unsigned* scan_ws, cudaStream_t s) {
+  constexpr int ND = 1 << BITS;
+  radix_hist_kernel<BITS><<<nblocks, RS_T, ND * 4, s>>>(kin, n, shift, hist, nblocks);
+  YOTA_CUDA(cudaGetLastError());
+  YOTA_TRY(exclusive_scan_u32(hist, (long long)ND * nblocks, scan_ws, s));
+  const size_t smem = (size_t)RS_WARPS * ND * 4;
+  static bool attr = false;
+  if (smem > 48 * 1024 && !attr) {
+    YOTA_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  radix_scatter_kernel<BITS><<<nblocks, RS_T, smem, s>>>(kin, vin, kout, vout, n, shift, hist, nblocks);
+  YOTA_CUDA(cudaGetLastError());
+  return YOTA_OK;
+}
+
+// Sort (idx -> dest key, position) and build segment starts.  Results: *perm (source
+// positions grouped by destination, ascending inside a group), *seg (n_dst + 1 starts).
+static int sort_by_destination(const int64_t* idx, long long n_src, long long n_dst, void* ws, const unsigned** perm,
+                               const unsigned** seg, cudaStream_t s) {
+  const SortPlan sp = sort_plan(n_dst, n_src);
+  char* base = static_cast<char*>(ws);
+  unsigned* keys[2] = {reinterpret_cast<unsigned*>(base + sp.off_keys[0]),
+                       reinterpret_cast<unsigned*>(base + sp.off_keys[1])};
+  unsigned* vals[2] = {reinterpret_cast<unsigned*>(base + sp.off_vals[0]),
+                       reinterpret_cast<unsigned*>(base + sp.off_vals[1])};
+  unsigned* hist = reinterpret_cast<unsigned*>(base + sp.off_hist);
+  unsigned* segp = reinterpret_cast<unsigned*>(base + sp.off_seg);
+  unsigned* scan_ws = reinterpret_cast<unsigned*>(base + sp.off_scan);
+  keys_from_idx_kernel<<<grid_for(n_src, 256), 256, 0, s>>>(keys[0], vals[0], idx, n_src, n_dst);
+  YOTA_CUDA(cudaGetLastError());
+  int cur = 0;
+  for (int pass = 0; pass < sp.passes; pass++) {
+    const int shift = pass * sp.bits;
+    int st;
+    switch (sp.bits) {
+#define RP(B)                                                                                                    \
+  case B:                                                                                                        \
+    st = radix_pass<B>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n_src, shift, hist, (int)sp.nblocks, \
+                       scan_ws, s);                                                                              \
+    break;
+      RP(4) RP(5) RP(6) RP(7) RP(8) RP(9) RP(10) RP(11)
+#undef RP
+      default:
+        YOTA_FAIL(YOTA_E_ARG, "radix sort: unsupported digit width %d", sp.bits);
+    }
+    YOTA_TRY(st);
+    cur ^= 1;
+  }
+  seg_start_kernel<<<grid_for(n_src + 1, 256), 256, 0, s>>>(keys[cur], n_src, segp, n_dst);
+  YOTA_CUDA(cudaGetLastError());
+  *perm = vals[cur];
+  *seg = segp;
+  return YOTA_OK;
+}
+
+size_t scatter_cols_workspace_bytes(long long n_dst, long long n_src) { return sort_plan(n_dst, n_src).total; }
+
+// ------------------------------------------------------------------------------------------
+// ordered fold: dx[:, j] = ((0 + dy[:, k1]) + dy[:, k2]) + ...   k1 < k2 < ... with idx[k] == j
+// ------------------------------------------------------------------------------------------
+template <int V>
+struct FV;
+template <>
+struct FV<4> {
+  using T = float4;
+  static __device__ __forceinline__ T zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  static __device__ __forceinline__ T add(T a, T b) {
+    return make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w));
+  }
+};
+template <>
+struct FV<1> {
+  using T = float;
+  static __device__ __forceinline__ T zero() { return 0.f; }
+  static __device__ __forceinline__ T add(T a, T b) { return __fadd_rn(a, b); }
+};
+
+template <int V>
+__global__ void __launch_bounds__(256) scatter_fold_cols_kernel(typename FV<V>::T* __restrict__ dx,
+                                                                const typename FV<V>::T* __restrict__ dy, int RV,
+                                                                long long n_dst, const unsigned* __restrict__ perm,
+                                                                const unsigned* __restrict__ seg) {
+  using T = typename FV<V>::T;
+  // TPC threads cooperate on one destination column; a CTA holds 256 / TPC columns
+  const int TPC = RV < 256 ? RV : 256;
+  const int cpb = 256 / TPC;
+  const int cs = threadIdx.x / TPC, rv0 = threadIdx.x % TPC;
+  if (cs >= cpb) return;
+  for (long long j = (long long)blockIdx.x * cpb + cs; j < n_dst; j += (long long)gridDim.x * cpb) {
+    const unsigned p0 = __ldg(seg + j), p1 = __ldg(seg + j + 1);
+    for (int rv = rv0; rv < RV; rv += TPC) {
+      T acc = FV<V>::zero();
+      unsigned p = p0;
+      for (; p + 4 <= p1; p += 4) {  // 4 independent loads in flight, folded in source order
+        const unsigned k0 = __ldg(perm + p), k1 = __ldg(perm + p + 1), k2 = __ldg(perm + p + 2), k3 = __ldg(perm + p + 3);
+        const T v0 = __ldg(dy + (long long)k0 * RV + rv);
+        const T v1 = __ldg(dy + (long long)k1 * RV + rv);
+        const T v2 = __ldg(dy + (long long)k2 * RV + rv);
+        const T v3 = __ldg(dy + (long long)k3 * RV + rv);
+        acc = FV<V>::add(FV<V>::add(FV<V>::add(FV<V>::add(acc, v0), v1), v2), v3);
+      }
+      for (; p < p1; p++) acc = FV<V>::add(acc, __ldg(dy + (long long)__ldg(perm + p) * RV + rv));
+      dx[j * RV + rv] = acc;
+    }
+  }
+}
+
+int launch_scatter_add_cols(float* dx, long long rows, long long n_dst, const float* dy, const int64_t* idx,
+                            long long n_src, void* workspace, size_t ws_bytes, cudaStream_t s) {
+  if (rows * n_dst == 0) return YOTA_OK;
+  if (n_src >= (1ll << 32) - 1 || n_dst >= (1ll << 32) - 2)
+    YOTA_FAIL(YOTA_E_SHAPE, "scatter-add: more than 2^32 sources/destinations are not supported");
+  if (ws_bytes < scatter_cols_workspace_bytes(n_dst, n_src)) YOTA_FAIL(YOTA_E_ARG, "scatter-add: workspace too small");
+  const unsigned *perm, *seg;
+  YOTA_TRY(sort_by_destination(idx, n_src, n_dst, workspace, &perm, &seg, s));
+  const bool v4 = (rows % 4 == 0) && ((reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(dy)) % 16 == 0);
+  if (v4) {
+    const int RV = (int)(rows / 4);
+    const int TPC = RV < 256 ? RV : 256, cpb = 256 / TPC;
+    scatter_fold_cols_kernel<4><<<grid_for((n_dst + cpb - 1) / cpb, 1, 148 * 32), 256, 0, s>>>(
+        reinterpret_cast<float4*>(dx), reinterpret_cast<const float4*>(dy), RV, n_dst, perm, seg);
+  } else {
+    if (rows > 0x7fffffff) YOTA_FAIL(YOTA_E_SHAPE, "scatter-add: too many rows");
+    const int RV = (int)rows;
+    const int TPC = RV < 256 ? RV : 256, cpb = 256 / TPC;
+    scatter_fold_cols_kernel<1><<<grid_for((n_dst + cpb - 1) / cpb, 1, 148 * 32), 256, 0, s>>>(dx, dy, RV, n_dst, perm,
+                                                                                             seg);
+  }
+  YOTA_CUDA(cudaGetLastError());
+  return YOTA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// general ungetindex: any mix of : / int / range / (at most one) index vector
+// ------------------------------------------------------------------------------------------
+struct UngetParams {
+  int nd;
+  long long xdim[4];
+  int kind[4];
+  long long a[4], b[4];
+  long long dystride[4];  // stride in dy of the coordinate along index d (0 for INT)
+  int vec_dim;            // -1: none
+  const unsigned* perm;
+  const unsigned* seg;
+};
+
+__global__ void ungetindex_generic_kernel(UngetParams p, float* __restrict__ dx, const float* __restrict__ dy,
+                                          long long n_x) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_x; i += (long long)gridDim.x * blockDim.x) {
+    long long rem = i, off = 0, jv = 0;
+    bool hit = true;
+#pragma unroll
+    for (int d = 0; d < 4; d++) {
+      if (d < p.nd) {
+        const long long c = rem % p.xdim[d];
+        rem /= p.xdim[d];
+        const int kd = p.kind[d];
+        if (kd == YOTA_IDX_COLON)
+          off += c * p.dystride[d];
+        else if (kd == YOTA_IDX_VEC)
+          jv = c;
+        else {
+          hit = hit && (c + 1 >= p.a[d]) && (c + 1 <= p.b[d]);
+          off += (c + 1 - p.a[d]) * p.dystride[d];
+        }
+      }
+    }
+    float acc = 0.f;
+    if (hit) {
+      if (p.vec_dim < 0) {
+        acc = __fadd_rn(0.f, dy[off]);  // 0.0f + (-0.0f) = +0.0f, exactly like zero(x) .+= dy
+      } else {
+        const unsigned p0 = p.seg[jv], p1 = p.seg[jv + 1];
+        const long long vs = p.dystride[p.vec_dim];
+        for (unsigned q = p0; q < p1; q++) acc = __fadd_rn(acc, dy[off + (long long)p.perm[q] * vs]);
+      }
+    }
+    dx[i] = acc;
+  }
+}
+
+size_t ungetindex_workspace_bytes(const IndexSpec& sp) {
+  for (int d = 0; d < sp.n; d++)
+    if (sp.kind[d] == YOTA_IDX_VEC) return scatter_cols_workspace_bytes(sp.xdims[d], sp.vlen[d]);
+  return 0;
+}
+
+int launch_ungetindex(const IndexSpec& sp, float* dx, const float* dy, void* workspace, size_t ws_bytes, int sm_count,
+                      cudaStream_t s) {
+  (void)sm_count;
+  long long n_x = 1;
+  for (int d = 0; d < sp.n; d++) n_x *= sp.xdims[d];
+  if (n_x == 0) return YOTA_OK;
+  int vec_dim = -1, nvec = 0;
+  for (int d = 0; d < sp.n; d++)
+    if (sp.kind[d] == YOTA_IDX_VEC) {
+      vec_dim = d;
+      nvec++;
+    }
+  if (nvec > 1) YOTA_FAIL(YOTA_E_UNSUPPORTED_OP, "ungetindex: more than one index vector is not supported");
+  // fast path: dx[:, idx] += dy on a matrix
+  if (sp.n == 2 && sp.kind[0] == YOTA_IDX_COLON && vec_dim == 1)
+    return launch_scatter_add_cols(dx, sp.xdims[0], sp.xdims[1], dy, sp.vec[1], sp.vlen[1], workspace, ws_bytes, s);
+  UngetParams p{};
+  p.nd = sp.n;
+  p.vec_dim = vec_dim;
+  long long st = 1;
+  for (int d = 0; d < 4; d++) {
+    p.xdim[d] = 1;
+    p.kind[d] = YOTA_IDX_COLON;
+    p.a[d] = p.b[d] = 1;
+    p.dystride[d] = 0;
+  }
+  for (int d = 0; d < sp.n; d++) {
+    p.xdim[d] = sp.xdims[d];
+    p.kind[d] = sp.kind[d];
+    p.a[d] = sp.a[d];
+    p.b[d] = sp.b[d];
+    long long ext;
+    switch (sp.kind[d]) {
+      case YOTA_IDX_COLON: ext = sp.xdims[d]; break;
+      case YOTA_IDX_INT: ext = 1; break;
+      case YOTA_IDX_RANGE: ext = sp.b[d] - sp.a[d] + 1; break;
+      default: ext = sp.vlen[d]; break;
+    }
+    p.dystride[d] = (sp.kind[d] == YOTA_IDX_INT) ? 0 : st;
+    st *= ext;
+  }
+  if (vec_dim >= 0) {
+    if (ws_bytes < ungetindex_workspace_bytes(sp)) YOTA_FAIL(YOTA_E_ARG, "ungetindex: workspace too small");
+    YOTA_TRY(sort_by_destination(sp.vec[vec_dim], sp.vlen[vec_dim], sp.xdims[vec_dim], workspace, &p.perm, &p.seg, s));
+  }
+  ungetindex_generic_kernel<<<grid_for(n_x, 256), 256, 0, s>>>(p, dx, dy, n_x);
+  YOTA_CUDA(cudaGetLastError());
+  return YOTA_OK;
+}
+
+}  // namespace yota

@@ -1,0 +1,1408 @@
+// The compiled gradient tape: planner (fusion, memory, launch list) and executor.
+//
+// Replaces what `grad_compile(tape)` produces and `invokelatest(gf, f, args...; seed)` runs
+// in the reference (/root/reference/src/grad.jl:293-307, 353-355): instead of one Julia
+// statement -> one BLAS call / broadcast loop / mapreduce with a fresh temporary each, the op
+// list is planned once into a short list of fused kernels over program-owned memory and
+// replayed as a CUDA graph.
+//
+// Planning (host only, no device calls -- also runs on a machine without a GPU):
+//   1. dead-code elimination from the OUTPUT tensors
+//   2. fusion of elementwise ops (+ their sum / unbroadcast sinks and the tape's
+//      broadcast(+, dx, old) accumulations) into regions: producer -> consumer and sibling
+//      fusion whenever every other operand is already available when the region runs
+//   3. region codegen: 2-d split (R x C), operand classes, shared-memory slot allocation,
+//      micro-op list; lookup of a precompiled chain with the same micro-program
+//   4. liveness-based arena planning for materialised intermediates and workspaces
+#include <algorithm>
+#include <cstring>
+#include <string>
+
+#include "common.h"
+
+namespace yota {
+
+static inline bool ew_is_binary(int op) { return op >= YOTA_EW_ADD && op <= YOTA_EW_DIV; }
+
+enum StepKind {
+  STEP_REGION,
+  STEP_ROWSUM_FINISH,
+  STEP_SCALAR_FINISH,
+  STEP_COLSUM,
+  STEP_GENERIC_EW,
+  STEP_GENERIC_SUM,
+  STEP_GEMM,
+  STEP_GETINDEX,
+  STEP_UNGETINDEX,
+  STEP_LOGSOFTMAX,
+  STEP_TRANSPOSE,
+  STEP_CAT,
+  STEP_SLICE
+};
+
+struct TInfo {
+  yota_tensor_desc d;
+  int nd = 0;             // canonical ndim (trailing 1s stripped)
+  long long dims[4] = {1, 1, 1, 1};
+  long long numel = 1;
+  int producer = -1;
+  std::vector<int> consumers;
+  int alias_of = -1;  // root tensor for RESHAPE outputs
+  bool needed = false;
+  bool materialized = false;
+  int region = -1;  // region index if produced by a fused EW op
+  // storage
+  long long arena_off = -1;
+  int def_step = -1, last_step = -1;
+  int const_index = -1;
+};
+
+struct Region {
+  std::vector<int> ops;   // EW op indices, program order
+  std::vector<int> sums;  // absorbed SUM op indices
+  int nd = 0;
+  long long dims[4] = {1, 1, 1, 1};
+  unsigned kmask = 0;
+  int step = -1;
+  // codegen results
+  int k = 0;
+  RegionLaunch L;
+  std::vector<int> in_tensors;   // tensor id per RegionIn
+  std::vector<int> out_tensors;  // tensor id per RegionOut (for sums: the SUM's output tensor)
+  std::vector<int> finish_steps;
+  long long ws_off[RG_MAX_OUT];
+  int n_partials[RG_MAX_OUT];
+};
+
+struct Step {
+  int kind = 0;
+  std::string label;
+  std::vector<int> reads, writes;
+  int region = -1;
+  int op = -1;
+  // finishers
+  int out_tensor = -1;
+  long long ws_off = -1;
+  size_t ws_bytes = 0;
+  long long R = 0, C = 0;
+  int P = 0;
+  float scale = 1.f;
+  int ws_owner_step = -1;  // finisher: the step whose workspace it reads
+};
+
+}  // namespace yota
+
+using namespace yota;
+
+struct yota_program {
+  yota_ctx* ctx = nullptr;
+  uint32_t flags = 0;
+  std::vector<yota_op_desc> ops;
+  std::vector<TInfo> T;
+  std::vector<Region> regions;
+  std::vector<Step> steps;
+  std::vector<char> op_needed;
+  int n_in = 0, n_out = 0;
+  size_t arena_bytes = 0, const_bytes = 0;
+  std::vector<int> const_tensors;  // CONST / SEED tensors, in const-buffer order
+  int n_launches = 0, n_static = 0;
+  // runtime
+  char* arena = nullptr;
+  std::vector<void*> bound_in, bound_out;
+  float last_seed = 0.f;
+  bool seed_valid = false;
+  int runs_with_binding = 0;
+  cudaGraphExec_t graph_exec = nullptr;
+  std::vector<int> allreduce_slots;
+  std::vector<cudaEvent_t> ar_events;
+};
+
+namespace yota {
+
+static long long prod(const long long* d, int a, int b) {
+  long long p = 1;
+  for (int i = a; i < b; i++) p *= d[i];
+  return p;
+}
+
+static bool is_ew(int opcode) { return opcode >= YOTA_EW_COPY && opcode <= YOTA_EW__LAST; }
+
+static int root_of(const yota_program& P, int t) {
+  while (P.T[t].alias_of >= 0) t = P.T[t].alias_of;
+  return t;
+}
+
+// valid split points of an operand with canonical dims E (ne) inside iteration dims D (nd)
+static unsigned operand_kmask(const long long* D, int nd, const long long* E, int ne) {
+  unsigned m = 0;
+  for (int k = 0; k <= nd; k++) {
+    bool fullR = true, onesR = true, fullC = true, onesC = true;
+    for (int i = 0; i < nd; i++) {
+      const long long e = i < ne ? E[i] : 1;
+      const bool full = e == D[i], one = e == 1;
+      if (i < k) {
+        fullR &= full;
+        onesR &= one;
+      } else {
+        fullC &= full;
+        onesC &= one;
+      }
+    }
+    if ((fullR || onesR) && (fullC || onesC)) m |= 1u << k;
+  }
+  return m;
+}
+
+static int operand_class(const long long* D, int nd, int k, const long long* E, int ne) {
+  bool fullR = true, fullC = true;
+  for (int i = 0; i < nd; i++) {
+    const long long e = i < ne ? E[i] : 1;
+    if (i < k)
+      fullR &= (e == D[i]);
+    else
+      fullC &= (e == D[i]);
+  }
+  if (fullR && fullC) return CLS_FULL;
+  if (fullR) return CLS_ROWVEC;
+  if (fullC) return CLS_COLVEC;
+  return CLS_SCALAR;
+}
+
+// classification of a reduction mask at split k: 0 none/invalid, 1 ROWSUM, 2 SCALAR, 3 COLSUM
+static int sum_class(const long long* D, int nd, int k, unsigned mask) {
+  bool redR = true, keepR = true, redC = true, keepC = true;
+  for (int i = 0; i < nd; i++) {
+    if (D[i] == 1) continue;
+    const bool r = mask >> i & 1;
+    if (i < k) {
+      redR &= r;
+      keepR &= !r;
+    } else {
+      redC &= r;
+      keepC &= !r;
+    }
+  }
+  if (redR && redC) return 2;
+  if (keepR && redC) return 1;
+  if (redR && keepC) return 3;
+  return 0;
+}
+
+static unsigned sum_kmask_fusable(const long long* D, int nd, unsigned mask) {
+  unsigned m = 0;
+  for (int k = 0; k <= nd; k++) {
+    const int c = sum_class(D, nd, k, mask);
+    if (c == 1 || c == 2) m |= 1u << k;
+  }
+  return m;
+}
+
+static bool same_dims(const TInfo& a, const long long* D, int nd) {
+  if (a.nd != nd) return false;
+  for (int i = 0; i < nd; i++)
+    if (a.dims[i] != D[i]) return false;
+  return true;
+}
+
+static const char* opname(int opc) {
+  switch (opc) {
+    case YOTA_EW_COPY: return "copy";
+    case YOTA_EW_ADD: return "add";
+    case YOTA_EW_SUB: return "sub";
+    case YOTA_EW_MUL: return "mul";
+    case YOTA_EW_DIV: return "div";
+    case YOTA_EW_NEG: return "neg";
+    case YOTA_EW_TANH: return "tanh";
+    case YOTA_EW_EXP: return "exp";
+    case YOTA_EW_LOG: return "log";
+    case YOTA_EW_SIN: return "sin";
+    case YOTA_EW_COS: return "cos";
+    case YOTA_EW_SQRT: return "sqrt";
+    case YOTA_EW_RELU: return "relu";
+    case YOTA_EW_SIGMOID: return "sigmoid";
+    case YOTA_EW_SQUARE: return "square";
+    case YOTA_EW_GT0: return "gt0";
+    case YOTA_EW_ADDC: return "addc";
+    case YOTA_EW_MULC: return "mulc";
+    case YOTA_EW_RSUBC: return "rsubc";
+    case YOTA_EW_RDIVC: return "rdivc";
+    case YOTA_EW_POWC: return "powc";
+    case YOTA_OP_SUM: return "sum";
+    case YOTA_OP_MATMUL: return "matmul";
+    case YOTA_OP_GETINDEX: return "getindex";
+    case YOTA_OP_UNGETINDEX: return "ungetindex";
+    case YOTA_OP_LOGSOFTMAX: return "logsoftmax";
+    case YOTA_OP_RESHAPE: return "reshape";
+    case YOTA_OP_TRANSPOSE: return "transpose";
+    case YOTA_OP_CAT: return "cat";
+    case YOTA_OP_SLICE: return "slice";
+  }
+  return "?";
+}
+
+// ------------------------------------------------------------------------------------------
+// validation
+// ------------------------------------------------------------------------------------------
+static int validate(yota_program& P) {
+  const int nt = (int)P.T.size();
+  for (size_t i = 0; i < P.ops.size(); i++) {
+    const yota_op_desc& o = P.ops[i];
+    if (o.n_in < 0 || o.n_in > YOTA_MAX_OP_INPUTS) YOTA_FAIL(YOTA_E_ARG, "op %zu: bad n_in", i);
+    if (o.out < 0 || o.out >= nt) YOTA_FAIL(YOTA_E_ARG, "op %zu: bad output tensor id", i);
+    for (int j = 0; j < o.n_in; j++) {
+      if (o.in[j] < 0 || o.in[j] >= nt) YOTA_FAIL(YOTA_E_ARG, "op %zu: bad input tensor id", i);
+      const TInfo& t = P.T[o.in[j]];
+      if (t.d.kind == YOTA_T_TEMP || t.d.kind == YOTA_T_OUTPUT)
+        if (t.producer < 0 || t.producer >= (int)i)
+          YOTA_FAIL(YOTA_E_ARG, "op %zu (%s): input %%%d is used before it is defined", i, opname(o.opcode), o.in[j]);
+    }
+    TInfo& out = P.T[o.out];
+    if (out.d.kind != YOTA_T_TEMP && out.d.kind != YOTA_T_OUTPUT)
+      YOTA_FAIL(YOTA_E_ARG, "op %zu writes a tensor that is not TEMP/OUTPUT", i);
+    const int opc = o.opcode;
+    if (is_ew(opc)) {
+      const int want = ew_is_binary(opc) ? 2 : 1;
+      if (o.n_in != want) YOTA_FAIL(YOTA_E_ARG, "op %zu (%s): expects %d inputs", i, opname(opc), want);
+      for (int j = 0; j < o.n_in; j++) {
+        const TInfo& a = P.T[o.in[j]];
+        if (a.d.dtype != YOTA_F32) YOTA_FAIL(YOTA_E_UNSUPPORTED_OP, "op %zu (%s): only Float32 operands", i, opname(opc));
+        for (int d = 0; d < std::max(a.nd, out.nd); d++) {
+          const long long e = d < a.nd ? a.dims[d] : 1, D = d < out.nd ? out.dims[d] : 1;
+          if (e != D && e != 1)
+            YOTA_FAIL(YOTA_E_SHAPE, "op %zu (%s): DimensionMismatch, operand %%%d cannot broadcast to the output", i,
+                      opname(opc), o.in[j]);
+        }
+      }
+    } else if (opc == YOTA_OP_SUM) {
+      const TInfo& x = P.T[o.in[0]];
+      long long keep = 1;
+      for (int d = 0; d < x.nd; d++)
+        if (!(o.iattr[0] >> d & 1)) keep *= x.dims[d];
+      if (keep != out.numel) YOTA_FAIL(YOTA_E_SHAPE, "op %zu (sum): output numel does not match the kept dims", i);
+    } else if (opc == YOTA_OP_MATMUL) {
+      const TInfo &A = P.T[o.in[0]], &B = P.T[o.in[1]];
+      if (A.d.ndim > 2 || B.d.ndim > 2) YOTA_FAIL(YOTA_E_SHAPE, "op %zu (matmul): operands must be vectors/matrices", i);
+      const long long ar = A.d.ndim >= 1 ? A.d.dims[0] : 1, ac = A.d.ndim == 2 ? A.d.dims[1] : 1;
+      const long long br = B.d.ndim >= 1 ? B.d.dims[0] : 1, bc = B.d.ndim == 2 ? B.d.dims[1] : 1;
+      const long long m = o.iattr[0] ? ac : ar, k1 = o.iattr[0] ? ar : ac;
+      const long long k2 = o.iattr[1] ? bc : br, n = o.iattr[1] ? br : bc;
+      if (k1 != k2 || m * n != out.numel)
+        YOTA_FAIL(YOTA_E_SHAPE, "op %zu (matmul): DimensionMismatch (%lldx%lld)*(%lldx%lld)", i, m, k1, k2, n);
+    } else if (opc == YOTA_OP_RESHAPE) {
+      if (P.T[o.in[0]].numel != out.numel) YOTA_FAIL(YOTA_E_SHAPE, "op %zu (reshape): numel mismatch", i);
+    } else if (opc == YOTA_OP_LOGSOFTMAX || opc == YOTA_OP_TRANSPOSE) {
+      if (P.T[o.in[0]].numel != out.numel) YOTA_FAIL(YOTA_E_SHAPE, "op %zu (%s): numel mismatch", i, opname(opc));
+    } else if (opc == YOTA_OP_GETINDEX || opc == YOTA_OP_UNGETINDEX || opc == YOTA_OP_CAT || opc == YOTA_OP_SLICE) {
+      // checked when the step is built
+    } else {
+      YOTA_FAIL(YOTA_E_UNSUPPORTED_OP, "op %zu: unsupported opcode %d (no CPU fallback exists)", i, opc);
+    }
+  }
+  return YOTA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// fusion
+// ------------------------------------------------------------------------------------------
+static int step_of_tensor(const yota_program& P, int t) {
+  // step index at which tensor t becomes available (-1: before the program starts)
+  const TInfo& ti = P.T[root_of(P, t)];
+  if (ti.d.kind == YOTA_T_INPUT || ti.d.kind == YOTA_T_CONST || ti.d.kind == YOTA_T_SEED) return -1;
+  return ti.def_step;
+}
+
+static int new_step(yota_program& P, int kind, const std::string& label) {
+  Step s;
+  s.kind = kind;
+  s.label = label;
+  P.steps.push_back(s);
+  return (int)P.steps.size() - 1;
+}
+
+// Elementwise placement.  T[t].region: -1 not placed, FLOATING waiting for a consumer,
+// >= 0 member of that region.  An op whose operands come from no region of its shape (the
+// broadcast-back of the seed, exp.(logp) of the logsoftmax pullback, ...) FLOATS until a
+// consumer is placed and then joins the consumer's region, so it is never materialised.
+constexpr int FLOATING = -2;
+
+struct Fuser {
+  yota_program& P;
+  bool fuse;
+  explicit Fuser(yota_program& p) : P(p), fuse(!(p.flags & YOTA_FLAG_NO_FUSE)) {}
+
+  unsigned op_kmask(int opi) const {
+    const yota_op_desc& o = P.ops[opi];
+    const TInfo& out = P.T[o.out];
+    unsigned km = ~0u;
+    for (int j = 0; j < o.n_in; j++) km &= operand_kmask(out.dims, out.nd, P.T[o.in[j]].dims, P.T[o.in[j]].nd);
+    return km & ((1u << (out.nd + 1)) - 1);
+  }
+  bool float_input(const yota_op_desc& o, int j) const { return P.T[o.in[j]].region == FLOATING; }
+
+  // the floating producers feeding op `opi` (transitively), in program order, plus opi
+  void group_of(int opi, std::vector<int>& g) const {
+    const yota_op_desc& o = P.ops[opi];
+    for (int j = 0; j < o.n_in; j++)
+      if (float_input(o, j)) group_of(P.T[o.in[j]].producer, g);
+    if (std::find(g.begin(), g.end(), opi) == g.end()) g.push_back(opi);
+  }
+
+  bool can_join(const std::vector<int>& g, int ri) const {
+    const Region& r = P.regions[ri];
+    unsigned km = r.kmask;
+    if ((int)(r.ops.size() + g.size()) > 40) return false;
+    std::vector<int> ins;
+    auto in_group = [&](int t) {
+      return P.T[t].producer >= 0 && std::find(g.begin(), g.end(), P.T[t].producer) != g.end();
+    };
+    for (int opi : r.ops)
+      for (int j = 0; j < P.ops[opi].n_in; j++) {
+        const int t = P.ops[opi].in[j];
+        if (P.T[t].region != ri && std::find(ins.begin(), ins.end(), t) == ins.end()) ins.push_back(t);
+      }
+    for (int opi : g) {
+      const yota_op_desc& o = P.ops[opi];
+      if (!same_dims(P.T[o.out], r.dims, r.nd)) return false;
+      km &= op_kmask(opi);
+      for (int j = 0; j < o.n_in; j++) {
+        const int t = o.in[j];
+        if (P.T[t].region == ri || in_group(t)) continue;
+        if (step_of_tensor(P, t) >= r.step) return false;  // operand not available when r runs
+        if (std::find(ins.begin(), ins.end(), t) == ins.end()) ins.push_back(t);
+      }
+    }
+    return km != 0 && (int)ins.size() <= RG_MAX_IN;
+  }
+
+  void do_join(const std::vector<int>& g, int ri) {
+    Region& r = P.regions[ri];
+    for (int opi : g) {
+      r.kmask &= op_kmask(opi);
+      r.ops.push_back(opi);
+      TInfo& out = P.T[P.ops[opi].out];
+      out.region = ri;
+      out.def_step = r.step;
+    }
+  }
+
+  int new_region(const TInfo& shape, unsigned km) {
+    Region r;
+    r.nd = shape.nd;
+    for (int d = 0; d < 4; d++) r.dims[d] = shape.dims[d];
+    r.kmask = km;
+    r.step = new_step(P, STEP_REGION, "region");
+    P.regions.push_back(r);
+    const int ri = (int)P.regions.size() - 1;
+    P.steps[r.step].region = ri;
+    return ri;
+  }
+
+  // place op `opi` (and the floating producers it pulls along) now
+  void place(int opi, bool allow_float) {
+    const yota_op_desc& o = P.ops[opi];
+    TInfo& out = P.T[o.out];
+    if (!fuse) {
+      do_join({opi}, new_region(out, op_kmask(opi)));
+      return;
+    }
+    std::vector<int> g;
+    group_of(opi, g);
+    // candidate: the latest region that produces one of the group's operands of this shape
+    int best = -1;
+    for (int gi : g)
+      for (int j = 0; j < P.ops[gi].n_in; j++) {
+        const TInfo& a = P.T[P.ops[gi].in[j]];
+        if (a.region >= 0 && same_dims(a, out.dims, out.nd) && a.region > best) best = a.region;
+      }
+    if (best >= 0 && can_join(g, best)) {
+      do_join(g, best);
+      return;
+    }
+    if (best < 0 && allow_float) {
+      out.region = FLOATING;
+      return;
+    }
+    // sibling fusion: the latest region of this shape that already has every operand
+    for (int ri = (int)P.regions.size() - 1; ri >= 0; ri--)
+      if (!P.regions[ri].ops.empty() && can_join(g, ri)) {
+        do_join(g, ri);
+        return;
+      }
+    // a fresh region; if the whole group does not fit one region, split off the producers
+    unsigned km = ~0u;
+    for (int gi : g) km &= op_kmask(gi);
+    if (km != 0 && g.size() <= 40) {
+      const int ri = new_region(out, km & ((1u << (out.nd + 1)) - 1));
+      do_join(g, ri);
+      return;
+    }
+    for (int gi : g) {
+      if (P.T[P.ops[gi].out].region != FLOATING && gi != opi) continue;
+      P.T[P.ops[gi].out].region = -1;
+      do_join({gi}, new_region(P.T[P.ops[gi].out], op_kmask(gi)));
+    }
+  }
+
+  // a non-elementwise consumer (or the end of the program) needs tensor t in memory
+  void force(int t) {
+    if (P.T[t].region == FLOATING) place(P.T[t].producer, false);
+  }
+};
+
+static int plan_fusion(yota_program& P) {
+  Fuser F(P);
+  const bool fuse = F.fuse;
+  for (size_t i = 0; i < P.ops.size(); i++) {
+    if (!P.op_needed[i]) continue;
+    const yota_op_desc& o = P.ops[i];
+    TInfo& out = P.T[o.out];
+    if (!is_ew(o.opcode))
+      for (int j = 0; j < o.n_in; j++) F.force(root_of(P, o.in[j]));
+    if (o.opcode == YOTA_OP_RESHAPE) {
+      out.alias_of = o.in[0];
+      const int r = root_of(P, o.in[0]);
+      P.T[r].materialized = true;
+      out.def_step = step_of_tensor(P, o.in[0]);
+      continue;
+    }
+    if (is_ew(o.opcode)) {
+      if (F.op_kmask((int)i) == 0) {
+        // broadcast pattern that does not collapse to 2-d: generic N-d kernel
+        for (int j = 0; j < o.n_in; j++) F.force(root_of(P, o.in[j]));
+        const int s = new_step(P, STEP_GENERIC_EW, std::string("ew_generic:") + opname(o.opcode));
+        P.steps[s].op = (int)i;
+        out.def_step = s;
+        out.materialized = true;
+        for (int j = 0; j < o.n_in; j++) P.T[root_of(P, o.in[j])].materialized = true;
+        continue;
+      }
+      // operands of another shape (bias vectors, scalars) must be in memory
+      for (int j = 0; j < o.n_in; j++)
+        if (!same_dims(P.T[o.in[j]], out.dims, out.nd)) F.force(root_of(P, o.in[j]));
+      F.place((int)i, out.d.kind != YOTA_T_OUTPUT);
+      continue;
+    }
+    if (o.opcode == YOTA_OP_SUM) {
+      const int x = o.in[0];
+      const TInfo& xi = P.T[x];
+      const unsigned mask = (unsigned)o.iattr[0];
+      const unsigned skm = sum_kmask_fusable(xi.dims, xi.nd, mask);
+      int target = -1;
+      if (fuse && xi.region >= 0 && (P.regions[xi.region].kmask & skm) &&
+          (int)P.regions[xi.region].sums.size() < 3)
+        target = xi.region;
+      if (target < 0 && skm != 0) {
+        // stand-alone fixed-order reduction = a region with no micro-ops
+        target = F.new_region(xi, (1u << (xi.nd + 1)) - 1);
+        P.T[root_of(P, x)].materialized = true;
+      }
+      if (target >= 0) {
+        Region& r = P.regions[target];
+        r.kmask &= skm;
+        r.sums.push_back((int)i);
+        // the finisher step is created at codegen; reserve the availability step now
+        const int fs = new_step(P, 0, "finish");
+        P.steps[fs].op = (int)i;
+        P.steps[fs].region = target;
+        r.finish_steps.push_back(fs);
+        out.def_step = fs;
+        out.materialized = true;
+        continue;
+      }
+      // column sums (sum over the leading dims) or arbitrary masks
+      int kc = -1;
+      for (int k = 1; k <= xi.nd; k++)
+        if (sum_class(xi.dims, xi.nd, k, mask) == 3) {
+          kc = k;
+          break;
+        }
+      const int s = new_step(P, kc >= 0 ? STEP_COLSUM : STEP_GENERIC_SUM, kc >= 0 ? "colsum" : "sum_generic");
+      P.steps[s].op = (int)i;
+      if (kc >= 0) {
+        P.steps[s].R = prod(xi.dims, 0, kc);
+        P.steps[s].C = prod(xi.dims, kc, xi.nd);
+      }
+      P.steps[s].scale = (float)o.fattr[0];
+      P.T[root_of(P, x)].materialized = true;
+      out.def_step = s;
+      out.materialized = true;
+      continue;
+    }
+    // everything else: one step per op, all operands materialised
+    int kind = 0;
+    switch (o.opcode) {
+      case YOTA_OP_MATMUL: kind = STEP_GEMM; break;
+      case YOTA_OP_GETINDEX: kind = STEP_GETINDEX; break;
+      case YOTA_OP_UNGETINDEX: kind = STEP_UNGETINDEX; break;
+      case YOTA_OP_LOGSOFTMAX: kind = STEP_LOGSOFTMAX; break;
+      case YOTA_OP_TRANSPOSE: kind = STEP_TRANSPOSE; break;
+      case YOTA_OP_CAT: kind = STEP_CAT; break;
+      case YOTA_OP_SLICE: kind = STEP_SLICE; break;
+    }
+    const int s = new_step(P, kind, opname(o.opcode));
+    P.steps[s].op = (int)i;
+    for (int j = 0; j < o.n_in; j++) P.T[root_of(P, o.in[j])].materialized = true;
+    out.def_step = s;
+    out.materialized = true;
+  }
+  // anything still floating has no placed consumer: place it now, in program order
+  for (size_t i = 0; i < P.ops.size(); i++)
+    if (P.op_needed[i] && is_ew(P.ops[i].opcode) && P.T[P.ops[i].out].region == FLOATING) F.place((int)i, false);
+  return YOTA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// region codegen
+// ------------------------------------------------------------------------------------------
+static int codegen_region(yota_program& P, int ri) {
+  Region& r = P.regions[ri];
+  // split point
+  int k = -1;
+  for (int kk = 1; kk <= r.nd && k < 0; kk++)
+    if ((r.kmask >> kk & 1) && prod(r.dims, 0, kk) % 4 == 0) k = kk;
+  for (int kk = 1; kk <= r.nd && k < 0; kk++)
+    if (r.kmask >> kk & 1) k = kk;
+  if (k < 0) k = 0;
+  if (!(r.kmask >> k & 1)) YOTA_FAIL(YOTA_E_ARG, "internal: region %d has no valid split", ri);
+  r.k = k;
+  RegionParams& p = r.L.p;
+  memset(&p, 0, sizeof(p));
+  p.R = prod(r.dims, 0, k);
+  p.C = prod(r.dims, k, r.nd);
+  r.L.V = (p.R % 4 == 0) ? 4 : 1;
+  r.L.static_id = -1;
+
+  // values: tensor id -> slot
+  std::map<int, int> slot_of;
+  std::vector<int> free_slots;
+  int n_slots = 0;
+  auto alloc_slot = [&]() {
+    if (!free_slots.empty()) {
+      const int s = free_slots.back();
+      free_slots.pop_back();
+      return s;
+    }
+    return n_slots++;
+  };
+  // inputs: FULL first (the kernel prefetches the first four FULL operands)
+  std::vector<int> ins;
+  auto add_in = [&](int t) {
+    if (P.T[t].region == ri) return;
+    if (std::find(ins.begin(), ins.end(), t) == ins.end()) ins.push_back(t);
+  };
+  for (int opi : r.ops)
+    for (int j = 0; j < P.ops[opi].n_in; j++) add_in(P.ops[opi].in[j]);
+  for (int si : r.sums) add_in(P.ops[si].in[0]);
+  std::stable_sort(ins.begin(), ins.end(), [&](int a, int b) {
+    const int ca = operand_class(r.dims, r.nd, k, P.T[a].dims, P.T[a].nd);
+    const int cb = operand_class(r.dims, r.nd, k, P.T[b].dims, P.T[b].nd);
+    return (ca == CLS_FULL) > (cb == CLS_FULL);
+  });
+  if ((int)ins.size() > RG_MAX_IN) YOTA_FAIL(YOTA_E_ARG, "internal: region %d has too many inputs", ri);
+  p.n_in = (int)ins.size();
+  r.in_tensors = ins;
+  for (int q = 0; q < p.n_in; q++) {
+    p.in[q].cls = operand_class(r.dims, r.nd, k, P.T[ins[q]].dims, P.T[ins[q]].nd);
+    p.in[q].slot = alloc_slot();
+    p.in[q].ptr = nullptr;
+    slot_of[ins[q]] = p.in[q].slot;
+    P.T[root_of(P, ins[q])].materialized = true;
+  }
+  // outputs: stores for values used outside the region, sinks for absorbed sums
+  std::vector<int> store_t;
+  for (int opi : r.ops) {
+    const int t = P.ops[opi].out;
+    bool ext = P.T[t].d.kind == YOTA_T_OUTPUT;
+    for (int c : P.T[t].consumers) {
+      if (!P.op_needed[c]) continue;
+      const yota_op_desc& co = P.ops[c];
+      const bool in_region_ew = is_ew(co.opcode) && P.T[co.out].region == ri;
+      const bool in_region_sum =
+          co.opcode == YOTA_OP_SUM && std::find(r.sums.begin(), r.sums.end(), c) != r.sums.end();
+      if (!in_region_ew && !in_region_sum) ext = true;
+    }
+    if (ext) {
+      store_t.push_back(t);
+      P.T[t].materialized = true;
+    }
+  }
+  if ((int)(store_t.size() + r.sums.size()) > RG_MAX_OUT)
+    YOTA_FAIL(YOTA_E_ARG, "internal: region %d has too many outputs", ri);
+
+  // last use (micro-op index) of every value; outputs/sinks are read after the op loop
+  const int n_ops = (int)r.ops.size();
+  std::map<int, int> last_use, n_uses;
+  for (int q = 0; q < n_ops; q++)
+    for (int j = 0; j < P.ops[r.ops[q]].n_in; j++) {
+      last_use[P.ops[r.ops[q]].in[j]] = q;
+      n_uses[P.ops[r.ops[q]].in[j]]++;
+    }
+  const int END = n_ops + 1;
+  for (int t : store_t) last_use[t] = END, n_uses[t] += 2;
+  for (int si : r.sums) last_use[P.ops[si].in[0]] = END, n_uses[P.ops[si].in[0]] += 2;
+
+  p.n_ops = n_ops;
+  if (n_ops > RG_MAX_OPS) YOTA_FAIL(YOTA_E_ARG, "internal: region %d has too many ops", ri);
+  for (int q = 0; q < n_ops; q++) {
+    const yota_op_desc& o = P.ops[r.ops[q]];
+    MicroOp& m = p.ops[q];
+    m.op = (uint8_t)o.opcode;
+    m.imm = (float)o.fattr[0];
+    const int prev_t = q > 0 ? P.ops[r.ops[q - 1]].out : -1;
+    auto operand = [&](int t) -> uint8_t {
+      if (t == prev_t) return RG_ACC;
+      return (uint8_t)slot_of.at(t);
+    };
+    m.a = operand(o.in[0]);
+    m.b = o.n_in > 1 ? operand(o.in[1]) : m.a;
+    // free operand slots whose last use is this op (inputs keep theirs: reloaded per column)
+    for (int j = 0; j < o.n_in; j++) {
+      const int t = o.in[j];
+      if (P.T[t].region == ri && last_use[t] == q && slot_of.count(t)) {
+        free_slots.push_back(slot_of[t]);
+        slot_of.erase(t);
+      }
+    }
+    // destination: accumulator only if the single use is the very next micro-op
+    const int t = o.out;
+    const bool acc_only = n_uses[t] == 1 && last_use[t] == q + 1;
+    if (acc_only || n_uses[t] == 0) {
+      m.dst = RG_NONE;
+    } else {
+      const int s = alloc_slot();
+      slot_of[t] = s;
+      m.dst = (uint8_t)s;
+    }
+  }
+  p.n_out = 0;
+  r.out_tensors.clear();
+  for (int t : store_t) {
+    RegionOut& o = p.out[p.n_out++];
+    o.kind = OUT_STORE;
+    o.src = slot_of.at(t);
+    o.acc = 0;
+    o.ptr = nullptr;
+    r.out_tensors.push_back(t);
+  }
+  for (size_t q = 0; q < r.sums.size(); q++) {
+    const yota_op_desc& so = P.ops[r.sums[q]];
+    RegionOut& o = p.out[p.n_out++];
+    const int cls = sum_class(r.dims, r.nd, k, (unsigned)so.iattr[0]);
+    o.kind = cls == 1 ? OUT_ROWSUM : OUT_SCALARSUM;
+    o.src = slot_of.at(so.in[0]);
+    o.acc = n_slots++;  // dedicated: accumulators persist across the column loop
+    o.ptr = nullptr;
+    r.out_tensors.push_back(so.out);
+  }
+  p.n_slots = n_slots;
+  if (n_slots > RG_MAX_SLOTS) YOTA_FAIL(YOTA_E_ARG, "internal: region %d needs %d slots", ri, n_slots);
+  region_geometry(r.L, P.ctx->sm_count);
+  if (!(P.flags & YOTA_FLAG_NO_STATIC)) r.L.static_id = static_chain_lookup(p, r.L.V);
+  if (r.L.static_id >= 0) P.n_static++;
+
+  // label + finisher steps
+  std::string lab = "region[";
+  for (int q = 0; q < n_ops; q++) lab += std::string(q ? "," : "") + opname(P.ops[r.ops[q]].opcode);
+  lab += "]";
+  for (size_t q = 0; q < r.sums.size(); q++) lab += "+sum";
+  char buf[160];
+  snprintf(buf, sizeof(buf), " %lldx%lld V%d in=%d out=%d slots=%d grid=%d%s%s", p.R, p.C, r.L.V, p.n_in, p.n_out,
+           n_slots, r.L.grid, r.L.static_id >= 0 ? " static=" : " interp",
+           r.L.static_id >= 0 ? static_chain_name(r.L.static_id) : "");
+  Step& st = P.steps[r.step];
+  st.label = lab + buf;
+  for (int t : ins) st.reads.push_back(t);
+  for (int t : store_t) st.writes.push_back(t);
+  for (size_t q = 0; q < r.sums.size(); q++) {
+    const int oi = (int)store_t.size() + (int)q;
+    Step& fs = P.steps[r.finish_steps[q]];
+    const yota_op_desc& so = P.ops[r.sums[q]];
+    fs.out_tensor = so.out;
+    fs.scale = (float)so.fattr[0];
+    fs.region = ri;
+    fs.ws_owner_step = r.step;
+    fs.writes.push_back(so.out);
+    if (p.out[oi].kind == OUT_ROWSUM) {
+      fs.kind = STEP_ROWSUM_FINISH;
+      fs.label = "rowsum_finish";
+      fs.R = p.R;
+      fs.P = p.colchunks * p.TCC;
+      fs.ws_bytes = (size_t)fs.P * p.R * sizeof(float);
+    } else {
+      fs.kind = STEP_SCALAR_FINISH;
+      fs.label = "scalar_finish";
+      fs.P = r.L.grid;
+      fs.ws_bytes = (size_t)r.L.grid * sizeof(float);
+    }
+    r.n_partials[oi] = fs.P;
+  }
+  return YOTA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// memory planning
+// ------------------------------------------------------------------------------------------
+struct FreeList {
+  std::vector<std::pair<size_t, size_t>> blocks;  // (offset, size), sorted by offset
+  size_t end = 0;
+  size_t alloc(size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (bytes == 0) bytes = 256;
+    int best = -1;
+    for (size_t i = 0; i < blocks.size(); i++)
+      if (blocks[i].second >= bytes && (best < 0 || blocks[i].second < blocks[best].second)) best = (int)i;
+    if (best >= 0) {
+      const size_t off = blocks[best].first;
+      if (blocks[best].second == bytes)
+        blocks.erase(blocks.begin() + best);
+      else {
+        blocks[best].first += bytes;
+        blocks[best].second -= bytes;
+      }
+      return off;
+    }
+    // grow: extend a trailing free block if there is one
+    if (!blocks.empty() && blocks.back().first + blocks.back().second == end) {
+      const size_t off = blocks.back().first;
+      end = off + bytes;
+      blocks.pop_back();
+      return off;
+    }
+    const size_t off = end;
+    end += bytes;
+    return off;
+  }
+  void release(size_t off, size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (bytes == 0) bytes = 256;
+    auto it = std::lower_bound(blocks.begin(), blocks.end(), std::make_pair(off, (size_t)0));
+    it = blocks.insert(it, {off, bytes});
+    const size_t i = it - blocks.begin();
+    if (i + 1 < blocks.size() && blocks[i].first + blocks[i].second == blocks[i + 1].first) {
+      blocks[i].second += blocks[i + 1].second;
+      blocks.erase(blocks.begin() + i + 1);
+    }
+    if (i > 0 && blocks[i - 1].first + blocks[i - 1].second == blocks[i].first) {
+      blocks[i - 1].second += blocks[i].second;
+      blocks.erase(blocks.begin() + i);
+    }
+  }
+};
+
+static size_t elem_size(const TInfo& t) { return t.d.dtype == YOTA_I64 ? 8 : 4; }
+
+static int plan_memory(yota_program& P) {
+  const int ns = (int)P.steps.size();
+  // constants first
+  size_t coff = 0;
+  for (size_t t = 0; t < P.T.size(); t++)
+    if (P.T[t].d.kind == YOTA_T_CONST || P.T[t].d.kind == YOTA_T_SEED) {
+      P.T[t].const_index = (int)P.const_tensors.size();
+      P.const_tensors.push_back((int)t);
+      coff += 256;  // one 256-byte line per scalar keeps every operand 16-byte aligned
+    }
+  P.const_bytes = coff;
+  // last use per root tensor
+  for (int s = 0; s < ns; s++) {
+    const Step& st = P.steps[s];
+    std::vector<int> reads = st.reads;
+    if (st.op >= 0 && st.kind != STEP_ROWSUM_FINISH && st.kind != STEP_SCALAR_FINISH)
+      for (int j = 0; j < P.ops[st.op].n_in; j++) reads.push_back(P.ops[st.op].in[j]);
+    for (int t : reads) {
+      TInfo& r = P.T[root_of(P, t)];
+      r.last_step = std::max(r.last_step, s);
+    }
+  }
+  std::vector<std::vector<int>> defs(ns), frees(ns);
+  for (size_t t = 0; t < P.T.size(); t++) {
+    TInfo& ti = P.T[t];
+    if (ti.alias_of >= 0 || ti.d.kind != YOTA_T_TEMP || !ti.materialized || ti.def_step < 0) continue;
+    if (ti.last_step < ti.def_step) ti.last_step = ti.def_step;
+    defs[ti.def_step].push_back((int)t);
+    frees[ti.last_step].push_back((int)t);
+  }
+  FreeList fl;
+  fl.end = P.const_bytes;
+  // workspaces: allocated at their owner step, released after the finisher / same step
+  std::vector<std::vector<std::pair<size_t, size_t>>> ws_frees(ns);
+  for (int s = 0; s < ns; s++) {
+    Step& st = P.steps[s];
+    for (int t : defs[s]) P.T[t].arena_off = (long long)fl.alloc((size_t)P.T[t].numel * elem_size(P.T[t]));
+    if (st.kind == STEP_REGION) {
+      Region& r = P.regions[st.region];
+      const int n_store = r.L.p.n_out - (int)r.sums.size();
+      for (size_t q = 0; q < r.sums.size(); q++) {
+        Step& fs = P.steps[r.finish_steps[q]];
+        fs.ws_off = (long long)fl.alloc(fs.ws_bytes);
+        r.ws_off[n_store + q] = fs.ws_off;
+        ws_frees[r.finish_steps[q]].push_back({(size_t)fs.ws_off, fs.ws_bytes});
+      }
+    } else if (st.kind == STEP_UNGETINDEX && st.ws_bytes > 0) {
+      st.ws_off = (long long)fl.alloc(st.ws_bytes);
+      ws_frees[s].push_back({(size_t)st.ws_off, st.ws_bytes});
+    }
+    for (int t : frees[s]) fl.release((size_t)P.T[t].arena_off, (size_t)P.T[t].numel * elem_size(P.T[t]));
+    for (auto& w : ws_frees[s]) fl.release(w.first, w.second);
+  }
+  P.arena_bytes = fl.end;
+  return YOTA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// index spec from op attributes
+// ------------------------------------------------------------------------------------------
+static int index_spec_of(const yota_program& P, const yota_op_desc& o, const TInfo& x, IndexSpec& sp,
+                         long long* n_sel) {
+  memset(&sp, 0, sizeof(sp));
+  sp.n = (int)o.iattr[0];
+  if (sp.n < 1 || sp.n > 4) YOTA_FAIL(YOTA_E_SHAPE, "getindex: 1..4 indices supported");
+  if (sp.n == 1) {
+    sp.xdims[0] = x.numel;  // linear indexing
+  } else {
+    if (sp.n < x.d.ndim) YOTA_FAIL(YOTA_E_SHAPE, "getindex: %d indices for a %d-d array", sp.n, x.d.ndim);
+    for (int d = 0; d < sp.n; d++) sp.xdims[d] = d < x.d.ndim ? x.d.dims[d] : 1;
+  }
+  long long nsel = 1;
+  for (int d = 0; d < sp.n; d++) {
+    sp.kind[d] = (int)o.iattr[1 + 3 * d];
+    sp.a[d] = o.iattr[2 + 3 * d];
+    sp.b[d] = o.iattr[3 + 3 * d];
+    long long ext = 1;
+    switch (sp.kind[d]) {
+      case YOTA_IDX_COLON:
+        sp.a[d] = 1;
+        sp.b[d] = sp.xdims[d];
+        ext = sp.xdims[d];
+        break;
+      case YOTA_IDX_INT:
+        sp.b[d] = sp.a[d];
+        if (sp.a[d] < 1 || sp.a[d] > sp.xdims[d]) YOTA_FAIL(YOTA_E_SHAPE, "getindex: BoundsError");
+        break;
+      case YOTA_IDX_RANGE:
+        if (sp.a[d] < 1 || sp.b[d] > sp.xdims[d]) YOTA_FAIL(YOTA_E_SHAPE, "getindex: BoundsError");
+        ext = std::max(0ll, sp.b[d] - sp.a[d] + 1);
+        break;
+      case YOTA_IDX_VEC: {
+        const int slot = (int)sp.a[d];
+        if (1 + slot >= o.n_in) YOTA_FAIL(YOTA_E_ARG, "getindex: missing index-vector operand");
+        const TInfo& v = P.T[o.in[1 + slot]];
+        if (v.d.dtype != YOTA_I64) YOTA_FAIL(YOTA_E_ARG, "getindex: index vectors must be Int64");
+        sp.vlen[d] = v.numel;
+        ext = v.numel;
+        break;
+      }
+      default:
+        YOTA_FAIL(YOTA_E_ARG, "getindex: bad index kind");
+    }
+    nsel *= ext;
+  }
+  sp.nd_x = sp.n;
+  *n_sel = nsel;
+  return YOTA_OK;
+}
+
+static int finish_steps(yota_program& P) {
+  for (size_t s = 0; s < P.steps.size(); s++) {
+    Step& st = P.steps[s];
+    if (st.op < 0 || st.kind == STEP_ROWSUM_FINISH || st.kind == STEP_SCALAR_FINISH) continue;
+    const yota_op_desc& o = P.ops[st.op];
+    st.writes.push_back(o.out);
+    if (st.kind == STEP_GETINDEX || st.kind == STEP_UNGETINDEX) {
+      IndexSpec sp;
+      long long nsel;
+      const TInfo& x = st.kind == STEP_GETINDEX ? P.T[o.in[0]] : P.T[o.out];
+      YOTA_TRY(index_spec_of(P, o, x, sp, &nsel));
+      const TInfo& sel = st.kind == STEP_GETINDEX ? P.T[o.out] : P.T[o.in[0]];
+      if (sel.numel != nsel && !(st.kind == STEP_UNGETINDEX && sel.numel == 1))
+        YOTA_FAIL(YOTA_E_SHAPE, "%s: selection has %lld elements, tensor has %lld", opname(o.opcode), nsel, sel.numel);
+      if (st.kind == STEP_UNGETINDEX) st.ws_bytes = ungetindex_workspace_bytes(sp);
+    }
+    char buf[128];
+    const TInfo& ot = P.T[o.out];
+    snprintf(buf, sizeof(buf), " -> %%%d[%lld,%lld,%lld,%lld]", o.out, ot.dims[0], ot.dims[1], ot.dims[2], ot.dims[3]);
+    st.label += buf;
+  }
+  return YOTA_OK;
+}
+
+}  // namespace yota
+
+// ==========================================================================================
+// C ABI: build / describe / stats / destroy
+// ==========================================================================================
+extern "C" int yota_program_build(yota_ctx* ctx, const yota_op_desc* ops, int64_t n_ops,
+                                  const yota_tensor_desc* tensors, int64_t n_tensors, uint32_t flags,
+                                  yota_program** out) {
+  if (!ctx || !out || n_ops < 0 || n_tensors <= 0 || (!ops && n_ops > 0) || !tensors)
+    YOTA_FAIL(YOTA_E_ARG, "yota_program_build: bad arguments");
+  yota_program* Pp = new yota_program();
+  yota_program& P = *Pp;
+  P.ctx = ctx;
+  P.flags = flags;
+  P.ops.assign(ops, ops + n_ops);
+  P.T.resize((size_t)n_tensors);
+  auto fail = [&](int code) {
+    delete Pp;
+    return code;
+  };
+  for (int64_t t = 0; t < n_tensors; t++) {
+    TInfo& ti = P.T[(size_t)t];
+    ti.d = tensors[t];
+    if (ti.d.ndim < 0 || ti.d.ndim > YOTA_MAX_DIMS) {
+      set_error("tensor %lld: ndim out of range", (long long)t);
+      return fail(YOTA_E_SHAPE);
+    }
+    ti.numel = 1;
+    int nd = ti.d.ndim;
+    for (int d = 0; d < ti.d.ndim; d++) {
+      if (ti.d.dims[d] < 0) {
+        set_error("tensor %lld: negative dim", (long long)t);
+        return fail(YOTA_E_SHAPE);
+      }
+      ti.numel *= ti.d.dims[d];
+    }
+    while (nd > 0 && ti.d.dims[nd - 1] == 1) nd--;
+    ti.nd = nd;
+    for (int d = 0; d < 4; d++) ti.dims[d] = d < nd ? ti.d.dims[d] : 1;
+    if (ti.d.kind == YOTA_T_INPUT) P.n_in = std::max(P.n_in, ti.d.slot + 1);
+    if (ti.d.kind == YOTA_T_OUTPUT) P.n_out = std::max(P.n_out, ti.d.slot + 1);
+    if ((ti.d.kind == YOTA_T_CONST || ti.d.kind == YOTA_T_SEED) && ti.d.ndim != 0) {
+      set_error("tensor %lld: constants and the seed must be 0-dim", (long long)t);
+      return fail(YOTA_E_SHAPE);
+    }
+  }
+  for (size_t i = 0; i < P.ops.size(); i++) {
+    const yota_op_desc& o = P.ops[i];
+    if (o.out >= 0 && o.out < n_tensors) {
+      if (P.T[o.out].producer >= 0) {
+        set_error("tensor %d has two writers (ops must be SSA)", o.out);
+        return fail(YOTA_E_ARG);
+      }
+      P.T[o.out].producer = (int)i;
+    }
+    for (int j = 0; j < o.n_in && j < YOTA_MAX_OP_INPUTS; j++)
+      if (o.in[j] >= 0 && o.in[j] < n_tensors) P.T[o.in[j]].consumers.push_back((int)i);
+  }
+  int st = validate(P);
+  if (st) return fail(st);
+  // dead-code elimination
+  P.op_needed.assign(P.ops.size(), 0);
+  for (int i = (int)P.ops.size() - 1; i >= 0; i--) {
+    const yota_op_desc& o = P.ops[i];
+    bool need = P.T[o.out].d.kind == YOTA_T_OUTPUT;
+    for (int c : P.T[o.out].consumers) need |= (bool)P.op_needed[c];
+    P.op_needed[i] = need;
+    P.T[o.out].needed = need;
+  }
+  for (auto& t : P.T)
+    if (t.d.kind == YOTA_T_OUTPUT && t.producer < 0) {
+      set_error("an OUTPUT tensor has no producer");
+      return fail(YOTA_E_ARG);
+    }
+  if ((st = plan_fusion(P))) return fail(st);
+  for (size_t r = 0; r < P.regions.size(); r++)
+    if ((st = codegen_region(P, (int)r))) return fail(st);
+  if ((st = finish_steps(P))) return fail(st);
+  if ((st = plan_memory(P))) return fail(st);
+  P.n_launches = 0;
+  for (auto& s : P.steps) P.n_launches += (s.kind == STEP_UNGETINDEX) ? 8 : 1;
+  *out = Pp;
+  return YOTA_OK;
+}
+
+extern "C" int64_t yota_program_describe(yota_program* p, char* buf, int64_t cap) {
+  if (!p) return 0;
+  std::string s;
+  char line[512];
+  snprintf(line, sizeof(line), "program: %zu ops, %zu steps, %zu regions (%d static), arena %zu bytes\n", p->ops.size(),
+           p->steps.size(), p->regions.size(), p->n_static, p->arena_bytes);
+  s += line;
+  for (size_t i = 0; i < p->steps.size(); i++) {
+    snprintf(line, sizeof(line), "  step %zu: %s\n", i, p->steps[i].label.c_str());
+    s += line;
+  }
+  if (buf && cap > 0) {
+    const size_t n = std::min((size_t)cap - 1, s.size());
+    memcpy(buf, s.data(), n);
+    buf[n] = 0;
+  }
+  return (int64_t)s.size();
+}
+
+extern "C" int yota_program_stats(yota_program* p, int64_t* n_steps, int64_t* n_launches, int64_t* workspace_bytes,
+                                  int64_t* n_fused_regions, int64_t* n_static_kernels) {
+  if (!p) YOTA_FAIL(YOTA_E_ARG, "null program");
+  if (n_steps) *n_steps = (int64_t)p->steps.size();
+  if (n_launches) *n_launches = p->n_launches;
+  if (workspace_bytes) *workspace_bytes = (int64_t)p->arena_bytes;
+  if (n_fused_regions) *n_fused_regions = (int64_t)p->regions.size();
+  if (n_static_kernels) *n_static_kernels = p->n_static;
+  return YOTA_OK;
+}
+
+extern "C" int yota_program_destroy(yota_program* p) {
+  if (!p) return YOTA_OK;
+  if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
+  for (auto e : p->ar_events) cudaEventDestroy(e);
+  if (p->arena) cudaFree(p->arena);
+  delete p;
+  return YOTA_OK;
+}
+
+// ==========================================================================================
+// executor
+// ==========================================================================================
+namespace yota {
+
+static void* tensor_ptr(yota_program& P, int t) {
+  const int r = root_of(P, t);
+  const TInfo& ti = P.T[r];
+  switch (ti.d.kind) {
+    case YOTA_T_INPUT: return P.bound_in[ti.d.slot];
+    case YOTA_T_OUTPUT: return P.bound_out[ti.d.slot];
+    case YOTA_T_CONST:
+    case YOTA_T_SEED: return P.arena + (size_t)ti.const_index * 256;
+    default: return ti.arena_off >= 0 ? P.arena + ti.arena_off : nullptr;
+  }
+}
+
+static int ensure_arena(yota_program& P) {
+  if (P.arena) return YOTA_OK;
+  YOTA_TRY(ctx_ensure_device(P.ctx));
+  const size_t bytes = std::max<size_t>(P.arena_bytes, 256);
+  cudaError_t e = cudaMalloc((void**)&P.arena, bytes);
+  if (e != cudaSuccess) {
+    P.arena = nullptr;
+    YOTA_FAIL(YOTA_E_NOMEM, "cannot allocate the program arena (%zu bytes): %s", bytes, cudaGetErrorString(e));
+  }
+  for (size_t i = 0; i < P.const_tensors.size(); i++) {
+    const TInfo& t = P.T[P.const_tensors[i]];
+    if (t.d.kind == YOTA_T_CONST) {
+      const float v = (float)t.d.cval;
+      YOTA_CUDA(cudaMemcpyAsync(P.arena + i * 256, &v, sizeof(float), cudaMemcpyHostToDevice, P.ctx->stream));
+    }
+  }
+  YOTA_CUDA(cudaStreamSynchronize(P.ctx->stream));
+  return YOTA_OK;
+}
+
+static int run_step(yota_program& P, Step& st, cudaStream_t s) {
+  switch (st.kind) {
+    case STEP_REGION: {
+      Region& r = P.regions[st.region];
+      RegionLaunch L = r.L;
+      const int n_store = L.p.n_out - (int)r.sums.size();
+      for (int q = 0; q < L.p.n_in; q++) {
+        L.p.in[q].ptr = static_cast<const float*>(tensor_ptr(P, r.in_tensors[q]));
+        if (L.V == 4 && (reinterpret_cast<uintptr_t>(L.p.in[q].ptr) & 15) &&
+            (L.p.in[q].cls == CLS_FULL || L.p.in[q].cls == CLS_ROWVEC))
+          YOTA_FAIL(YOTA_E_ARG, "array bound to the program is not 16-byte aligned (use yota_alloc)");
+      }
+      for (int q = 0; q < L.p.n_out; q++) {
+        if (q < n_store) {
+          L.p.out[q].ptr = static_cast<float*>(tensor_ptr(P, r.out_tensors[q]));
+          if (L.V == 4 && (reinterpret_cast<uintptr_t>(L.p.out[q].ptr) & 15))
+            YOTA_FAIL(YOTA_E_ARG, "array bound to the program is not 16-byte aligned (use yota_alloc)");
+        } else
+          L.p.out[q].ptr = reinterpret_cast<float*>(P.arena + r.ws_off[q]);
+      }
+      return launch_region(L, s);
+    }
+    case STEP_ROWSUM_FINISH:
+      return launch_rowsum_finish(static_cast<float*>(tensor_ptr(P, st.out_tensor)),
+                                  reinterpret_cast<const float*>(P.arena + st.ws_off), st.R, st.P, st.scale, s);
+    case STEP_SCALAR_FINISH:
+      return launch_scalar_finish(static_cast<float*>(tensor_ptr(P, st.out_tensor)),
+                                  reinterpret_cast<const float*>(P.arena + st.ws_off), st.P, st.scale, s);
+    default: break;
+  }
+  const yota_op_desc& o = P.ops[st.op];
+  float* out = static_cast<float*>(tensor_ptr(P, o.out));
+  const float* in0 = static_cast<const float*>(tensor_ptr(P, o.in[0]));
+  const TInfo& ot = P.T[o.out];
+  switch (st.kind) {
+    case STEP_COLSUM: return launch_colsum(out, in0, st.R, st.C, st.scale, s);
+    case STEP_GENERIC_SUM: {
+      const TInfo& x = P.T[o.in[0]];
+      GenericSum g{};
+      g.nd = x.nd;
+      for (int d = 0; d < 4; d++) g.dims[d] = x.dims[d];
+      g.mask = (unsigned)o.iattr[0] & ((1u << x.nd) - 1);
+      g.scale = st.scale;
+      return launch_generic_sum(g, out, in0, s);
+    }
+    case STEP_GENERIC_EW: {
+      GenericEw g{};
+      g.opcode = o.opcode;
+      g.nd = ot.nd;
+      g.imm = (float)o.fattr[0];
+      const TInfo& a = P.T[o.in[0]];
+      const TInfo& b = P.T[o.in[o.n_in > 1 ? 1 : 0]];
+      long long sa = 1, sb = 1;
+      for (int d = 0; d < 4; d++) {
+        g.dims[d] = ot.dims[d];
+        g.sa[d] = (d < a.nd && a.dims[d] != 1) ? sa : 0;
+        g.sb[d] = (d < b.nd && b.dims[d] != 1) ? sb : 0;
+        sa *= d < a.nd ? a.dims[d] : 1;
+        sb *= d < b.nd ? b.dims[d] : 1;
+      }
+      const float* in1 = o.n_in > 1 ? static_cast<const float*>(tensor_ptr(P, o.in[1])) : nullptr;
+      return launch_generic_ew(g, out, in0, in1, s);
+    }
+    case STEP_GEMM: {
+      const TInfo &A = P.T[o.in[0]], &B = P.T[o.in[1]];
+      GemmArgs g{};
+      g.transA = (int)o.iattr[0];
+      g.transB = (int)o.iattr[1];
+      const long long ar = A.d.ndim >= 1 ? A.d.dims[0] : 1, ac = A.d.ndim == 2 ? A.d.dims[1] : 1;
+      const long long br = B.d.ndim >= 1 ? B.d.dims[0] : 1, bc = B.d.ndim == 2 ? B.d.dims[1] : 1;
+      g.M = g.transA ? ac : ar;
+      g.K = g.transA ? ar : ac;
+      g.N = g.transB ? br : bc;
+      g.A = in0;
+      g.lda = ar;
+      g.B = static_cast<const float*>(tensor_ptr(P, o.in[1]));
+      g.ldb = br;
+      g.C = out;
+      g.ldc = g.M;
+      g.accumulate = 0;
+      g.mode = (P.flags & YOTA_FLAG_GEMM_TF32) ? 1 : (P.flags & YOTA_FLAG_GEMM_BF16) ? 2 : 0;
+      if (g.mode != 0 && gemm_tc_eligible(g)) return launch_gemm_tc(P.ctx, g, s);
+      return launch_gemm_ffma(g, s);
+    }
+    case STEP_GETINDEX:
+    case STEP_UNGETINDEX: {
+      IndexSpec sp;
+      long long nsel;
+      const TInfo& x = st.kind == STEP_GETINDEX ? P.T[o.in[0]] : ot;
+      YOTA_TRY(index_spec_of(P, o, x, sp, &nsel));
+      for (int d = 0; d < sp.n; d++)
+        if (sp.kind[d] == YOTA_IDX_VEC)
+          sp.vec[d] = static_cast<const int64_t*>(tensor_ptr(P, o.in[1 + (int)sp.a[d]]));
+      if (st.kind == STEP_GETINDEX) return launch_getindex(sp, out, in0, ot.numel, s);
+      return launch_ungetindex(sp, out, in0, st.ws_off >= 0 ? P.arena + st.ws_off : nullptr, st.ws_bytes,
+                               P.ctx->sm_count, s);
+    }
+    case STEP_LOGSOFTMAX: {
+      const TInfo& x = P.T[o.in[0]];
+      const long long R = x.nd >= 1 ? x.dims[0] : 1;
+      return launch_logsoftmax(out, in0, R, x.numel / std::max(1ll, R), s);
+    }
+    case STEP_TRANSPOSE: {
+      const TInfo& x = P.T[o.in[0]];
+      const long long R = x.d.ndim >= 1 ? x.d.dims[0] : 1, C = x.d.ndim == 2 ? x.d.dims[1] : 1;
+      if (R == 1 || C == 1) {  // vector <-> row matrix: same memory
+        YOTA_CUDA(cudaMemcpyAsync(out, in0, (size_t)x.numel * 4, cudaMemcpyDeviceToDevice, s));
+        return YOTA_OK;
+      }
+      return launch_transpose(out, in0, R, C, s);
+    }
+    case STEP_CAT: {
+      const int dim = (int)o.iattr[0] - 1;
+      long long odims[4], ostr[4];
+      for (int d = 0; d < 4; d++) odims[d] = d < ot.d.ndim ? ot.d.dims[d] : 1;
+      ostr[0] = 1;
+      for (int d = 1; d < 4; d++) ostr[d] = ostr[d - 1] * odims[d - 1];
+      long long off = 0;
+      for (int j = 0; j < o.n_in; j++) {
+        const TInfo& x = P.T[o.in[j]];
+        long long xd[4], xs[4];
+        for (int d = 0; d < 4; d++) xd[d] = d < x.d.ndim ? x.d.dims[d] : 1;
+        xs[0] = 1;
+        for (int d = 1; d < 4; d++) xs[d] = xs[d - 1] * xd[d - 1];
+        YOTA_TRY(launch_copy_strided(out + off * ostr[dim], static_cast<const float*>(tensor_ptr(P, o.in[j])), 4, xd,
+                                     ostr, xs, s));
+        off += xd[dim];
+      }
+      return YOTA_OK;
+    }
+    case STEP_SLICE: {
+      const TInfo& x = P.T[o.in[0]];
+      const int dim = (int)o.iattr[0] - 1;
+      long long xd[4], xs[4], od[4], os[4];
+      for (int d = 0; d < 4; d++) xd[d] = d < x.d.ndim ? x.d.dims[d] : 1;
+      for (int d = 0; d < 4; d++) od[d] = xd[d];
+      od[dim] = o.iattr[2] - o.iattr[1] + 1;
+      xs[0] = os[0] = 1;
+      for (int d = 1; d < 4; d++) {
+        xs[d] = xs[d - 1] * xd[d - 1];
+        os[d] = os[d - 1] * od[d - 1];
+      }
+      return launch_copy_strided(out, in0 + (o.iattr[1] - 1) * xs[dim], 4, od, os, xs, s);
+    }
+    default: break;
+  }
+  YOTA_FAIL(YOTA_E_UNSUPPORTED_OP, "internal: unknown step kind %d", st.kind);
+}
+
+static int run_all_steps(yota_program& P, cudaStream_t s, bool with_comm) {
+  // which step last writes each all-reduced output
+  std::vector<int> ar_after(P.steps.size(), 0);
+  std::vector<std::vector<int>> ar_at(P.steps.size());
+  if (with_comm) {
+    for (int slot : P.allreduce_slots) {
+      int last = -1;
+      for (size_t q = 0; q < P.steps.size(); q++)
+        for (int t : P.steps[q].writes)
+          if (P.T[t].d.kind == YOTA_T_OUTPUT && P.T[t].d.slot == slot) last = (int)q;
+      if (last >= 0) ar_at[last].push_back(slot);
+    }
+  }
+  size_t ev = 0;
+  for (size_t q = 0; q < P.steps.size(); q++) {
+    YOTA_TRY(run_step(P, P.steps[q], s));
+    if (with_comm && !ar_at[q].empty()) {
+      // bucket = the outputs finished by this step; all-reduce them on the comm stream while
+      // the compute stream continues with the rest of the pullback sweep
+      if (ev >= P.ar_events.size()) {
+        cudaEvent_t e;
+        YOTA_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        P.ar_events.push_back(e);
+      }
+      YOTA_CUDA(cudaEventRecord(P.ar_events[ev], s));
+      YOTA_CUDA(cudaStreamWaitEvent(P.ctx->comm_stream, P.ar_events[ev], 0));
+      ev++;
+      YOTA_TRY(comm_group_start(P.ctx));
+      for (int slot : ar_at[q]) {
+        long long n = 0;
+        for (auto& t : P.T)
+          if (t.d.kind == YOTA_T_OUTPUT && t.d.slot == slot) n = t.numel;
+        YOTA_TRY(comm_allreduce(P.ctx, static_cast<float*>(P.bound_out[slot]), n, P.ctx->comm_stream));
+      }
+      YOTA_TRY(comm_group_end(P.ctx));
+    }
+  }
+  if (with_comm && ev > 0) {
+    // the compute stream (and therefore yota_d2h / yota_sync) waits for the reductions
+    if (ev >= P.ar_events.size()) {
+      cudaEvent_t e;
+      YOTA_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      P.ar_events.push_back(e);
+    }
+    YOTA_CUDA(cudaEventRecord(P.ar_events[ev], P.ctx->comm_stream));
+    YOTA_CUDA(cudaStreamWaitEvent(s, P.ar_events[ev], 0));
+  }
+  return YOTA_OK;
+}
+
+static int bind(yota_program& P, void* const* in_ptrs, int64_t n_in, void* const* out_ptrs, int64_t n_out,
+                bool* changed) {
+  if (n_in < P.n_in || n_out < P.n_out)
+    YOTA_FAIL(YOTA_E_ARG, "yota_program_run: program needs %d inputs / %d outputs", P.n_in, P.n_out);
+  *changed = (int)P.bound_in.size() != P.n_in || (int)P.bound_out.size() != P.n_out;
+  P.bound_in.resize(P.n_in);
+  P.bound_out.resize(P.n_out);
+  for (int i = 0; i < P.n_in; i++) {
+    if (!in_ptrs[i]) YOTA_FAIL(YOTA_E_ARG, "yota_program_run: input %d is null", i);
+    if (P.bound_in[i] != in_ptrs[i]) *changed = true;
+    P.bound_in[i] = in_ptrs[i];
+  }
+  for (int i = 0; i < P.n_out; i++) {
+    if (!out_ptrs[i]) YOTA_FAIL(YOTA_E_ARG, "yota_program_run: output %d is null", i);
+    if (P.bound_out[i] != out_ptrs[i]) *changed = true;
+    P.bound_out[i] = out_ptrs[i];
+  }
+  return YOTA_OK;
+}
+
+static int set_seed(yota_program& P, float seed) {
+  if (P.seed_valid && P.last_seed == seed) return YOTA_OK;
+  for (size_t i = 0; i < P.const_tensors.size(); i++)
+    if (P.T[P.const_tensors[i]].d.kind == YOTA_T_SEED)
+      YOTA_TRY(launch_fill_const(reinterpret_cast<float*>(P.arena + i * 256), seed, P.ctx->stream));
+  P.last_seed = seed;
+  P.seed_valid = true;
+  return YOTA_OK;
+}
+
+}  // namespace yota
+
+extern "C" int yota_program_run(yota_program* p, void* const* in_ptrs, int64_t n_in, void* const* out_ptrs,
+                                int64_t n_out, float seed) {
+  if (!p) YOTA_FAIL(YOTA_E_ARG, "null program");
+  yota_program& P = *p;
+  YOTA_TRY(ensure_arena(P));
+  bool changed = false;
+  YOTA_TRY(bind(P, in_ptrs, n_in, out_ptrs, n_out, &changed));
+  YOTA_TRY(set_seed(P, seed));
+  cudaStream_t s = P.ctx->stream;
+  const bool with_comm = !P.allreduce_slots.empty() && P.ctx->nccl_comm;
+  const bool use_graph = !(P.flags & YOTA_FLAG_NO_GRAPH) && !with_comm;
+  if (changed) {
+    P.runs_with_binding = 0;
+    if (P.graph_exec) {
+      cudaGraphExecDestroy(P.graph_exec);
+      P.graph_exec = nullptr;
+    }
+  }
+  P.runs_with_binding++;
+  if (!use_graph || P.runs_with_binding == 1) return run_all_steps(P, s, with_comm);  // eager (also the warm-up)
+  if (!P.graph_exec) {
+    cudaGraph_t g = nullptr;
+    YOTA_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    const int st = run_all_steps(P, s, false);
+    cudaError_t e = cudaStreamEndCapture(s, &g);
+    if (st != YOTA_OK) {
+      if (g) cudaGraphDestroy(g);
+      return st;
+    }
+    if (e != cudaSuccess) YOTA_FAIL(YOTA_E_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&P.graph_exec, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) {
+      P.graph_exec = nullptr;
+      YOTA_FAIL(YOTA_E_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+    }
+  }
+  YOTA_CUDA(cudaGraphLaunch(P.graph_exec, s));
+  return YOTA_OK;
+}
+
+extern "C" int yota_program_profile(yota_program* p, void* const* in_ptrs, int64_t n_in, void* const* out_ptrs,
+                                    int64_t n_out, float seed, float* step_ms, int64_t cap_steps, char* names,
+                                    int64_t cap_names) {
+  if (!p) YOTA_FAIL(YOTA_E_ARG, "null program");
+  yota_program& P = *p;
+  YOTA_TRY(ensure_arena(P));
+  bool changed = false;
+  YOTA_TRY(bind(P, in_ptrs, n_in, out_ptrs, n_out, &changed));
+  YOTA_TRY(set_seed(P, seed));
+  cudaStream_t s = P.ctx->stream;
+  const size_t n = P.steps.size();
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) YOTA_CUDA(cudaEventCreate(&e));
+  YOTA_CUDA(cudaEventRecord(ev[0], s));
+  for (size_t q = 0; q < n; q++) {
+    YOTA_TRY(run_step(P, P.steps[q], s));
+    YOTA_CUDA(cudaEventRecord(ev[q + 1], s));
+  }
+  YOTA_CUDA(cudaStreamSynchronize(s));
+  std::string nm;
+  for (size_t q = 0; q < n; q++) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev[q], ev[q + 1]);
+    if ((int64_t)q < cap_steps && step_ms) step_ms[q] = ms;
+    nm += P.steps[q].label;
+    if (q + 1 < n) nm += "\n";
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  if (names && cap_names > 0) {
+    const size_t m = std::min((size_t)cap_names - 1, nm.size());
+    memcpy(names, nm.data(), m);
+    names[m] = 0;
+  }
+  return (int)std::min<int64_t>((int64_t)n, cap_steps);
+}
+
+extern "C" int yota_program_set_allreduce(yota_program* p, const int32_t* out_slots, int64_t n) {
+  if (!p) YOTA_FAIL(YOTA_E_ARG, "null program");
+  p->allreduce_slots.assign(out_slots, out_slots + n);
+  for (int s : p->allreduce_slots)
+    if (s < 0 || s >= p->n_out) YOTA_FAIL(YOTA_E_ARG, "yota_program_set_allreduce: bad out slot %d", s);
+  if (p->graph_exec) {
+    cudaGraphExecDestroy(p->graph_exec);
+    p->graph_exec = nullptr;
+  }
+  p->runs_with_binding = 0;
+  return YOTA_OK;
+}
