@@ -418,7 +418,7 @@ struct Fuser {
       do_join(g, best);
       return;
     }
-    if (best < 0 && allow_float) {
+    if (best < 0 && allow_float && group_inputs(g) <= RG_MAX_IN - 2 && g.size() <= 32) {
       out.region = FLOATING;
       return;
     }
@@ -428,19 +428,38 @@ struct Fuser {
         do_join(g, ri);
         return;
       }
-    // a fresh region; if the whole group does not fit one region, split off the producers
+    // a fresh region for the whole group, if it fits one
     unsigned km = ~0u;
     for (int gi : g) km &= op_kmask(gi);
-    if (km != 0 && g.size() <= 40) {
-      const int ri = new_region(out, km & ((1u << (out.nd + 1)) - 1));
-      do_join(g, ri);
+    km &= (1u << (out.nd + 1)) - 1;
+    if (km != 0 && g.size() <= 40 && group_inputs(g) <= RG_MAX_IN) {
+      do_join(g, new_region(out, km));
       return;
     }
-    for (int gi : g) {
-      if (P.T[P.ops[gi].out].region != FLOATING && gi != opi) continue;
-      P.T[P.ops[gi].out].region = -1;
-      do_join({gi}, new_region(P.T[P.ops[gi].out], op_kmask(gi)));
+    // too big: settle the floating producers on their own first, then this op joins them
+    bool any = false;
+    for (int j = 0; j < o.n_in; j++)
+      if (float_input(o, j)) {
+        place(P.T[o.in[j]].producer, false);
+        any = true;
+      }
+    if (any) {
+      place(opi, false);
+      return;
     }
+    do_join({opi}, new_region(out, op_kmask(opi)));
+  }
+
+  int group_inputs(const std::vector<int>& g) const {
+    std::vector<int> ins;
+    for (int opi : g)
+      for (int j = 0; j < P.ops[opi].n_in; j++) {
+        const int t = P.ops[opi].in[j];
+        const int pr = P.T[t].producer;
+        if (pr >= 0 && std::find(g.begin(), g.end(), pr) != g.end()) continue;
+        if (std::find(ins.begin(), ins.end(), t) == ins.end()) ins.push_back(t);
+      }
+    return (int)ins.size();
   }
 
   // a non-elementwise consumer (or the end of the program) needs tensor t in memory

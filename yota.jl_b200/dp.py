@@ -1,0 +1,83 @@
+"""Batch-sharded data parallelism: one process per GPU, the tape replicated, each rank runs
+its column shard of the batch, parameter gradients are summed by NCCL inside
+`yota_program_run` (include/yota_cuda.h: yota_comm_init / yota_program_set_allreduce).
+
+The reference has no multi-device code; the loss is a sum over the batch
+axis (the last dim, contiguous in column-major), so sharding is exact up to FP32 summation
+order.  `torch.distributed` is used only as the rendezvous that ships the ncclUniqueId."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import ffi
+from .device import context
+
+
+def world():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def shard_columns(a, rank, nranks):
+    """Contiguous column (last-dim) shard of a column-major array; ragged tails go to the
+    first ranks."""
+    n = a.shape[-1]
+    base, extra = divmod(n, nranks)
+    lo = rank * base + min(rank, extra)
+    hi = lo + base + (1 if rank < extra else 0)
+    return np.asfortranarray(a[..., lo:hi])
+
+
+def init_process_group():
+    """gloo rendezvous from the torchrun environment (RANK / WORLD_SIZE / MASTER_*)."""
+    import torch.distributed as dist
+
+    if not dist.is_initialized():
+        dist.init_process_group(backend="gloo")
+    return dist
+
+
+def init_comm(ctx=None):
+    """Create the NCCL communicator of this process' context; returns (rank, nranks)."""
+    import torch
+
+    rank, nranks, _ = world()
+    if nranks == 1:
+        return 0, 1
+    dist = init_process_group()
+    ctx = ctx or context()
+    buf = (C.c_ubyte * 128)()
+    if rank == 0:
+        ffi.check(ffi.lib().yota_comm_unique_id(buf))
+    t = torch.tensor(list(bytes(buf)), dtype=torch.uint8)
+    dist.broadcast(t, src=0)
+    idb = (C.c_ubyte * 128)(*t.tolist())
+    ffi.check(ffi.lib().yota_comm_init(ctx.h, rank, nranks, idb))
+    return rank, nranks
+
+
+def param_grad_slots(compiled, n_params):
+    """Out slots of the gradients of the first `n_params` arguments (the replicated
+    parameters); data gradients stay sharded."""
+    return [g[1] for g in compiled.low.grads[:n_params] if isinstance(g, tuple) and g[0] == "out"]
+
+
+def allreduce_host_max(x):
+    """max over ranks of a Python float (timing: max over ranks, never the wall clock)."""
+    import torch
+
+    rank, nranks, _ = world()
+    if nranks == 1:
+        return x
+    dist = init_process_group()
+    t = torch.tensor([x], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0])
+
+
+def barrier():
+    rank, nranks, _ = world()
+    if nranks > 1:
+        init_process_group().barrier()
