@@ -1,0 +1,64 @@
+"""tcgen05 / TMEM tensor-core GEMM (TF32 operands read from Float32 storage, FP32 accumulate)
+through the C ABI (yota_gemm mode 1) and through grad() with YOTA_FLAG_GEMM_TF32.
+
+Stated tolerance of the tensor-core mode: TF32 keeps 10 mantissa bits, so each product
+carries <= 2^-10 relative error; gate = 2e-3 * (|A| |B|) element-wise bound, and gradients
+of the MLP configs within 5e-3 of max|g| against the Float64 oracle.  Small-integer inputs
+are exactly representable in TF32, so those results must be EXACT -- that pins every
+descriptor / swizzle / layout choice of the kernel."""
+import numpy as np
+import pytest
+
+import cases
+import gpu_util as U
+import yota_b200 as Y
+from oracle import yota_oracle as O
+from yota_b200 import ffi
+
+pytestmark = pytest.mark.gpu
+F32 = np.float32
+
+
+@pytest.mark.parametrize("tA,tB", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_tf32_exact_on_small_integers(tA, tB):
+    r = cases.rng(20)
+    for m, n, k in [(128, 128, 32), (128, 256, 64), (384, 640, 160), (1024, 1024, 512)]:
+        A = r.integers(-3, 4, size=(k, m) if tA else (m, k)).astype(F32)
+        B = r.integers(-3, 4, size=(n, k) if tB else (k, n)).astype(F32)
+        ref = (A.T if tA else A).astype(np.float64) @ (B.T if tB else B).astype(np.float64)
+        got = U.gemm(1, tA, tB, np.asfortranarray(A), np.asfortranarray(B))
+        assert np.array_equal(got, ref), (m, n, k)
+        C0 = np.asfortranarray(r.integers(-5, 6, size=(m, n)).astype(F32))
+        got = U.gemm(1, tA, tB, np.asfortranarray(A), np.asfortranarray(B), C0)  # accumulate: C += A*B
+        assert np.array_equal(got, ref + C0)
+
+
+@pytest.mark.parametrize("tA,tB", [(0, 0), (0, 1), (1, 0)])
+def test_tf32_tolerance_on_random_data(tA, tB):
+    r = cases.rng(21)
+    m, n, k = 512, 768, 1024
+    A = r.standard_normal((k, m) if tA else (m, k)).astype(F32)
+    B = r.standard_normal((n, k) if tB else (k, n)).astype(F32)
+    a, b = (A.T if tA else A).astype(np.float64), (B.T if tB else B).astype(np.float64)
+    ref = a @ b
+    got = U.gemm(1, tA, tB, np.asfortranarray(A), np.asfortranarray(B))
+    bound = 2e-3 * (np.abs(a) @ np.abs(b))
+    assert np.all(np.abs(got - ref) <= bound), float(np.max(np.abs(got - ref) / bound))
+
+
+def test_ineligible_shapes_are_refused_not_silently_rerouted():
+    A = np.ones((100, 64), F32, order="F")
+    with pytest.raises(Y.YotaError):
+        U.gemm(1, 0, 0, A, np.ones((64, 130), F32, order="F"))
+
+
+def test_mlp_gradients_in_tf32_mode():
+    """C3 at a tile-aligned scale: forward, dW (NT) and dh (TN) all on tensor cores; small
+    GEMMs of other configs fall through to the FFMA kernel inside the same program."""
+    f, args = cases.make_c3(3, 256), cases.c3_args(3, 256, 256)
+    val, g = Y.grad(f, *map(Y.cu, args), flags=ffi.FLAG_GEMM_TF32)
+    v64, g64 = O.grad(f, *U.to_f64(args), dtype=np.float64)
+    assert abs(val - v64) <= 5e-3 * abs(v64)
+    for a, b in zip(g[1:], g64[1:]):
+        a = a.to_host()
+        assert np.max(np.abs(a - b)) <= 5e-3 * np.max(np.abs(b)), np.max(np.abs(a - b)) / np.max(np.abs(b))

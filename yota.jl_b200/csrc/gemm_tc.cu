@@ -1,9 +1,394 @@
-// tcgen05 / TMEM tensor-core GEMM (placeholder until the kernel lands in this file).
+// Tensor-core GEMM for sm_100a: tcgen05.mma (kind::tf32) with TMEM accumulators, TMA-fed
+// shared-memory pipeline, warp-specialised persistent CTAs.  Hand-written inline PTX; no
+// CUTLASS / cuBLAS.
+//
+// This is the fast path of the matmul rrule (ChainRules rrule(*, A, B): forward A*B (NN),
+// dA = Ȳ*B' (NT), dB = A'*Ȳ (TN) -- dispatched at /root/reference/src/grad.jl:147, forced at
+// src/grad.jl:235).  Operands stay Float32 in HBM and are read by
+// the tensor core as TF32 (10-bit mantissa), accumulation is FP32 in TMEM: stated tolerance
+// ~1e-3 relative (tests/test_gpu_gemm_tc.py); the strict-FP32 FFMA kernel (gemm_ffma.cu)
+// remains the rtol-1e-5 variant.
+//
+// Layout: everything is Julia column-major.  D[M x N] (M contiguous) = op(A)[M x K] op(B)[K x N].
+//   op(A) with M contiguous in memory (A not transposed)  -> "MN-major" A operand
+//   op(A) with K contiguous (A transposed)                 -> "K-major"  A operand
+//   op(B) with K contiguous (B not transposed)             -> "K-major"  B operand
+//   op(B) with N contiguous (B transposed)                 -> "MN-major" B operand
+// so NN / NT / TN / TT need no transposes or copies: TMA loads the tile as it lies in HBM and
+// the smem matrix descriptor tells the tensor core which way it is laid out.
+//   K-major  tile: rows of 32 K-elements (128 B), SWIZZLE_128B;     k-step of 8 = +32 B
+//   MN-major tile: rows of 32 MN-elements (128 B), one row per k, SWIZZLE_128B with 32-byte
+//                  atoms (the only MN-major mode of 32-bit operands); 32-wide MN chunks are
+//                  4 KiB apart (LBO), k-groups of 4 rows 512 B apart (SBO); k-step of 8 = +1 KiB
+//
+// CTA = 6 warps: warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc), warps 2-5 epilogue
+// (TMEM -> registers -> coalesced 128-byte global stores; lane = row m, so a warp writes 32
+// consecutive floats of one column).  4-stage smem ring (48 KiB / stage at 128x256x32), two
+// TMEM accumulator stages (2 x 256 columns) so the epilogue of tile i overlaps the mainloop
+// of tile i+1.  Persistent: grid = min(#tiles, #SMs), static round-robin tile order with the
+// M index fastest so concurrently running CTAs share B panels in L2.
+#include <cuda.h>
+
 #include "common.h"
+
 namespace yota {
-bool gemm_tc_eligible(const GemmArgs& g) { (void)g; return false; }
-int launch_gemm_tc(yota_ctx* ctx, const GemmArgs& g, cudaStream_t s) {
-  (void)ctx; (void)g; (void)s;
-  YOTA_FAIL(YOTA_E_UNSUPPORTED_OP, "tensor-core GEMM not built");
+
+namespace tc {
+
+constexpr int TM = 128;      // tile M (= UMMA M, cta_group::1)
+constexpr int TK = 32;       // tile K in elements = one 128-byte swizzle row
+constexpr int UMMA_K = 8;    // tf32: 32 bytes per MMA k-step
+constexpr int STAGES = 4;
+constexpr int THREADS = 192;
+constexpr int EPI_WARP0 = 2;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// 64-bit shared-memory matrix descriptor (PTX ISA "tcgen05 matrix descriptor")
+//  [0,14) start address >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4
+//  [46,48) version = 1       | [61,64) swizzle: 2 = 128B, 1 = 128B with 32-byte atoms
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+
+struct Params {
+  long long M, N, K;
+  float* C;
+  long long ldc;
+  int accumulate;
+  int num_m, num_n;
+};
+
+template <int TN>
+struct Smem {
+  static constexpr int A_BYTES = TM * TK * 4;
+  static constexpr int B_BYTES = TN * TK * 4;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;  // + barriers + slack for 1 KiB alignment
+};
+
+template <int TN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
+  using S = Smem<TN>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m * p.num_n;
+  const int nkb = (int)(p.K / TK);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; a++) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM: 2 accumulator stages x TN columns (512 when TN = 256)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(2 * TN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (one elected lane) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m0 = (t % p.num_m) * TM, n0 = (t / p.num_m) * TN;
+        for (int kb = 0; kb < nkb; kb++) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], S::STAGE_BYTES);
+          unsigned char* sa = smem + stage * S::STAGE_BYTES;
+          unsigned char* sb = sa + S::A_BYTES;
+          const int k0 = kb * TK;
+          if (A_MN) {
+#pragma unroll
+            for (int c = 0; c < TM / 32; c++) tma_load_2d(sa + c * (TK * 128), &map_a, &full[stage], m0 + 32 * c, k0);
+          } else {
+            tma_load_2d(sa, &map_a, &full[stage], k0, m0);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int c = 0; c < TN / 32; c++) tma_load_2d(sb + c * (TK * 128), &map_b, &full[stage], n0 + 32 * c, k0);
+          } else {
+            tma_load_2d(sb, &map_b, &full[stage], k0, n0);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one elected lane) =====================
+    if (lane == 0) {
+      // instruction descriptor: D = F32, A = B = TF32, majors, N >> 3, M >> 4
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                             ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * TN;
+        for (int kb = 0; kb < nkb; kb++) {
+          mbar_wait(&full[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
+          const uint32_t sb = sa + S::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < TK / UMMA_K; k++) {
+            const uint64_t da = A_MN ? make_desc(sa + k * (UMMA_K * 128), TK * 128, 512, 1)
+                                     : make_desc(sa + k * (UMMA_K * 4), 16, 1024, 2);
+            const uint64_t db = B_MN ? make_desc(sb + k * (UMMA_K * 128), TK * 128, 512, 1)
+                                     : make_desc(sb + k * (UMMA_K * 4), 16, 1024, 2);
+            umma_tf32(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull[acc]);  // accumulator complete
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps: TMEM -> registers -> global =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const long long m = (long long)(t % p.num_m) * TM + q * 32 + lane;
+      const long long n0 = (long long)(t / p.num_m) * TN;
+      mbar_wait(&tfull[acc], acc_phase);
+      tcgen05_fence_after();
+      float* crow = p.C + m + n0 * p.ldc;
+#pragma unroll 1
+      for (int c = 0; c < TN / 32; c++) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + (uint32_t)(acc * TN + c * 32) + ((uint32_t)(q * 32) << 16);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float* cp = crow + (long long)(c * 32) * p.ldc;
+        if (p.accumulate) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) cp[j * p.ldc] = __uint_as_float(v[j]) + cp[j * p.ldc];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j++) cp[j * p.ldc] = __uint_as_float(v[j]);
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive(&tempty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * TN) : "memory");
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// operand with `mn` rows/cols along MN and `k` along K.
+//   mn_major: memory is [k][mn] (mn contiguous, leading dim ld): dims (mn, k), box (32, TK), 32-byte-atom swizzle
+//   k_major:  memory is [mn][k] (k contiguous):                   dims (k, mn), box (TK, tile_mn), 128B swizzle
+static int make_map(CUtensorMap* map, const float* ptr, long long mn, long long k, long long ld, bool mn_major,
+                    int tile_mn) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) YOTA_FAIL(YOTA_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2], strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2], estr[2] = {1, 1};
+  CUtensorMapSwizzle sw;
+  if (mn_major) {
+    dims[0] = (cuuint64_t)mn;
+    dims[1] = (cuuint64_t)k;
+    box[0] = 32;
+    box[1] = TK;
+    sw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+  } else {
+    dims[0] = (cuuint64_t)k;
+    dims[1] = (cuuint64_t)mn;
+    box[0] = TK;
+    box[1] = (cuuint32_t)tile_mn;
+    sw = CU_TENSOR_MAP_SWIZZLE_128B;
+  }
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) YOTA_FAIL(YOTA_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return YOTA_OK;
+}
+
+template <int TN, bool A_MN, bool B_MN>
+static int launch(const GemmArgs& g, const CUtensorMap& ma, const CUtensorMap& mb, int sm_count, cudaStream_t s) {
+  static bool attr = false;
+  auto kern = gemm_tf32_kernel<TN, A_MN, B_MN>;
+  if (!attr) {
+    YOTA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<TN>::TOTAL));
+    attr = true;
+  }
+  Params p;
+  p.M = g.M;
+  p.N = g.N;
+  p.K = g.K;
+  p.C = g.C;
+  p.ldc = g.ldc;
+  p.accumulate = g.accumulate;
+  p.num_m = (int)(g.M / TM);
+  p.num_n = (int)(g.N / TN);
+  const int tiles = p.num_m * p.num_n;
+  const int grid = tiles < sm_count ? tiles : sm_count;
+  kern<<<grid, THREADS, Smem<TN>::TOTAL, s>>>(ma, mb, p);
+  YOTA_CUDA(cudaGetLastError());
+  return YOTA_OK;
+}
+
+}  // namespace tc
+
+bool gemm_tc_eligible(const GemmArgs& g) {
+  if (g.mode != 1) return false;  // only the TF32 kernel exists so far
+  if (g.M < tc::TM || g.N < 128 || g.K < tc::TK) return false;
+  if (g.M % tc::TM || g.N % 128 || g.K % tc::TK) return false;
+  if ((g.lda | g.ldb) % 4) return false;
+  if ((reinterpret_cast<uintptr_t>(g.A) | reinterpret_cast<uintptr_t>(g.B)) & 15) return false;
+  return true;
+}
+
+int launch_gemm_tc(yota_ctx* ctx, const GemmArgs& g, cudaStream_t s) {
+  if (!gemm_tc_eligible(g)) YOTA_FAIL(YOTA_E_UNSUPPORTED_OP, "gemm: shape not eligible for the tensor-core kernel");
+  const bool A_MN = !g.transA;      // A stored M x K column-major: M contiguous
+  const bool B_MN = g.transB != 0;  // B stored N x K column-major: N contiguous
+  const int TN = (g.N % 256 == 0 && (g.M / tc::TM) * (g.N / 256) >= ctx->sm_count / 2) ? 256 : 128;
+  CUtensorMap ma, mb;
+  YOTA_TRY(tc::make_map(&ma, g.A, g.M, g.K, g.lda, A_MN, tc::TM));
+  YOTA_TRY(tc::make_map(&mb, g.B, g.N, g.K, g.ldb, B_MN, TN));
+#define GO(TNv, a, b) return tc::launch<TNv, a, b>(g, ma, mb, ctx->sm_count, s)
+  if (TN == 256) {
+    if (A_MN && B_MN) GO(256, true, true);
+    if (A_MN && !B_MN) GO(256, true, false);
+    if (!A_MN && B_MN) GO(256, false, true);
+    GO(256, false, false);
+  } else {
+    if (A_MN && B_MN) GO(128, true, true);
+    if (A_MN && !B_MN) GO(128, true, false);
+    if (!A_MN && B_MN) GO(128, false, true);
+    GO(128, false, false);
+  }
+#undef GO
+}
+
 }  // namespace yota
