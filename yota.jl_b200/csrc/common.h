@@ -141,6 +141,7 @@ int launch_fill_const(float* out, float v, cudaStream_t s);
 // static (precompiled) chain registry
 int static_chain_lookup(const RegionParams& p, int V);
 const char* static_chain_name(int id);
+std::string region_signature(const RegionParams& p, int V);
 
 // ---- GEMM (gemm_ffma.cu / gemm_tc.cu) ---------------------------------------------------
 struct GemmArgs {

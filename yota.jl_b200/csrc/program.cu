@@ -70,6 +70,7 @@ struct Region {
   std::vector<int> in_tensors;   // tensor id per RegionIn
   std::vector<int> out_tensors;  // tensor id per RegionOut (for sums: the SUM's output tensor)
   std::vector<int> finish_steps;
+  std::string sig;
   long long ws_off[RG_MAX_OUT];
   int n_partials[RG_MAX_OUT];
 };
@@ -716,6 +717,7 @@ static int codegen_region(yota_program& P, int ri) {
   p.n_slots = n_slots;
   if (n_slots > RG_MAX_SLOTS) YOTA_FAIL(YOTA_E_ARG, "internal: region %d needs %d slots", ri, n_slots);
   region_geometry(r.L, P.ctx->sm_count);
+  r.sig = region_signature(p, r.L.V);
   if (!(P.flags & YOTA_FLAG_NO_STATIC)) r.L.static_id = static_chain_lookup(p, r.L.V);
   if (r.L.static_id >= 0) P.n_static++;
 
@@ -1039,6 +1041,7 @@ extern "C" int64_t yota_program_describe(yota_program* p, char* buf, int64_t cap
   for (size_t i = 0; i < p->steps.size(); i++) {
     snprintf(line, sizeof(line), "  step %zu: %s\n", i, p->steps[i].label.c_str());
     s += line;
+    if (p->steps[i].kind == STEP_REGION) s += "    sig " + p->regions[p->steps[i].region].sig + "\n";
   }
   if (buf && cap > 0) {
     const size_t n = std::min((size_t)cap - 1, s.size());
