@@ -47,7 +47,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True).start()
         except Exception:
             self.proc = None
@@ -227,20 +227,32 @@ def main():
         pinned.append((i, p, hargs[i].nbytes))
         h2d += hargs[i].nbytes
     hloss = np.zeros(1, np.float32)
+    # double-buffered batch: the upload of step i+1 (copy stream) overlaps the sweep of step i
+    bufs = [list(dargs), list(dargs)]
+    for i in bidx:
+        bufs[1][i] = Y.B200Array(dargs[i].dims, dargs[i].dtype, ctx)
 
-    def e2e_step():
+    def upload(k):
         for i, p, nb in pinned:
-            ffi.check(lib.yota_h2d_async(ctx.h, dargs[i].ptr, p, nb))
-        val, _ = gf.run(dargs, out=outs)
-        ffi.check(lib.yota_d2h(ctx.h, hloss.ctypes.data, val.ptr, 4))
+            ffi.check(lib.yota_h2d_async(ctx.h, bufs[k][i].ptr, p, nb))
 
-    for _ in range(2):
-        e2e_step()
+    def e2e_steps(n):
+        upload(0)
+        ffi.check(lib.yota_stream_fence(ctx.h, 1, 0))
+        for it in range(n):
+            k = it & 1
+            ffi.check(lib.yota_stream_fence(ctx.h, 0, 1))  # copy stream: runs <= it-1 are done with buffer k^1
+            val, _ = gf.run(bufs[k], out=outs)
+            if it + 1 < n:
+                upload(k ^ 1)
+            ffi.check(lib.yota_d2h(ctx.h, hloss.ctypes.data, val.ptr, 4))  # the step's result, read every step
+            ffi.check(lib.yota_stream_fence(ctx.h, 1, 0))  # next run waits for its batch
+
+    e2e_steps(4)
     dp.barrier()
     ctx.sync()
     ffi.check(lib.yota_event_record(ctx.h, e0))
-    for _ in range(a.steps):
-        e2e_step()
+    e2e_steps(a.steps)
     ffi.check(lib.yota_event_record(ctx.h, e1))
     ctx.sync()
     dp.barrier()
@@ -262,13 +274,18 @@ def main():
     total_prof = sum(t for _, t in prof)
     dom = max(groups, key=lambda k: groups[k][0])
     roof = None
+    try:
+        traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+    except Exception:
+        traffic_tab = {}
     if dom == "matmul" and wl["gemm_flops"]:
         n_g = groups[dom][1]
         avg_ms = groups[dom][0] / n_g
         ach = wl["gemm_flops"] / n_g / (avg_ms * 1e-3) / 1e12
         peak = pk["tc_sust"] * (0.5 if a.gemm == "tf32" else 1.0)
         roof = {"bound": "tensor", "kernel": f"gemm ({a.gemm})", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                "frac": ach / peak, "traffic": None, "avg_launch_ms": avg_ms, "launches_per_step": n_g,
+                "frac": ach / peak, "traffic": traffic_tab.get(f"gemm ({a.gemm})") if a.workload == "c3" and not a.small else None,
+                "avg_launch_ms": avg_ms, "launches_per_step": n_g,
                 "share_of_step": groups[dom][0] / total_prof,
                 "peak_source": f"{pk['src']} bf16 sustained" + (" x 0.5 (TF32 runs at half the BF16 rate)" if a.gemm == "tf32" else "")
                                + ("; strict-FP32 FFMA kernel, not a tensor-core kernel" if a.gemm == "fp32" else "")}
@@ -276,7 +293,7 @@ def main():
         t_dom = groups[dom][0]
         ach = wl["hbm_bytes"] / (t_dom * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
-                "traffic": None, "avg_launch_ms": t_dom / groups[dom][1], "launches_per_step": groups[dom][1],
+                "traffic": traffic_tab.get(f"{dom}:{a.workload}") if not a.small else None, "avg_launch_ms": t_dom / groups[dom][1], "launches_per_step": groups[dom][1],
                 "share_of_step": t_dom / total_prof, "peak_source": f"{pk['src']} HBM copy"}
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle on a bounded sample -----------------
@@ -302,7 +319,7 @@ def main():
                 "clocks": clocks,
                 "e2e": {"value": 1e3 / e2e_ms, "unit": "evals/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": 4,
-                        "note": "per step: batch (x, Y) uploaded from pinned host memory, loss read back; parameters and gradients stay on the device"},
+                        "note": "per step: batch (x, Y) uploaded from pinned host memory on the copy stream (double-buffered, overlapping the previous sweep), loss read back every step; parameters and gradients stay on the device"},
                 "gpu_launches": int(stats["launches"]) * a.steps,
                 "program": stats,
                 "roofline": roof, "cpu_baseline": cpu,

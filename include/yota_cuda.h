@@ -158,7 +158,12 @@ int yota_d2h(yota_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
 /* pinned host staging (for overlapped uploads of each step's batch) */
 int yota_host_alloc(yota_ctx* ctx, size_t bytes, void** hptr);
 int yota_host_free(yota_ctx* ctx, void* hptr);
+/* Asynchronous upload on the context's COPY stream (overlaps yota_program_run on the compute
+ * stream).  Order the two streams with yota_stream_fence. */
 int yota_h2d_async(yota_ctx* ctx, void* dst_dev, const void* src_pinned, size_t bytes);
+/* Make stream `to` wait for everything enqueued so far on stream `from`
+ * (0 = compute stream, 1 = copy stream). */
+int yota_stream_fence(yota_ctx* ctx, int from, int to);
 int yota_memset(yota_ctx* ctx, void* dptr, int byte, size_t bytes);
 int yota_sync(yota_ctx* ctx);
 

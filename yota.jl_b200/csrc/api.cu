@@ -38,6 +38,8 @@ int ctx_ensure_device(yota_ctx* ctx) {
               pr.minor);
   YOTA_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   YOTA_CUDA(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+  YOTA_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  YOTA_CUDA(cudaEventCreateWithFlags(&ctx->fence_event, cudaEventDisableTiming));
   ctx->device_ready = true;
   return YOTA_OK;
 }
@@ -88,6 +90,8 @@ int yota_shutdown(yota_ctx* ctx) {
     if (ctx->scratch) cudaFree(ctx->scratch);
     cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->comm_stream);
+    cudaStreamDestroy(ctx->copy_stream);
+    cudaEventDestroy(ctx->fence_event);
   }
   delete ctx;
   return YOTA_OK;
@@ -171,7 +175,16 @@ int yota_host_free(yota_ctx* ctx, void* hptr) {
 int yota_h2d_async(yota_ctx* ctx, void* dst, const void* src, size_t bytes) {
   if (!ctx) YOTA_FAIL(YOTA_E_ARG, "null ctx");
   YOTA_TRY(ctx_ensure_device(ctx));
-  YOTA_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  YOTA_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+  return YOTA_OK;
+}
+
+int yota_stream_fence(yota_ctx* ctx, int from, int to) {
+  if (!ctx || from == to || from < 0 || from > 1 || to < 0 || to > 1) YOTA_FAIL(YOTA_E_ARG, "yota_stream_fence: bad arguments");
+  YOTA_TRY(ctx_ensure_device(ctx));
+  cudaStream_t s[2] = {ctx->stream, ctx->copy_stream};
+  YOTA_CUDA(cudaEventRecord(ctx->fence_event, s[from]));
+  YOTA_CUDA(cudaStreamWaitEvent(s[to], ctx->fence_event, 0));
   return YOTA_OK;
 }
 
@@ -187,6 +200,7 @@ int yota_sync(yota_ctx* ctx) {
   YOTA_TRY(ctx_ensure_device(ctx));
   YOTA_CUDA(cudaStreamSynchronize(ctx->stream));
   YOTA_CUDA(cudaStreamSynchronize(ctx->comm_stream));
+  YOTA_CUDA(cudaStreamSynchronize(ctx->copy_stream));
   return YOTA_OK;
 }
 

@@ -49,6 +49,8 @@ struct yota_ctx {
   bool device_ready = false;  // lazily initialised so that plan-only use works without a GPU
   cudaStream_t stream = nullptr;
   cudaStream_t comm_stream = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t fence_event = nullptr;
   // size-bucketed free lists (caller-owned buffers come and go every grad() call)
   std::multimap<size_t, void*> free_blocks;
   std::map<void*, size_t> live_blocks;

@@ -197,18 +197,28 @@ int launch_region(const RegionLaunch& L, cudaStream_t s) {
 }
 
 // ---- finishers ---------------------------------------------------------------------------
-__global__ void rowsum_finish_kernel(float* __restrict__ out, const float* __restrict__ partial, long long R, int P,
-                                     float scale) {
-  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= R) return;
+// 32 rows x 8 partial-lanes per CTA: lane j folds partials j, j+8, ... in order, then the 8
+// lane sums are folded in order 0..7 -- a fixed order, 8x the parallelism of one thread per row.
+__global__ void __launch_bounds__(256) rowsum_finish_kernel(float* __restrict__ out, const float* __restrict__ partial,
+                                                            long long R, int P, float scale) {
+  __shared__ float sm[8][33];
+  const int rl = threadIdx.x & 31, j = threadIdx.x >> 5;
+  const long long r = (long long)blockIdx.x * 32 + rl;
   float s = 0.f;
-  for (int q = 0; q < P; q++) s = __fadd_rn(s, partial[(long long)q * R + r]);
-  out[r] = scale == 1.f ? s : __fmul_rn(s, scale);
+  if (r < R)
+    for (int q = j; q < P; q += 8) s = __fadd_rn(s, __ldg(partial + (long long)q * R + r));
+  sm[j][rl] = s;
+  __syncthreads();
+  if (j == 0 && r < R) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; q++) t = __fadd_rn(t, sm[q][rl]);
+    out[r] = scale == 1.f ? t : __fmul_rn(t, scale);
+  }
 }
 
 int launch_rowsum_finish(float* out, const float* partial, long long R, int P, float scale, cudaStream_t s) {
-  const int T = 128;
-  rowsum_finish_kernel<<<(unsigned)((R + T - 1) / T), T, 0, s>>>(out, partial, R, P, scale);
+  rowsum_finish_kernel<<<(unsigned)((R + 31) / 32), 256, 0, s>>>(out, partial, R, P, scale);
   YOTA_CUDA(cudaGetLastError());
   return YOTA_OK;
 }

@@ -112,8 +112,14 @@ struct yota_program {
   std::vector<void*> bound_in, bound_out;
   float last_seed = 0.f;
   bool seed_valid = false;
-  int runs_with_binding = 0;
-  cudaGraphExec_t graph_exec = nullptr;
+  struct GraphEntry {
+    std::vector<void*> in, out;
+    cudaGraphExec_t exec = nullptr;
+    int runs = 0;
+    long long last_use = 0;
+  };
+  std::vector<GraphEntry> graphs;  // one captured graph per pointer binding (double-buffered batches)
+  long long run_counter = 0;
   std::vector<int> allreduce_slots;
   std::vector<cudaEvent_t> ar_events;
 };
@@ -1064,7 +1070,8 @@ extern "C" int yota_program_stats(yota_program* p, int64_t* n_steps, int64_t* n_
 
 extern "C" int yota_program_destroy(yota_program* p) {
   if (!p) return YOTA_OK;
-  if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
+  for (auto& g : p->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
   for (auto e : p->ar_events) cudaEventDestroy(e);
   if (p->arena) cudaFree(p->arena);
   delete p;
@@ -1350,16 +1357,29 @@ extern "C" int yota_program_run(yota_program* p, void* const* in_ptrs, int64_t n
   cudaStream_t s = P.ctx->stream;
   const bool with_comm = !P.allreduce_slots.empty() && P.ctx->nccl_comm;
   const bool use_graph = !(P.flags & YOTA_FLAG_NO_GRAPH) && !with_comm;
-  if (changed) {
-    P.runs_with_binding = 0;
-    if (P.graph_exec) {
-      cudaGraphExecDestroy(P.graph_exec);
-      P.graph_exec = nullptr;
+  (void)changed;
+  if (!use_graph) return run_all_steps(P, s, with_comm);
+  // one graph per pointer binding: eager on the first run with a binding (also the warm-up
+  // that sets function attributes), captured on the second, replayed afterwards
+  yota_program::GraphEntry* ge = nullptr;
+  for (auto& g : P.graphs)
+    if (g.in == P.bound_in && g.out == P.bound_out) ge = &g;
+  if (!ge) {
+    if (P.graphs.size() >= 8) {  // evict the least recently used binding
+      size_t lru = 0;
+      for (size_t i = 1; i < P.graphs.size(); i++)
+        if (P.graphs[i].last_use < P.graphs[lru].last_use) lru = i;
+      if (P.graphs[lru].exec) cudaGraphExecDestroy(P.graphs[lru].exec);
+      P.graphs.erase(P.graphs.begin() + lru);
     }
+    P.graphs.emplace_back();
+    ge = &P.graphs.back();
+    ge->in = P.bound_in;
+    ge->out = P.bound_out;
   }
-  P.runs_with_binding++;
-  if (!use_graph || P.runs_with_binding == 1) return run_all_steps(P, s, with_comm);  // eager (also the warm-up)
-  if (!P.graph_exec) {
+  ge->last_use = ++P.run_counter;
+  if (++ge->runs == 1) return run_all_steps(P, s, false);
+  if (!ge->exec) {
     cudaGraph_t g = nullptr;
     YOTA_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
     const int st = run_all_steps(P, s, false);
@@ -1369,14 +1389,14 @@ extern "C" int yota_program_run(yota_program* p, void* const* in_ptrs, int64_t n
       return st;
     }
     if (e != cudaSuccess) YOTA_FAIL(YOTA_E_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
-    e = cudaGraphInstantiate(&P.graph_exec, g, 0);
+    e = cudaGraphInstantiate(&ge->exec, g, 0);
     cudaGraphDestroy(g);
     if (e != cudaSuccess) {
-      P.graph_exec = nullptr;
+      ge->exec = nullptr;
       YOTA_FAIL(YOTA_E_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
     }
   }
-  YOTA_CUDA(cudaGraphLaunch(P.graph_exec, s));
+  YOTA_CUDA(cudaGraphLaunch(ge->exec, s));
   return YOTA_OK;
 }
 
@@ -1421,10 +1441,8 @@ extern "C" int yota_program_set_allreduce(yota_program* p, const int32_t* out_sl
   p->allreduce_slots.assign(out_slots, out_slots + n);
   for (int s : p->allreduce_slots)
     if (s < 0 || s >= p->n_out) YOTA_FAIL(YOTA_E_ARG, "yota_program_set_allreduce: bad out slot %d", s);
-  if (p->graph_exec) {
-    cudaGraphExecDestroy(p->graph_exec);
-    p->graph_exec = nullptr;
-  }
-  p->runs_with_binding = 0;
+  for (auto& g : p->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  p->graphs.clear();
   return YOTA_OK;
 }
