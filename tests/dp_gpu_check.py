@@ -1,0 +1,43 @@
+"""Run under torchrun on N GPUs (gpurun --gpus N): batch-sharded grads + NCCL all-reduce must
+equal the single-GPU full-batch grads (FP32 summation order aside)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import cases  # noqa: E402
+import yota_b200 as Y  # noqa: E402
+from yota_b200 import dp, ffi  # noqa: E402
+
+rank, nranks, local = dp.world()
+ctx = Y.context(local)
+dp.init_comm(ctx)
+for mode, flags, tol in (("fp32", 0, 2e-5), ("tf32", ffi.FLAG_GEMM_TF32, 5e-3)):
+    L, W, B = 3, 256, 256 * nranks
+    args = cases.c3_args(L, W, B)
+    f = cases.make_c3(L, B)
+    full = [Y.cu(a) for a in args]
+    fv, fg = Y.grad(f, *full, flags=flags)  # replicated full-batch reference on every rank
+    shard = list(args)
+    shard[-2], shard[-1] = dp.shard_columns(args[-2], rank, nranks), dp.shard_columns(args[-1], rank, nranks)
+    dsh = [Y.cu(a) for a in shard]
+    gf = Y.CompiledGrad(Y.gradtape(f, *dsh), ctx, flags)
+    gf.set_allreduce(dp.param_grad_slots(gf, 2 * L) + [gf.low.val[1]])
+    for it in range(3):  # eager + repeated runs
+        val, g = gf.run(dsh)
+        ctx.sync()
+    v = float(val.to_host())
+    assert abs(v - fv) <= tol * abs(fv), (mode, v, fv)
+    for i in range(2 * L):
+        a, b = g[i].to_host(), fg[1 + i].to_host()
+        err = np.abs(a - b).max() / np.abs(b).max()
+        assert err <= tol, (mode, i, err)
+    for i in (2 * L, 2 * L + 1):  # data grads stay sharded
+        a, b = g[i].to_host(), dp.shard_columns(fg[1 + i].to_host(), rank, nranks)
+        assert np.abs(a - b).max() <= tol * np.abs(b).max(), (mode, i)
+    dp.barrier()
+    if rank == 0:
+        print(f"DP_GPU_OK mode={mode} nranks={nranks} loss={v:.6f}", flush=True)
