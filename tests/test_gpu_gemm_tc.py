@@ -62,3 +62,38 @@ def test_mlp_gradients_in_tf32_mode():
     for a, b in zip(g[1:], g64[1:]):
         a = a.to_host()
         assert np.max(np.abs(a - b)) <= 5e-3 * np.max(np.abs(b)), np.max(np.abs(a - b)) / np.max(np.abs(b))
+
+
+# ---- BF16 operand mode (BF16 shadows of the Float32 arrays, FP32 accumulate in TMEM) -------
+@pytest.mark.parametrize("tA,tB", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_bf16_exact_on_small_integers(tA, tB):
+    r = cases.rng(22)
+    for m, n, k in [(128, 128, 64), (128, 256, 128), (384, 640, 192), (1024, 1024, 512)]:
+        A = r.integers(-3, 4, size=(k, m) if tA else (m, k)).astype(F32)
+        B = r.integers(-3, 4, size=(n, k) if tB else (k, n)).astype(F32)
+        ref = (A.T if tA else A).astype(np.float64) @ (B.T if tB else B).astype(np.float64)
+        got = U.gemm(2, tA, tB, np.asfortranarray(A), np.asfortranarray(B))
+        assert np.array_equal(got, ref), (m, n, k)
+
+
+@pytest.mark.parametrize("tA,tB", [(0, 0), (0, 1), (1, 0)])
+def test_bf16_tolerance_on_random_data(tA, tB):
+    r = cases.rng(23)
+    m, n, k = 512, 768, 1024
+    A = r.standard_normal((k, m) if tA else (m, k)).astype(F32)
+    B = r.standard_normal((n, k) if tB else (k, n)).astype(F32)
+    a, b = (A.T if tA else A).astype(np.float64), (B.T if tB else B).astype(np.float64)
+    ref = a @ b
+    got = U.gemm(2, tA, tB, np.asfortranarray(A), np.asfortranarray(B))
+    bound = 1.2e-2 * (np.abs(a) @ np.abs(b))  # two operands rounded to 8 significant bits: 2 * 2^-9 per product
+    assert np.all(np.abs(got - ref) <= bound), float(np.max(np.abs(got - ref) / bound))
+
+
+def test_mlp_gradients_in_bf16_mode():
+    f, args = cases.make_c3(3, 256), cases.c3_args(3, 256, 256)
+    val, g = Y.grad(f, *map(Y.cu, args), flags=ffi.FLAG_GEMM_BF16)
+    v64, g64 = O.grad(f, *U.to_f64(args), dtype=np.float64)
+    assert abs(val - v64) <= 2e-2 * abs(v64)
+    for a, b in zip(g[1:], g64[1:]):
+        a = a.to_host()
+        assert np.max(np.abs(a - b)) <= 3e-2 * np.max(np.abs(b)), np.max(np.abs(a - b)) / np.max(np.abs(b))

@@ -237,6 +237,16 @@ int yota_gemm(yota_ctx* ctx, int mode, int transA, int transB, int64_t m, int64_
     if (!gemm_tc_eligible(g))
       YOTA_FAIL(YOTA_E_UNSUPPORTED_OP, "yota_gemm: shape %lldx%lldx%lld is not eligible for the tensor-core kernel",
                 (long long)m, (long long)n, (long long)k);
+    if (mode == 2) {  // BF16 operands: cast shadows of A and B into scratch first
+      const long long na = lda * (transA ? m : k), nb = ldb * (transB ? k : n);
+      const size_t offb = ((size_t)na * 2 + 255) & ~(size_t)255;
+      void* w = nullptr;
+      YOTA_TRY(ctx_scratch(ctx, offb + (size_t)nb * 2 + 256, &w));
+      YOTA_TRY(launch_cast_bf16(w, A, na, ctx->stream));
+      YOTA_TRY(launch_cast_bf16(static_cast<char*>(w) + offb, B, nb, ctx->stream));
+      g.A = w;
+      g.B = static_cast<char*>(w) + offb;
+    }
     return launch_gemm_tc(ctx, g, ctx->stream);
   }
   return launch_gemm_ffma(g, ctx->stream);

@@ -150,9 +150,9 @@ struct GemmArgs {
   int mode;  // 0 fp32 ffma, 1 tf32 tcgen05, 2 bf16 tcgen05
   int transA, transB;
   long long M, N, K;
-  const float* A;
+  const void* A;  // Float32 (modes 0, 1) or BF16 shadow (mode 2)
   long long lda;
-  const float* B;
+  const void* B;
   long long ldb;
   float* C;
   long long ldc;
@@ -161,6 +161,7 @@ struct GemmArgs {
 int launch_gemm_ffma(const GemmArgs& g, cudaStream_t s);
 int launch_gemm_tc(yota_ctx* ctx, const GemmArgs& g, cudaStream_t s);  // returns YOTA_E_UNSUPPORTED_OP if shape not eligible
 bool gemm_tc_eligible(const GemmArgs& g);
+int launch_cast_bf16(void* dst, const float* src, long long n, cudaStream_t s);
 
 // ---- indexing (index_kernels.cu) --------------------------------------------------------
 struct IndexSpec {

@@ -147,7 +147,8 @@ int launch_gemm_ffma(const GemmArgs& g, cudaStream_t s) {
   if (grid.y > 65535) YOTA_FAIL(YOTA_E_SHAPE, "gemm: N too large for the FFMA kernel grid");
   const bool AM = !g.transA, BNc = g.transB != 0;
 #define LAUNCH(a, b) \
-  gemm_ffma_kernel<a, b><<<grid, GT, 0, s>>>(g.M, g.N, g.K, g.A, sam, sak, g.B, sbk, sbn, g.C, g.ldc, g.accumulate)
+  gemm_ffma_kernel<a, b><<<grid, GT, 0, s>>>(g.M, g.N, g.K, static_cast<const float*>(g.A), sam, sak,          \
+                                             static_cast<const float*>(g.B), sbk, sbn, g.C, g.ldc, g.accumulate)
   if (AM && BNc)
     LAUNCH(true, true);
   else if (AM && !BNc)

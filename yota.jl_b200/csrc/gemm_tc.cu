@@ -28,6 +28,7 @@
 // of tile i+1.  Persistent: grid = min(#tiles, #SMs), static round-robin tile order with the
 // M index fastest so concurrently running CTAs share B panels in L2.
 #include <cuda.h>
+#include <cuda_bf16.h>
 
 #include "common.h"
 
@@ -36,9 +37,20 @@ namespace yota {
 namespace tc {
 
 constexpr int TM = 128;      // tile M (= UMMA M, cta_group::1)
-constexpr int TK = 32;       // tile K in elements = one 128-byte swizzle row
-constexpr int UMMA_K = 8;    // tf32: 32 bytes per MMA k-step
 constexpr int STAGES = 4;
+// EB = operand element bytes: 4 (Float32 read as TF32) or 2 (BF16 shadows of the Float32 arrays).
+// A tile row is always one 128-byte swizzle row: TK = 128/EB elements; one MMA consumes 32 bytes
+// of K: UMMA_K = 32/EB.  MN-major tiles: 128-byte rows of 128/EB MN-elements, one row per k.
+template <int EB>
+struct El {
+  static constexpr int TK = 128 / EB;
+  static constexpr int UMMA_K = 32 / EB;
+  static constexpr int CHUNK = 128 / EB;                 // MN elements per 128-byte row
+  static constexpr int CHUNK_BYTES = TK * 128;            // one MN-major box: TK rows x 128 B
+  static constexpr int MN_SBO = EB == 4 ? 512 : 1024;     // k-group stride: 4-row (32B-atom) / 8-row atoms
+  static constexpr int MN_LAYOUT = EB == 4 ? 1 : 2;       // SWIZZLE_128B_BASE32B / SWIZZLE_128B
+  static constexpr int MN_KSTEP = UMMA_K * 128;           // bytes per MMA k-step in an MN-major tile
+};
 constexpr int THREADS = 192;
 constexpr int EPI_WARP0 = 2;
 
@@ -91,6 +103,18 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
       : "memory");
 }
 
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // 64-bit shared-memory matrix descriptor (PTX ISA "tcgen05 matrix descriptor")
 //  [0,14) start address >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4
 //  [46,48) version = 1       | [61,64) swizzle: 2 = 128B, 1 = 128B with 32-byte atoms
@@ -114,17 +138,19 @@ struct Params {
 
 template <int TN>
 struct Smem {
-  static constexpr int A_BYTES = TM * TK * 4;
-  static constexpr int B_BYTES = TN * TK * 4;
+  static constexpr int A_BYTES = TM * 128;  // TM rows (or TM*EB/128 chunks of TK rows) of 128 bytes
+  static constexpr int B_BYTES = TN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;  // + barriers + slack for 1 KiB alignment
 };
 
-template <int TN, bool A_MN, bool B_MN>
+template <int TN, bool A_MN, bool B_MN, int EB>
 __global__ void __launch_bounds__(THREADS, 1)
-gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
   using S = Smem<TN>;
+  using E = El<EB>;
+  constexpr int TK = E::TK;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
@@ -135,7 +161,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = p.num_m * p.num_n;
-  const int nkb = (int)(p.K / TK);
+  const int nkb = (int)(p.K / (128 / EB));
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; s++) {
@@ -178,13 +204,15 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const int k0 = kb * TK;
           if (A_MN) {
 #pragma unroll
-            for (int c = 0; c < TM / 32; c++) tma_load_2d(sa + c * (TK * 128), &map_a, &full[stage], m0 + 32 * c, k0);
+            for (int c = 0; c < TM / E::CHUNK; c++)
+              tma_load_2d(sa + c * E::CHUNK_BYTES, &map_a, &full[stage], m0 + E::CHUNK * c, k0);
           } else {
             tma_load_2d(sa, &map_a, &full[stage], k0, m0);
           }
           if (B_MN) {
 #pragma unroll
-            for (int c = 0; c < TN / 32; c++) tma_load_2d(sb + c * (TK * 128), &map_b, &full[stage], n0 + 32 * c, k0);
+            for (int c = 0; c < TN / E::CHUNK; c++)
+              tma_load_2d(sb + c * E::CHUNK_BYTES, &map_b, &full[stage], n0 + E::CHUNK * c, k0);
           } else {
             tma_load_2d(sb, &map_b, &full[stage], k0, n0);
           }
@@ -198,8 +226,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   } else if (warp == 1) {
     // ===================== MMA issuer (one elected lane) =====================
     if (lane == 0) {
-      // instruction descriptor: D = F32, A = B = TF32, majors, N >> 3, M >> 4
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+      // instruction descriptor: D = F32, A = B = TF32 (2) or BF16 (1), majors, N >> 3, M >> 4
+      constexpr uint32_t FMT = EB == 4 ? 2u : 1u;
+      const uint32_t idesc = (1u << 4) | (FMT << 7) | (FMT << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                              ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
@@ -215,12 +244,15 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
           const uint32_t sb = sa + S::A_BYTES;
 #pragma unroll
-          for (int k = 0; k < TK / UMMA_K; k++) {
-            const uint64_t da = A_MN ? make_desc(sa + k * (UMMA_K * 128), TK * 128, 512, 1)
-                                     : make_desc(sa + k * (UMMA_K * 4), 16, 1024, 2);
-            const uint64_t db = B_MN ? make_desc(sb + k * (UMMA_K * 128), TK * 128, 512, 1)
-                                     : make_desc(sb + k * (UMMA_K * 4), 16, 1024, 2);
-            umma_tf32(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; k++) {  // 4 MMA k-steps of 32 bytes per 128-byte stage
+            const uint64_t da = A_MN ? make_desc(sa + k * E::MN_KSTEP, E::CHUNK_BYTES, E::MN_SBO, E::MN_LAYOUT)
+                                     : make_desc(sa + k * 32, 16, 1024, 2);
+            const uint64_t db = B_MN ? make_desc(sb + k * E::MN_KSTEP, E::CHUNK_BYTES, E::MN_SBO, E::MN_LAYOUT)
+                                     : make_desc(sb + k * 32, 16, 1024, 2);
+            if (EB == 4)
+              umma_tf32(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            else
+              umma_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
           if (++stage == STAGES) {
@@ -306,37 +338,39 @@ static EncodeTiledFn encode_fn() {
 // operand with `mn` rows/cols along MN and `k` along K.
 //   mn_major: memory is [k][mn] (mn contiguous, leading dim ld): dims (mn, k), box (32, TK), 32-byte-atom swizzle
 //   k_major:  memory is [mn][k] (k contiguous):                   dims (k, mn), box (TK, tile_mn), 128B swizzle
-static int make_map(CUtensorMap* map, const float* ptr, long long mn, long long k, long long ld, bool mn_major,
-                    int tile_mn) {
+static int make_map(CUtensorMap* map, const void* ptr, long long mn, long long k, long long ld, bool mn_major,
+                    int tile_mn, int eb) {
   EncodeTiledFn enc = encode_fn();
   if (!enc) YOTA_FAIL(YOTA_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-  cuuint64_t dims[2], strides[1] = {(cuuint64_t)ld * 4};
+  cuuint64_t dims[2], strides[1] = {(cuuint64_t)ld * eb};
+  const cuuint32_t tk = 128 / eb;
   cuuint32_t box[2], estr[2] = {1, 1};
   CUtensorMapSwizzle sw;
   if (mn_major) {
     dims[0] = (cuuint64_t)mn;
     dims[1] = (cuuint64_t)k;
-    box[0] = 32;
-    box[1] = TK;
-    sw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+    box[0] = tk;
+    box[1] = tk;
+    sw = eb == 4 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
   } else {
     dims[0] = (cuuint64_t)k;
     dims[1] = (cuuint64_t)mn;
-    box[0] = TK;
+    box[0] = tk;
     box[1] = (cuuint32_t)tile_mn;
     sw = CU_TENSOR_MAP_SWIZZLE_128B;
   }
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+  CUresult r = enc(map, eb == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                   const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) YOTA_FAIL(YOTA_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return YOTA_OK;
 }
 
-template <int TN, bool A_MN, bool B_MN>
+template <int TN, bool A_MN, bool B_MN, int EB>
 static int launch(const GemmArgs& g, const CUtensorMap& ma, const CUtensorMap& mb, int sm_count, cudaStream_t s) {
   static bool attr = false;
-  auto kern = gemm_tf32_kernel<TN, A_MN, B_MN>;
+  auto kern = gemm_tc_kernel<TN, A_MN, B_MN, EB>;
   if (!attr) {
     YOTA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<TN>::TOTAL));
     attr = true;
@@ -360,23 +394,29 @@ static int launch(const GemmArgs& g, const CUtensorMap& ma, const CUtensorMap& m
 }  // namespace tc
 
 bool gemm_tc_eligible(const GemmArgs& g) {
-  if (g.mode != 1) return false;  // only the TF32 kernel exists so far
-  if (g.M < tc::TM || g.N < 128 || g.K < tc::TK) return false;
-  if (g.M % tc::TM || g.N % 128 || g.K % tc::TK) return false;
-  if ((g.lda | g.ldb) % 4) return false;
+  if (g.mode != 1 && g.mode != 2) return false;
+  const int tk = g.mode == 1 ? 32 : 64;
+  if (g.M < tc::TM || g.N < 128 || g.K < tk) return false;
+  if (g.M % tc::TM || g.N % 128 || g.K % tk) return false;
+  if ((g.lda | g.ldb) % 8) return false;
   if ((reinterpret_cast<uintptr_t>(g.A) | reinterpret_cast<uintptr_t>(g.B)) & 15) return false;
   return true;
 }
 
+// mode 1: A/B are the Float32 arrays (read as TF32).  mode 2: A/B point at BF16 shadows with the
+// same dims / leading dimensions (see launch_cast_bf16 and the planner's shadow tensors).
 int launch_gemm_tc(yota_ctx* ctx, const GemmArgs& g, cudaStream_t s) {
   if (!gemm_tc_eligible(g)) YOTA_FAIL(YOTA_E_UNSUPPORTED_OP, "gemm: shape not eligible for the tensor-core kernel");
   const bool A_MN = !g.transA;      // A stored M x K column-major: M contiguous
   const bool B_MN = g.transB != 0;  // B stored N x K column-major: N contiguous
   const int TN = (g.N % 256 == 0 && (g.M / tc::TM) * (g.N / 256) >= ctx->sm_count / 2) ? 256 : 128;
+  const int eb = g.mode == 1 ? 4 : 2;
   CUtensorMap ma, mb;
-  YOTA_TRY(tc::make_map(&ma, g.A, g.M, g.K, g.lda, A_MN, tc::TM));
-  YOTA_TRY(tc::make_map(&mb, g.B, g.N, g.K, g.ldb, B_MN, TN));
-#define GO(TNv, a, b) return tc::launch<TNv, a, b>(g, ma, mb, ctx->sm_count, s)
+  YOTA_TRY(tc::make_map(&ma, g.A, g.M, g.K, g.lda, A_MN, tc::TM, eb));
+  YOTA_TRY(tc::make_map(&mb, g.B, g.N, g.K, g.ldb, B_MN, TN, eb));
+#define GO(TNv, a, b)                                                          \
+  return eb == 4 ? tc::launch<TNv, a, b, 4>(g, ma, mb, ctx->sm_count, s)       \
+                 : tc::launch<TNv, a, b, 2>(g, ma, mb, ctx->sm_count, s)
   if (TN == 256) {
     if (A_MN && B_MN) GO(256, true, true);
     if (A_MN && !B_MN) GO(256, true, false);
@@ -389,6 +429,23 @@ int launch_gemm_tc(yota_ctx* ctx, const GemmArgs& g, cudaStream_t s) {
     GO(128, false, false);
   }
 #undef GO
+}
+
+// Float32 -> BF16 (round to nearest even) shadow of a GEMM operand
+__global__ void cast_bf16_kernel(__nv_bfloat162* __restrict__ dst, const float2* __restrict__ src, long long n2) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+    const float2 v = __ldg(src + i);
+    dst[i] = __floats2bfloat162_rn(v.x, v.y);
+  }
+}
+int launch_cast_bf16(void* dst, const float* src, long long n, cudaStream_t s) {
+  if (n == 0) return YOTA_OK;
+  if (n & 1) YOTA_FAIL(YOTA_E_SHAPE, "cast_bf16: odd element count");
+  long long blocks = (n / 2 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  cast_bf16_kernel<<<(unsigned)blocks, 256, 0, s>>>(static_cast<__nv_bfloat162*>(dst), reinterpret_cast<const float2*>(src), n / 2);
+  YOTA_CUDA(cudaGetLastError());
+  return YOTA_OK;
 }
 
 }  // namespace yota

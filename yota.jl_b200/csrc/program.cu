@@ -89,6 +89,8 @@ struct Step {
   int P = 0;
   float scale = 1.f;
   int ws_owner_step = -1;  // finisher: the step whose workspace it reads
+  int shadow[2] = {-1, -1};  // GEMM (BF16 mode): index of the BF16 shadow of operand A / B
+  bool cast[2] = {false, false};  // this step is the first user: cast before the GEMM
 };
 
 }  // namespace yota
@@ -120,6 +122,12 @@ struct yota_program {
   };
   std::vector<GraphEntry> graphs;  // one captured graph per pointer binding (double-buffered batches)
   long long run_counter = 0;
+  struct Shadow {
+    int tensor = -1;  // root tensor id
+    long long arena_off = -1;
+    int first_step = -1, last_step = -1;
+  };
+  std::vector<Shadow> shadows;
   std::vector<int> allreduce_slots;
   std::vector<cudaEvent_t> ar_events;
 };
@@ -818,6 +826,53 @@ struct FreeList {
 
 static size_t elem_size(const TInfo& t) { return t.d.dtype == YOTA_I64 ? 8 : 4; }
 
+static void gemm_dims(const yota_program& P, const yota_op_desc& o, long long* M, long long* N, long long* K,
+                      long long* lda, long long* ldb) {
+  const TInfo &A = P.T[o.in[0]], &B = P.T[o.in[1]];
+  const long long ar = A.d.ndim >= 1 ? A.d.dims[0] : 1, ac = A.d.ndim == 2 ? A.d.dims[1] : 1;
+  const long long br = B.d.ndim >= 1 ? B.d.dims[0] : 1, bc = B.d.ndim == 2 ? B.d.dims[1] : 1;
+  *M = o.iattr[0] ? ac : ar;
+  *K = o.iattr[0] ? ar : ac;
+  *N = o.iattr[1] ? br : bc;
+  *lda = ar;
+  *ldb = br;
+}
+
+// BF16 mode: every tensor-core-eligible GEMM reads BF16 shadows of its Float32 operands.  A
+// shadow is cast once (by the first GEMM step that needs it) and shared by all later GEMMs of
+// the same tensor (H_l feeds the forward and the dW GEMM, ΔZ_l the dW and dH GEMMs, ...).
+static int plan_bf16_shadows(yota_program& P) {
+  if (!(P.flags & YOTA_FLAG_GEMM_BF16)) return YOTA_OK;
+  std::map<int, int> shadow_of;
+  for (size_t s = 0; s < P.steps.size(); s++) {
+    Step& st = P.steps[s];
+    if (st.kind != STEP_GEMM) continue;
+    const yota_op_desc& o = P.ops[st.op];
+    GemmArgs g{};
+    g.mode = 2;
+    g.transA = (int)o.iattr[0];
+    g.transB = (int)o.iattr[1];
+    gemm_dims(P, o, &g.M, &g.N, &g.K, &g.lda, &g.ldb);
+    if (!gemm_tc_eligible(g)) continue;
+    for (int j = 0; j < 2; j++) {
+      const int root = root_of(P, o.in[j]);
+      auto it = shadow_of.find(root);
+      if (it == shadow_of.end()) {
+        yota_program::Shadow sh;
+        sh.tensor = root;
+        sh.first_step = sh.last_step = (int)s;
+        P.shadows.push_back(sh);
+        it = shadow_of.insert({root, (int)P.shadows.size() - 1}).first;
+        st.cast[j] = true;
+      }
+      st.shadow[j] = it->second;
+      P.shadows[it->second].last_step = (int)s;
+    }
+    if (st.shadow[0] == st.shadow[1]) st.cast[1] = false;
+  }
+  return YOTA_OK;
+}
+
 static int plan_memory(yota_program& P) {
   const int ns = (int)P.steps.size();
   // constants first
@@ -854,6 +909,8 @@ static int plan_memory(yota_program& P) {
   std::vector<std::vector<std::pair<size_t, size_t>>> ws_frees(ns);
   for (int s = 0; s < ns; s++) {
     Step& st = P.steps[s];
+    for (auto& sh : P.shadows)
+      if (sh.first_step == s) sh.arena_off = (long long)fl.alloc((size_t)P.T[sh.tensor].numel * 2);
     for (int t : defs[s]) P.T[t].arena_off = (long long)fl.alloc((size_t)P.T[t].numel * elem_size(P.T[t]));
     if (st.kind == STEP_REGION) {
       Region& r = P.regions[st.region];
@@ -870,6 +927,8 @@ static int plan_memory(yota_program& P) {
     }
     for (int t : frees[s]) fl.release((size_t)P.T[t].arena_off, (size_t)P.T[t].numel * elem_size(P.T[t]));
     for (auto& w : ws_frees[s]) fl.release(w.first, w.second);
+    for (auto& sh : P.shadows)
+      if (sh.last_step == s) fl.release((size_t)sh.arena_off, (size_t)P.T[sh.tensor].numel * 2);
   }
   P.arena_bytes = fl.end;
   return YOTA_OK;
@@ -1030,6 +1089,7 @@ extern "C" int yota_program_build(yota_ctx* ctx, const yota_op_desc* ops, int64_
   for (size_t r = 0; r < P.regions.size(); r++)
     if ((st = codegen_region(P, (int)r))) return fail(st);
   if ((st = finish_steps(P))) return fail(st);
+  if ((st = plan_bf16_shadows(P))) return fail(st);
   if ((st = plan_memory(P))) return fail(st);
   P.n_launches = 0;
   for (auto& s : P.steps) P.n_launches += (s.kind == STEP_UNGETINDEX) ? 8 : 1;
@@ -1179,24 +1239,30 @@ static int run_step(yota_program& P, Step& st, cudaStream_t s) {
       return launch_generic_ew(g, out, in0, in1, s);
     }
     case STEP_GEMM: {
-      const TInfo &A = P.T[o.in[0]], &B = P.T[o.in[1]];
       GemmArgs g{};
       g.transA = (int)o.iattr[0];
       g.transB = (int)o.iattr[1];
-      const long long ar = A.d.ndim >= 1 ? A.d.dims[0] : 1, ac = A.d.ndim == 2 ? A.d.dims[1] : 1;
-      const long long br = B.d.ndim >= 1 ? B.d.dims[0] : 1, bc = B.d.ndim == 2 ? B.d.dims[1] : 1;
-      g.M = g.transA ? ac : ar;
-      g.K = g.transA ? ar : ac;
-      g.N = g.transB ? br : bc;
+      gemm_dims(P, o, &g.M, &g.N, &g.K, &g.lda, &g.ldb);
       g.A = in0;
-      g.lda = ar;
-      g.B = static_cast<const float*>(tensor_ptr(P, o.in[1]));
-      g.ldb = br;
+      g.B = tensor_ptr(P, o.in[1]);
       g.C = out;
       g.ldc = g.M;
       g.accumulate = 0;
       g.mode = (P.flags & YOTA_FLAG_GEMM_TF32) ? 1 : (P.flags & YOTA_FLAG_GEMM_BF16) ? 2 : 0;
-      if (g.mode != 0 && gemm_tc_eligible(g)) return launch_gemm_tc(P.ctx, g, s);
+      if (g.mode == 2 && st.shadow[0] >= 0) {
+        const void* src[2] = {g.A, g.B};
+        void* sh[2];
+        for (int j = 0; j < 2; j++) {
+          sh[j] = P.arena + P.shadows[st.shadow[j]].arena_off;
+          if (st.cast[j])
+            YOTA_TRY(launch_cast_bf16(sh[j], static_cast<const float*>(src[j]), P.T[root_of(P, o.in[j])].numel, s));
+        }
+        g.A = sh[0];
+        g.B = sh[1];
+        return launch_gemm_tc(P.ctx, g, s);
+      }
+      if (g.mode == 1 && gemm_tc_eligible(g)) return launch_gemm_tc(P.ctx, g, s);
+      g.mode = 0;
       return launch_gemm_ffma(g, s);
     }
     case STEP_GETINDEX:
