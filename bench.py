@@ -157,7 +157,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default="c3")
-    ap.add_argument("--gemm", default=os.environ.get("YOTA_GEMM_MODE", "fp32"))
+    ap.add_argument("--gemm", default=os.environ.get("YOTA_GEMM_MODE", "tf32"),
+                    help="contraction mode: tf32 (default: tcgen05, Float32 storage), bf16 (tcgen05, BF16 shadows), fp32 (strict FFMA)")
+    ap.add_argument("--no-other-modes", action="store_true", help="skip the short runs of the other GEMM modes")
     ap.add_argument("--small", action="store_true", help="tiny shapes (CI smoke of the bench itself)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
@@ -307,10 +309,29 @@ def main():
         except Exception:
             cpu = {"value": None, "unit": "evals/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: " + r.stderr[-200:]}
 
+    # ---- the other contraction modes, briefly (same workload, device-resident, 5 evals) -----
+    other = {}
+    if a.workload == "c3" and nranks == 1 and not a.no_other_modes:
+        for mode in ("fp32", "tf32", "bf16"):
+            if mode == a.gemm:
+                continue
+            g2 = Y.CompiledGrad(tape, ctx, {"fp32": 0, "tf32": ffi.FLAG_GEMM_TF32, "bf16": ffi.FLAG_GEMM_BF16}[mode])
+            for _ in range(3):
+                g2.run(dargs, out=outs)
+            ctx.sync()
+            ffi.check(lib.yota_event_record(ctx.h, e0))
+            for _ in range(5):
+                g2.run(dargs, out=outs)
+            ffi.check(lib.yota_event_record(ctx.h, e1))
+            ctx.sync()
+            t = elapsed(e0, e1) / 5
+            other[mode] = {"evals_per_s": 1e3 / t, "ms_per_step": t, "loss": float(outs[g2.low.val[1]].to_host())}
+            del g2
+
     if rank == 0:
         line = {"metric": "Yota.grad evals/sec", "value": value, "unit": "evals/s", "n_gpus": nranks, "steps": a.steps,
                 "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32 (f32 storage and accumulate)", "bf16": "bf16"}[a.gemm],
+                "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32 (f32 storage, f32 accumulate)", "bf16": "bf16 (f32 storage + bf16 operand shadows, f32 accumulate)"}[a.gemm],
                 "data": "synthetic",
                 "config": {"workload": wl["label"], "gemm_mode": a.gemm, "global_batch": 8192 if a.workload == "c3" and not a.small else None,
                            "parallelism": f"dp{nranks} (batch columns sharded, NCCL all-reduce of parameter grads)",
@@ -322,7 +343,7 @@ def main():
                         "note": "per step: batch (x, Y) uploaded from pinned host memory on the copy stream (double-buffered, overlapping the previous sweep), loss read back every step; parameters and gradients stay on the device"},
                 "gpu_launches": int(stats["launches"]) * a.steps,
                 "program": stats,
-                "roofline": roof, "cpu_baseline": cpu,
+                "roofline": roof, "cpu_baseline": cpu, "other_gemm_modes": other,
                 "step_breakdown_ms": {k: round(v[0], 4) for k, v in sorted(groups.items(), key=lambda kv: -kv[1][0])}}
         print(json.dumps(line))
 

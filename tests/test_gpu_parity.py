@@ -110,7 +110,7 @@ def test_unary_rules():
 @pytest.mark.parametrize("tA,tB", [(0, 0), (0, 1), (1, 0), (1, 1)])
 def test_gemm_ffma(tA, tB):
     r = cases.rng(8)
-    for m, n, k in [(128, 128, 64), (200, 77, 33), (10, 64, 128), (1, 5, 3), (257, 130, 300)]:
+    for m, n, k in [(128, 128, 64), (200, 77, 33), (10, 64, 128), (1, 5, 3), (257, 130, 300), (640, 384, 100), (300, 500, 77)]:
         A = r.standard_normal((k, m) if tA else (m, k)).astype(F32)
         B = r.standard_normal((n, k) if tB else (k, n)).astype(F32)
         ref = (A.T if tA else A).astype(np.float64) @ (B.T if tB else B).astype(np.float64)

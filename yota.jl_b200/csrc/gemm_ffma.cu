@@ -14,7 +14,7 @@ constexpr int BM = 128, BN = 128, BK = 16, GT = 256;
 // AM: A is contiguous along m (non-transposed column-major); else contiguous along k.
 // BNc: B is contiguous along n (transposed B); else contiguous along k (non-transposed).
 template <bool AM, bool BNc>
-__global__ void __launch_bounds__(GT) gemm_ffma_kernel(long long M, long long N, long long K,
+__global__ void __launch_bounds__(GT, 2) gemm_ffma_kernel(long long M, long long N, long long K,
                                                         const float* __restrict__ A, long long sam, long long sak,
                                                         const float* __restrict__ B, long long sbk, long long sbn,
                                                         float* __restrict__ C, long long ldc, int accumulate) {
@@ -138,11 +138,47 @@ __global__ void __launch_bounds__(GT) gemm_ffma_kernel(long long M, long long N,
     }
 }
 
+// Latency kernel for tiny problems (C1: 784-128-10 MLP at batch 64): one thread per output
+// element, sequential k (deterministic), operands served from L1/L2.  The 128x128 tiling above
+// would put such a GEMM on 1-7 CTAs and walk K serially on each.
+__global__ void __launch_bounds__(256) gemm_small_kernel(long long M, long long N, long long K,
+                                                         const float* __restrict__ A, long long sam, long long sak,
+                                                         const float* __restrict__ B, long long sbk, long long sbn,
+                                                         float* __restrict__ C, long long ldc, int accumulate) {
+  const long long m = (long long)blockIdx.x * 32 + (threadIdx.x & 31);
+  const long long n = (long long)blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (m >= M || n >= N) return;
+  const float* a = A + m * sam;
+  const float* b = B + n * sbn;
+  float acc = 0.f;
+  long long k = 0;
+  for (; k + 4 <= K; k += 4) {
+    const float a0 = __ldg(a + k * sak), a1 = __ldg(a + (k + 1) * sak), a2 = __ldg(a + (k + 2) * sak),
+                a3 = __ldg(a + (k + 3) * sak);
+    const float b0 = __ldg(b + k * sbk), b1 = __ldg(b + (k + 1) * sbk), b2 = __ldg(b + (k + 2) * sbk),
+                b3 = __ldg(b + (k + 3) * sbk);
+    acc = fmaf(a0, b0, acc);
+    acc = fmaf(a1, b1, acc);
+    acc = fmaf(a2, b2, acc);
+    acc = fmaf(a3, b3, acc);
+  }
+  for (; k < K; k++) acc = fmaf(__ldg(a + k * sak), __ldg(b + k * sbk), acc);
+  float* dst = C + m + n * ldc;
+  *dst = accumulate ? *dst + acc : acc;
+}
+
 int launch_gemm_ffma(const GemmArgs& g, cudaStream_t s) {
   if (g.M <= 0 || g.N <= 0) return YOTA_OK;
   // element strides: op(A)(m,k), op(B)(k,n)
   const long long sam = g.transA ? g.lda : 1, sak = g.transA ? 1 : g.lda;
   const long long sbk = g.transB ? g.ldb : 1, sbn = g.transB ? 1 : g.ldb;
+  if (g.M * g.N <= 128 * 1024 && g.M * g.N * g.K <= (64ll << 20) && (g.N + 7) / 8 <= 65535) {
+    dim3 grid((unsigned)((g.M + 31) / 32), (unsigned)((g.N + 7) / 8));
+    gemm_small_kernel<<<grid, 256, 0, s>>>(g.M, g.N, g.K, static_cast<const float*>(g.A), sam, sak,
+                                           static_cast<const float*>(g.B), sbk, sbn, g.C, g.ldc, g.accumulate);
+    YOTA_CUDA(cudaGetLastError());
+    return YOTA_OK;
+  }
   dim3 grid((unsigned)((g.M + BM - 1) / BM), (unsigned)((g.N + BN - 1) / BN));
   if (grid.y > 65535) YOTA_FAIL(YOTA_E_SHAPE, "gemm: N too large for the FFMA kernel grid");
   const bool AM = !g.transA, BNc = g.transB != 0;

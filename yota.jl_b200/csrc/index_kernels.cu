@@ -223,27 +223,31 @@ static int exclusive_scan_u32(unsigned* data, long long n, unsigned* ws, cudaStr
 // ------------------------------------------------------------------------------------------
 constexpr int RS_T = 256, RS_WARPS = 8, RS_ROUNDS = 16, RS_TILE = RS_T * RS_ROUNDS;  // 4096 keys per CTA
 
-__global__ void keys_from_idx_kernel(unsigned* __restrict__ keys, unsigned* __restrict__ vals,
-                                     const int64_t* __restrict__ idx, long long n, long long n_dst) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    long long j = __ldg(idx + i) - 1;
-    // out-of-range indices (a BoundsError in Julia) go to an overflow bucket that is never read
-    keys[i] = (j < 0 || j >= n_dst) ? (unsigned)n_dst : (unsigned)j;
-    vals[i] = (unsigned)i;
-  }
+__device__ __forceinline__ unsigned key_of_idx(const int64_t* __restrict__ idx, long long i, long long n_dst) {
+  const long long j = __ldg(idx + i) - 1;
+  // out-of-range indices (a BoundsError in Julia) go to an overflow bucket that is never read
+  return (j < 0 || j >= n_dst) ? (unsigned)n_dst : (unsigned)j;
 }
 
-template <int BITS>
-__global__ void __launch_bounds__(RS_T) radix_hist_kernel(const unsigned* __restrict__ keys, long long n, int shift,
-                                                          unsigned* __restrict__ hist, int nblocks) {
+// FROM_IDX: first pass -- keys are derived from the Int64 index vector on the fly and the value
+// is the source position itself, so no separate (key, value) initialisation pass is needed.
+template <int BITS, bool FROM_IDX>
+__global__ void __launch_bounds__(RS_T) radix_hist_kernel(const unsigned* __restrict__ keys,
+                                                          const int64_t* __restrict__ idx, long long n_dst,
+                                                          long long n, int shift, unsigned* __restrict__ hist,
+                                                          int nblocks) {
   constexpr int ND = 1 << BITS;
-  extern __shared__ unsigned sh[];  // ND
+  __shared__ unsigned sh[ND];
   for (int i = threadIdx.x; i < ND; i += RS_T) sh[i] = 0;
   __syncthreads();
   const long long base = (long long)blockIdx.x * RS_TILE;
+#pragma unroll 4
   for (int r = 0; r < RS_ROUNDS; r++) {
     const long long i = base + r * RS_T + threadIdx.x;
-    if (i < n) atomicAdd(&sh[(keys[i] >> shift) & (ND - 1)], 1u);  // integer counts: order-independent
+    if (i < n) {
+      const unsigned k = FROM_IDX ? key_of_idx(idx, i, n_dst) : keys[i];
+      atomicAdd(&sh[(k >> shift) & (ND - 1)], 1u);  // integer counts: order-independent
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < ND; i += RS_T) hist[(long long)i * nblocks + blockIdx.x] = sh[i];
@@ -253,14 +257,15 @@ __global__ void __launch_bounds__(RS_T) radix_hist_kernel(const unsigned* __rest
 // keys at a time; match-any gives the rank among equal digits inside a round.  Position =
 // global digit base (scan of hist) + earlier warps' count + this warp's running count + rank
 // => a stable split.
-template <int BITS>
+template <int BITS, bool FROM_IDX>
 __global__ void __launch_bounds__(RS_T) radix_scatter_kernel(const unsigned* __restrict__ keys_in,
                                                              const unsigned* __restrict__ vals_in,
+                                                             const int64_t* __restrict__ idx, long long n_dst,
                                                              unsigned* __restrict__ keys_out,
                                                              unsigned* __restrict__ vals_out, long long n, int shift,
                                                              const unsigned* __restrict__ hist, int nblocks) {
   constexpr int ND = 1 << BITS;
-  extern __shared__ unsigned sh[];  // [RS_WARPS][ND] counts, then running offsets
+  __shared__ unsigned sh[RS_WARPS * ND];  // [warp][digit] counts, then running offsets
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   unsigned* mine = sh + w * ND;
   for (int i = threadIdx.x; i < RS_WARPS * ND; i += RS_T) sh[i] = 0;
@@ -272,7 +277,7 @@ __global__ void __launch_bounds__(RS_T) radix_scatter_kernel(const unsigned* __r
   for (int r = 0; r < RS_ROUNDS; r++) {
     const long long i = wbase + r * 32 + lane;
     const bool ok = i < n;
-    k[r] = ok ? keys_in[i] : 0xffffffffu;
+    k[r] = ok ? (FROM_IDX ? key_of_idx(idx, i, n_dst) : keys_in[i]) : 0xffffffffu;
     const unsigned d = (k[r] >> shift) & (ND - 1);
     const unsigned act = __ballot_sync(0xffffffffu, ok);
     if (ok) {
@@ -306,7 +311,7 @@ __global__ void __launch_bounds__(RS_T) radix_scatter_kernel(const unsigned* __r
       const unsigned rank = __popc(peers & ((1u << lane) - 1u));
       const unsigned pos = mine[d] + rank;
       keys_out[pos] = k[r];
-      vals_out[pos] = vals_in[i];
+      vals_out[pos] = FROM_IDX ? (unsigned)i : vals_in[i];
     }
     __syncwarp();
     if (ok && lane == __ffs(peers) - 1) mine[d] += __popc(peers);
@@ -335,7 +340,7 @@ static SortPlan sort_plan(long long n_dst, long long n_src) {
   SortPlan sp{};
   int keybits = 1;
   while ((1ll << keybits) <= n_dst) keybits++;  // keys in [0, n_dst] (n_dst = overflow bucket)
-  sp.passes = (keybits + 10) / 11;
+  sp.passes = (keybits + 7) / 8;  // <= 8-bit digits: the per-warp rank tables stay small next to the tile
   sp.bits = (keybits + sp.passes - 1) / sp.passes;
   if (sp.bits < 4) sp.bits = 4;
   sp.nblocks = (n_src + RS_TILE - 1) / RS_TILE;
@@ -359,20 +364,15 @@ static SortPlan sort_plan(long long n_dst, long long n_src) {
   return sp;
 }
 
-template <int BITS>
-static int radix_pass(const unsigned* kin, const unsigned* vin, unsigned* kout, unsigned* vout, long long n, int shift,
-                      unsigned* hist, int nblocks, unsigned* scan_ws, cudaStream_t s) {
+template <int BITS, bool FROM_IDX>
+static int radix_pass(const unsigned* kin, const unsigned* vin, const int64_t* idx, long long n_dst, unsigned* kout,
+                      unsigned* vout, long long n, int shift, unsigned* hist, int nblocks, unsigned* scan_ws,
+                      cudaStream_t s) {
   constexpr int ND = 1 << BITS;
-  radix_hist_kernel<BITS><<<nblocks, RS_T, ND * 4, s>>>(kin, n, shift, hist, nblocks);
+  radix_hist_kernel<BITS, FROM_IDX><<<nblocks, RS_T, 0, s>>>(kin, idx, n_dst, n, shift, hist, nblocks);
   YOTA_CUDA(cudaGetLastError());
   YOTA_TRY(exclusive_scan_u32(hist, (long long)ND * nblocks, scan_ws, s));
-  const size_t smem = (size_t)RS_WARPS * ND * 4;
-  static bool attr = false;
-  if (smem > 48 * 1024 && !attr) {
-    YOTA_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
-  radix_scatter_kernel<BITS><<<nblocks, RS_T, smem, s>>>(kin, vin, kout, vout, n, shift, hist, nblocks);
+  radix_scatter_kernel<BITS, FROM_IDX><<<nblocks, RS_T, 0, s>>>(kin, vin, idx, n_dst, kout, vout, n, shift, hist, nblocks);
   YOTA_CUDA(cudaGetLastError());
   return YOTA_OK;
 }
@@ -390,25 +390,25 @@ static int sort_by_destination(const int64_t* idx, long long n_src, long long n_
   unsigned* hist = reinterpret_cast<unsigned*>(base + sp.off_hist);
   unsigned* segp = reinterpret_cast<unsigned*>(base + sp.off_seg);
   unsigned* scan_ws = reinterpret_cast<unsigned*>(base + sp.off_scan);
-  keys_from_idx_kernel<<<grid_for(n_src, 256), 256, 0, s>>>(keys[0], vals[0], idx, n_src, n_dst);
-  YOTA_CUDA(cudaGetLastError());
-  int cur = 0;
+  int cur = 1;  // the first pass reads idx and writes buffer 0
   for (int pass = 0; pass < sp.passes; pass++) {
     const int shift = pass * sp.bits;
     int st;
     switch (sp.bits) {
-#define RP(B)                                                                                                    \
-  case B:                                                                                                        \
-    st = radix_pass<B>(keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n_src, shift, hist, (int)sp.nblocks, \
-                       scan_ws, s);                                                                              \
+#define RP(B)                                                                                                     \
+  case B:                                                                                                         \
+    st = pass == 0 ? radix_pass<B, true>(nullptr, nullptr, idx, n_dst, keys[0], vals[0], n_src, shift, hist,      \
+                                         (int)sp.nblocks, scan_ws, s)                                             \
+                   : radix_pass<B, false>(keys[cur], vals[cur], idx, n_dst, keys[cur ^ 1], vals[cur ^ 1], n_src,  \
+                                          shift, hist, (int)sp.nblocks, scan_ws, s);                              \
     break;
-      RP(4) RP(5) RP(6) RP(7) RP(8) RP(9) RP(10) RP(11)
+      RP(4) RP(5) RP(6) RP(7) RP(8)
 #undef RP
       default:
         YOTA_FAIL(YOTA_E_ARG, "radix sort: unsupported digit width %d", sp.bits);
     }
     YOTA_TRY(st);
-    cur ^= 1;
+    cur = pass == 0 ? 0 : cur ^ 1;
   }
   seg_start_kernel<<<grid_for(n_src + 1, 256), 256, 0, s>>>(keys[cur], n_src, segp, n_dst);
   YOTA_CUDA(cudaGetLastError());
