@@ -177,6 +177,8 @@ int launch_getindex(const IndexSpec& sp, float* y, const float* x, long long n_o
 size_t ungetindex_workspace_bytes(const IndexSpec& sp);
 int launch_ungetindex(const IndexSpec& sp, float* dx, const float* dy, void* workspace, size_t ws_bytes,
                       int sm_count, cudaStream_t s);
+// acc[I...] = acc[I...] + (0.0f + dy) over the selection (no index vectors); other elements untouched
+int launch_slice_accum(const IndexSpec& sp, float* acc, const float* dy, bool scalar_dy, cudaStream_t s);
 size_t scatter_cols_workspace_bytes(long long n_dst, long long n_src);
 int launch_scatter_add_cols(float* dx, long long rows, long long n_dst, const float* dy, const int64_t* idx,
                             long long n_src, void* workspace, size_t ws_bytes, cudaStream_t s);

@@ -190,36 +190,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer (one elected lane) =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int m0 = (t % p.num_m) * TM, n0 = (t / p.num_m) * TN;
-        for (int kb = 0; kb < nkb; kb++) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], S::STAGE_BYTES);
-          unsigned char* sa = smem + stage * S::STAGE_BYTES;
-          unsigned char* sb = sa + S::A_BYTES;
-          const int k0 = kb * TK;
-          if (A_MN) {
-#pragma unroll
-            for (int c = 0; c < TM / E::CHUNK; c++)
-              tma_load_2d(sa + c * E::CHUNK_BYTES, &map_a, &full[stage], m0 + E::CHUNK * c, k0);
-          } else {
+    // ===================== TMA producer warp =====================
+    // An MN-major operand needs one box per 128-byte-wide MN chunk (up to 4 + 8 boxes per
+    // stage); issuing them from one thread costs more than the stage's MMA time, so lane c
+    // issues box c: the whole stage is in flight after one issue slot.
+    constexpr int NA = A_MN ? TM / E::CHUNK : 1;
+    constexpr int NB = B_MN ? TN / E::CHUNK : 1;
+    static_assert(NA + NB <= 32, "one lane per TMA box");
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int m0 = (t % p.num_m) * TM, n0 = (t / p.num_m) * TN;
+      for (int kb = 0; kb < nkb; kb++) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (lane == 0) mbar_expect_tx(&full[stage], S::STAGE_BYTES);
+        __syncwarp();
+        unsigned char* sa = smem + stage * S::STAGE_BYTES;
+        unsigned char* sb = sa + S::A_BYTES;
+        const int k0 = kb * TK;
+        if (lane < NA) {
+          if (A_MN)
+            tma_load_2d(sa + lane * E::CHUNK_BYTES, &map_a, &full[stage], m0 + E::CHUNK * lane, k0);
+          else
             tma_load_2d(sa, &map_a, &full[stage], k0, m0);
-          }
-          if (B_MN) {
-#pragma unroll
-            for (int c = 0; c < TN / E::CHUNK; c++)
-              tma_load_2d(sb + c * E::CHUNK_BYTES, &map_b, &full[stage], n0 + E::CHUNK * c, k0);
-          } else {
+        } else if (lane < NA + NB) {
+          const int c = lane - NA;
+          if (B_MN)
+            tma_load_2d(sb + c * E::CHUNK_BYTES, &map_b, &full[stage], n0 + E::CHUNK * c, k0);
+          else
             tma_load_2d(sb, &map_b, &full[stage], k0, n0);
-          }
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }

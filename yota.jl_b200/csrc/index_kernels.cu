@@ -137,6 +137,37 @@ int launch_getindex(const IndexSpec& sp, float* y, const float* x, long long n_o
   return YOTA_OK;
 }
 
+// in-place slice accumulation: the selection is walked in dy order (same index math as the
+// gather), every selected element is touched exactly once
+__global__ void slice_accum_kernel(GetIdxParams p, float* __restrict__ acc, const float* __restrict__ dy,
+                                   long long n_sel, int scalar_dy) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_sel;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long rem = i, off = 0;
+#pragma unroll
+    for (int d = 0; d < 4; d++) {
+      if (d < p.n) {
+        const long long c = rem % p.odim[d];
+        rem /= p.odim[d];
+        off += (p.kind[d] == YOTA_IDX_COLON ? c : p.a[d] - 1 + c) * p.xstride[d];
+      }
+    }
+    const float v = __fadd_rn(0.f, dy[scalar_dy ? 0 : i]);
+    acc[off] = __fadd_rn(v, acc[off]);
+  }
+}
+
+int launch_slice_accum(const IndexSpec& sp, float* acc, const float* dy, bool scalar_dy, cudaStream_t s) {
+  GetIdxParams p;
+  fill_getidx(sp, p);
+  long long n_sel = 1;
+  for (int d = 0; d < sp.n; d++) n_sel *= p.odim[d];
+  if (n_sel == 0) return YOTA_OK;
+  slice_accum_kernel<<<grid_for(n_sel, 256), 256, 0, s>>>(p, acc, dy, n_sel, scalar_dy ? 1 : 0);
+  YOTA_CUDA(cudaGetLastError());
+  return YOTA_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // exclusive scan of u32 (in place), any length; deterministic
 // ------------------------------------------------------------------------------------------
@@ -271,19 +302,30 @@ __global__ void __launch_bounds__(RS_T) radix_scatter_kernel(const unsigned* __r
   for (int i = threadIdx.x; i < RS_WARPS * ND; i += RS_T) sh[i] = 0;
   __syncthreads();
   const long long wbase = (long long)blockIdx.x * RS_TILE + (long long)w * (RS_TILE / RS_WARPS);
-  unsigned k[RS_ROUNDS];
-  // pass 1: per-warp digit counts
+  const unsigned lt = (1u << lane) - 1u;
+  // Lanes holding the same digit, from BITS ballots (MATCH.ANY is microcoded and ~50x slower
+  // than VOTE on this part: it made this kernel 5x slower than the data movement).
+  auto peers_of = [&](unsigned d, unsigned act) {
+    unsigned peers = act;
 #pragma unroll
+    for (int b = 0; b < BITS; b++) {
+      const unsigned bit = (d >> b) & 1u;
+      const unsigned v = __ballot_sync(0xffffffffu, bit);
+      peers &= bit ? v : ~v;
+    }
+    return peers;
+  };
+  // pass 1: per-warp digit counts (keys are re-read in pass 2: 16 MB from L2 is cheaper than
+  // 16 live registers per thread)
+#pragma unroll 4
   for (int r = 0; r < RS_ROUNDS; r++) {
     const long long i = wbase + r * 32 + lane;
     const bool ok = i < n;
-    k[r] = ok ? (FROM_IDX ? key_of_idx(idx, i, n_dst) : keys_in[i]) : 0xffffffffu;
-    const unsigned d = (k[r] >> shift) & (ND - 1);
+    const unsigned key = ok ? (FROM_IDX ? key_of_idx(idx, i, n_dst) : keys_in[i]) : 0xffffffffu;
+    const unsigned d = (key >> shift) & (ND - 1);
     const unsigned act = __ballot_sync(0xffffffffu, ok);
-    if (ok) {
-      const unsigned peers = __match_any_sync(act, d);
-      if (lane == __ffs(peers) - 1) mine[d] += __popc(peers);
-    }
+    const unsigned peers = peers_of(d, act);
+    if (ok && (peers & lt) == 0) mine[d] += __popc(peers);  // lowest lane of each digit group
     __syncwarp();
   }
   __syncthreads();
@@ -299,22 +341,21 @@ __global__ void __launch_bounds__(RS_T) radix_scatter_kernel(const unsigned* __r
   }
   __syncthreads();
   // pass 2: stable scatter
-#pragma unroll
+#pragma unroll 2
   for (int r = 0; r < RS_ROUNDS; r++) {
     const long long i = wbase + r * 32 + lane;
     const bool ok = i < n;
-    const unsigned d = (k[r] >> shift) & (ND - 1);
+    const unsigned key = ok ? (FROM_IDX ? key_of_idx(idx, i, n_dst) : keys_in[i]) : 0xffffffffu;
+    const unsigned d = (key >> shift) & (ND - 1);
     const unsigned act = __ballot_sync(0xffffffffu, ok);
-    unsigned peers = 0;
+    const unsigned peers = peers_of(d, act);
+    const unsigned pos = mine[d] + __popc(peers & lt);
     if (ok) {
-      peers = __match_any_sync(act, d);
-      const unsigned rank = __popc(peers & ((1u << lane) - 1u));
-      const unsigned pos = mine[d] + rank;
-      keys_out[pos] = k[r];
+      keys_out[pos] = key;
       vals_out[pos] = FROM_IDX ? (unsigned)i : vals_in[i];
     }
     __syncwarp();
-    if (ok && lane == __ffs(peers) - 1) mine[d] += __popc(peers);
+    if (ok && (peers & lt) == 0) mine[d] += __popc(peers);
     __syncwarp();
   }
 }

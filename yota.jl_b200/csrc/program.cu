@@ -37,7 +37,8 @@ enum StepKind {
   STEP_LOGSOFTMAX,
   STEP_TRANSPOSE,
   STEP_CAT,
-  STEP_SLICE
+  STEP_SLICE,
+  STEP_SLICE_ACCUM  // out (aliasing acc) [I...] += dy : in-place form of ADD(UNGETINDEX(dy), acc)
 };
 
 struct TInfo {
@@ -55,6 +56,7 @@ struct TInfo {
   long long arena_off = -1;
   int def_step = -1, last_step = -1;
   int const_index = -1;
+  int fwd_out_slot = -1;  // TEMP root whose in-place chain ends in an OUTPUT: lives in out_ptrs[slot]
 };
 
 struct Region {
@@ -91,6 +93,8 @@ struct Step {
   int ws_owner_step = -1;  // finisher: the step whose workspace it reads
   int shadow[2] = {-1, -1};  // GEMM (BF16 mode): index of the BF16 shadow of operand A / B
   bool cast[2] = {false, false};  // this step is the first user: cast before the GEMM
+  int out_override = -1;  // in-place accumulation: the ADD's output tensor (aliases acc_tensor)
+  int acc_tensor = -1;
 };
 
 }  // namespace yota
@@ -320,7 +324,10 @@ static int validate(yota_program& P) {
 // fusion
 // ------------------------------------------------------------------------------------------
 static int step_of_tensor(const yota_program& P, int t) {
-  // step index at which tensor t becomes available (-1: before the program starts)
+  // step index at which tensor t becomes available (-1: before the program starts).  Aliases
+  // carry their own step: a RESHAPE the step of its source, an in-place accumulation the step
+  // that performs it (later than the step that produced the buffer it lives in).
+  if (P.T[t].alias_of >= 0) return P.T[t].def_step;
   const TInfo& ti = P.T[root_of(P, t)];
   if (ti.d.kind == YOTA_T_INPUT || ti.d.kind == YOTA_T_CONST || ti.d.kind == YOTA_T_SEED) return -1;
   return ti.def_step;
@@ -483,6 +490,64 @@ struct Fuser {
   }
 };
 
+// Tape gradient accumulation  acc' = broadcast(+, new, acc)  (src/grad.jl:91) where `new` is a
+// whole-array temporary with a single use: the reference allocates `new`, then a third array
+// for the sum (C4: 127 x 3 passes over the 64 MiB dx, 127 x 2 over each dW).  When `acc` has
+// no other reader either, the sum is formed IN PLACE in acc's buffer:
+//   new = A*B (matmul rrule thunk)            ->  GEMM with C += ...  (same single add per element)
+//   new = ungetindex of a slice (no index vec) ->  acc[I...] += dy; the other elements keep
+//        their bits (the reference adds +0.0f to them: identical except -0.0f -> +0.0f)
+static int count_needed_consumers(const yota_program& P, int t) {
+  int n = 0;
+  for (int c : P.T[t].consumers) n += P.op_needed[c] ? 1 : 0;
+  return n;
+}
+
+static bool try_inplace_accumulate(yota_program& P, Fuser& F, int add_op) {
+  const yota_op_desc& o = P.ops[add_op];
+  TInfo& out = P.T[o.out];
+  for (int side = 0; side < 2; side++) {
+    const int a = o.in[side], b = o.in[1 - side];
+    if (a == b) continue;
+    const TInfo &ta = P.T[a], &tb = P.T[b];
+    if (ta.producer < 0 || tb.producer < 0) continue;
+    if (ta.d.kind != YOTA_T_TEMP || tb.d.kind != YOTA_T_TEMP) continue;
+    if (ta.alias_of >= 0) continue;
+    if (!same_dims(ta, out.dims, out.nd) || !same_dims(tb, out.dims, out.nd)) continue;
+    if (count_needed_consumers(P, a) != 1 || count_needed_consumers(P, b) != 1) continue;
+    // b's buffer must not be visible through another alias that is still read elsewhere
+    const int rb = root_of(P, b);
+    if (P.T[rb].d.kind != YOTA_T_TEMP) continue;
+    const yota_op_desc& pa = P.ops[ta.producer];
+    int kind = -1;
+    if (pa.opcode == YOTA_OP_MATMUL)
+      kind = STEP_GEMM;
+    else if (pa.opcode == YOTA_OP_UNGETINDEX) {
+      bool vec = false;
+      for (int d = 0; d < (int)pa.iattr[0]; d++) vec |= pa.iattr[1 + 3 * d] == YOTA_IDX_VEC;
+      if (!vec) kind = STEP_SLICE_ACCUM;
+    }
+    if (kind < 0) continue;
+    const int st = ta.def_step;
+    if (st < 0 || P.steps[st].op != ta.producer || P.steps[st].out_override >= 0) continue;
+    F.force(rb);
+    if (step_of_tensor(P, b) >= st) continue;  // acc is not ready when the producer runs
+    Step& step = P.steps[st];
+    step.kind = kind;
+    step.acc_tensor = b;
+    step.out_override = o.out;
+    step.reads.push_back(b);
+    step.label += kind == STEP_GEMM ? " (+= in place)" : " -> slice += in place";
+    P.T[rb].materialized = true;
+    P.T[a].materialized = false;
+    out.alias_of = b;
+    out.def_step = st;
+    out.materialized = true;
+    return true;
+  }
+  return false;
+}
+
 static int plan_fusion(yota_program& P) {
   Fuser F(P);
   const bool fuse = F.fuse;
@@ -499,6 +564,7 @@ static int plan_fusion(yota_program& P) {
       out.def_step = step_of_tensor(P, o.in[0]);
       continue;
     }
+    if (o.opcode == YOTA_EW_ADD && fuse && try_inplace_accumulate(P, F, (int)i)) continue;
     if (is_ew(o.opcode)) {
       if (F.op_kmask((int)i) == 0) {
         // broadcast pattern that does not collapse to 2-d: generic N-d kernel
@@ -895,10 +961,16 @@ static int plan_memory(yota_program& P) {
       r.last_step = std::max(r.last_step, s);
     }
   }
+  for (size_t t = 0; t < P.T.size(); t++)
+    if (P.T[t].alias_of >= 0 && P.T[t].d.kind == YOTA_T_OUTPUT && P.T[t].needed) {
+      TInfo& r = P.T[root_of(P, (int)t)];
+      if (r.d.kind == YOTA_T_TEMP) r.fwd_out_slot = P.T[t].d.slot;
+    }
   std::vector<std::vector<int>> defs(ns), frees(ns);
   for (size_t t = 0; t < P.T.size(); t++) {
     TInfo& ti = P.T[t];
     if (ti.alias_of >= 0 || ti.d.kind != YOTA_T_TEMP || !ti.materialized || ti.def_step < 0) continue;
+    if (ti.fwd_out_slot >= 0) continue;  // lives in the caller's output buffer
     if (ti.last_step < ti.def_step) ti.last_step = ti.def_step;
     defs[ti.def_step].push_back((int)t);
     frees[ti.last_step].push_back((int)t);
@@ -992,14 +1064,14 @@ static int finish_steps(yota_program& P) {
     Step& st = P.steps[s];
     if (st.op < 0 || st.kind == STEP_ROWSUM_FINISH || st.kind == STEP_SCALAR_FINISH) continue;
     const yota_op_desc& o = P.ops[st.op];
-    st.writes.push_back(o.out);
-    if (st.kind == STEP_GETINDEX || st.kind == STEP_UNGETINDEX) {
+    st.writes.push_back(st.out_override >= 0 ? st.out_override : o.out);
+    if (st.kind == STEP_GETINDEX || st.kind == STEP_UNGETINDEX || st.kind == STEP_SLICE_ACCUM) {
       IndexSpec sp;
       long long nsel;
       const TInfo& x = st.kind == STEP_GETINDEX ? P.T[o.in[0]] : P.T[o.out];
       YOTA_TRY(index_spec_of(P, o, x, sp, &nsel));
       const TInfo& sel = st.kind == STEP_GETINDEX ? P.T[o.out] : P.T[o.in[0]];
-      if (sel.numel != nsel && !(st.kind == STEP_UNGETINDEX && sel.numel == 1))
+      if (sel.numel != nsel && !(st.kind != STEP_GETINDEX && sel.numel == 1))
         YOTA_FAIL(YOTA_E_SHAPE, "%s: selection has %lld elements, tensor has %lld", opname(o.opcode), nsel, sel.numel);
       if (st.kind == STEP_UNGETINDEX) st.ws_bytes = ungetindex_workspace_bytes(sp);
     }
@@ -1151,7 +1223,9 @@ static void* tensor_ptr(yota_program& P, int t) {
     case YOTA_T_OUTPUT: return P.bound_out[ti.d.slot];
     case YOTA_T_CONST:
     case YOTA_T_SEED: return P.arena + (size_t)ti.const_index * 256;
-    default: return ti.arena_off >= 0 ? P.arena + ti.arena_off : nullptr;
+    default:
+      if (ti.fwd_out_slot >= 0) return P.bound_out[ti.fwd_out_slot];
+      return ti.arena_off >= 0 ? P.arena + ti.arena_off : nullptr;
   }
 }
 
@@ -1206,7 +1280,7 @@ static int run_step(yota_program& P, Step& st, cudaStream_t s) {
     default: break;
   }
   const yota_op_desc& o = P.ops[st.op];
-  float* out = static_cast<float*>(tensor_ptr(P, o.out));
+  float* out = static_cast<float*>(tensor_ptr(P, st.out_override >= 0 ? st.out_override : o.out));
   const float* in0 = static_cast<const float*>(tensor_ptr(P, o.in[0]));
   const TInfo& ot = P.T[o.out];
   switch (st.kind) {
@@ -1247,7 +1321,7 @@ static int run_step(yota_program& P, Step& st, cudaStream_t s) {
       g.B = tensor_ptr(P, o.in[1]);
       g.C = out;
       g.ldc = g.M;
-      g.accumulate = 0;
+      g.accumulate = st.acc_tensor >= 0 ? 1 : 0;
       g.mode = (P.flags & YOTA_FLAG_GEMM_TF32) ? 1 : (P.flags & YOTA_FLAG_GEMM_BF16) ? 2 : 0;
       if (g.mode == 2 && st.shadow[0] >= 0) {
         const void* src[2] = {g.A, g.B};
@@ -1264,6 +1338,12 @@ static int run_step(yota_program& P, Step& st, cudaStream_t s) {
       if (g.mode == 1 && gemm_tc_eligible(g)) return launch_gemm_tc(P.ctx, g, s);
       g.mode = 0;
       return launch_gemm_ffma(g, s);
+    }
+    case STEP_SLICE_ACCUM: {
+      IndexSpec sp;
+      long long nsel;
+      YOTA_TRY(index_spec_of(P, o, ot, sp, &nsel));
+      return launch_slice_accum(sp, out, in0, P.T[o.in[0]].numel == 1, s);
     }
     case STEP_GETINDEX:
     case STEP_UNGETINDEX: {
