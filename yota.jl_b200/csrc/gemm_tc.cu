@@ -29,6 +29,7 @@
 // M index fastest so concurrently running CTAs share B panels in L2.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.h"
 
@@ -134,6 +135,7 @@ struct Params {
   long long ldc;
   int accumulate;
   int num_m, num_n;
+  int spread;  // 1: lane c of the producer warp issues TMA box c; 0: lane 0 issues all boxes
 };
 
 template <int TN>
@@ -208,7 +210,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         unsigned char* sa = smem + stage * S::STAGE_BYTES;
         unsigned char* sb = sa + S::A_BYTES;
         const int k0 = kb * TK;
-        if (lane < NA) {
+        if (!p.spread) {
+          if (lane == 0) {
+            if (A_MN) {
+#pragma unroll
+              for (int c = 0; c < NA; c++) tma_load_2d(sa + c * E::CHUNK_BYTES, &map_a, &full[stage], m0 + E::CHUNK * c, k0);
+            } else
+              tma_load_2d(sa, &map_a, &full[stage], k0, m0);
+            if (B_MN) {
+#pragma unroll
+              for (int c = 0; c < NB; c++) tma_load_2d(sb + c * E::CHUNK_BYTES, &map_b, &full[stage], n0 + E::CHUNK * c, k0);
+            } else
+              tma_load_2d(sb, &map_b, &full[stage], k0, n0);
+          }
+        } else if (lane < NA) {
           if (A_MN)
             tma_load_2d(sa + lane * E::CHUNK_BYTES, &map_a, &full[stage], m0 + E::CHUNK * lane, k0);
           else
@@ -385,11 +400,300 @@ static int launch(const GemmArgs& g, const CUtensorMap& ma, const CUtensorMap& m
   p.C = g.C;
   p.ldc = g.ldc;
   p.accumulate = g.accumulate;
+  p.spread = getenv("YOTA_TMA_1LANE") ? 0 : 1;
   p.num_m = (int)(g.M / TM);
   p.num_n = (int)(g.N / TN);
   const int tiles = p.num_m * p.num_n;
   const int grid = tiles < sm_count ? tiles : sm_count;
   kern<<<grid, THREADS, Smem<TN>::TOTAL, s>>>(ma, mb, p);
+  YOTA_CUDA(cudaGetLastError());
+  return YOTA_OK;
+}
+
+
+// =============================================================================================
+// 2-CTA variant (cta_group::2): a CTA pair on one TPC computes a 256 x 256 tile.  Each CTA
+// holds its own 128 rows of A and HALF of B (128 columns); the tensor cores of both SMs read
+// both halves of B, so per-CTA L2->smem traffic per MMA drops by a third (32 KiB instead of
+// 48 KiB per 128-byte k-block) and the ring is 6 stages deep instead of 4.  At 128x256x32 the
+// single-CTA kernel pulls ~17 TB/s through L2 -- that, not the tensor pipe, is its ceiling
+// (profiles/README.md).  Protocol (leader = CTA rank 0 of the pair):
+//   full[s]   lives in the leader; TMA loads of BOTH CTAs complete_tx on it (cta_group::2 form),
+//             the peer's producer also arrives on it remotely (count 2)
+//   empty[s]  per CTA; the leader's tcgen05.commit multicasts the arrive to both CTAs
+//   tfull[a]  per CTA, multicast commit;  tempty[a] in the leader, 256 epilogue threads arrive
+// =============================================================================================
+constexpr int STAGES2 = 6;
+constexpr int TN2 = 256;
+
+struct Smem2 {
+  static constexpr int A_BYTES = TM * 128;
+  static constexpr int B_BYTES = (TN2 / 2) * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFF = STAGES2 * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same smem offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
+// TMA load whose completion is signalled on the LEADER CTA's mbarrier (peer bit cleared)
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+template <int EB>
+__device__ __forceinline__ void umma_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  if (EB == 4)
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+template <bool A_MN, bool B_MN, int EB>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
+  using S = Smem2;
+  using E = El<EB>;
+  constexpr int TK = E::TK;
+  constexpr int TNH = TN2 / 2;  // B columns held by one CTA
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+  uint64_t* empty = full + STAGES2;
+  uint64_t* tfull = empty + STAGES2;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int num_tiles = p.num_m * p.num_n;  // in 256 x 256 tiles
+  const int nkb = (int)(p.K / TK);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES2; s++) {
+      mbar_init(&full[s], 2);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; a++) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 256);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(2 * TN2)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer warp (both CTAs) =====================
+    constexpr int NA = A_MN ? TM / E::CHUNK : 1;
+    constexpr int NB = B_MN ? TNH / E::CHUNK : 1;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = pair; t < num_tiles; t += num_pairs) {
+      const int m0 = (t % p.num_m) * (2 * TM) + (int)rank * TM;
+      const int n0 = (t / p.num_m) * TN2 + (int)rank * TNH;
+      for (int kb = 0; kb < nkb; kb++) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (lane == 0) {
+          if (leader)
+            mbar_expect_tx(&full[stage], 2 * S::STAGE_BYTES);
+          else
+            mbar_arrive_remote(&full[stage], 0);
+        }
+        __syncwarp();
+        unsigned char* sa = smem + stage * S::STAGE_BYTES;
+        unsigned char* sb = sa + S::A_BYTES;
+        const int k0 = kb * TK;
+        if (lane < NA) {
+          if (A_MN)
+            tma_load_2d_2sm(sa + lane * E::CHUNK_BYTES, &map_a, &full[stage], m0 + E::CHUNK * lane, k0);
+          else
+            tma_load_2d_2sm(sa, &map_a, &full[stage], k0, m0);
+        } else if (lane < NA + NB) {
+          const int c = lane - NA;
+          if (B_MN)
+            tma_load_2d_2sm(sb + c * E::CHUNK_BYTES, &map_b, &full[stage], n0 + E::CHUNK * c, k0);
+          else
+            tma_load_2d_2sm(sb, &map_b, &full[stage], k0, n0);
+        }
+        if (++stage == STAGES2) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: the leader CTA drives both tensor cores =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t FMT = EB == 4 ? 2u : 1u;
+      const uint32_t idesc = (1u << 4) | (FMT << 7) | (FMT << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                             ((uint32_t)(TN2 >> 3) << 17) | ((uint32_t)((2 * TM) >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = pair; t < num_tiles; t += num_pairs) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * TN2;
+        for (int kb = 0; kb < nkb; kb++) {
+          mbar_wait(&full[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
+          const uint32_t sb = sa + S::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const uint64_t da = A_MN ? make_desc(sa + k * E::MN_KSTEP, E::CHUNK_BYTES, E::MN_SBO, E::MN_LAYOUT)
+                                     : make_desc(sa + k * 32, 16, 1024, 2);
+            const uint64_t db = B_MN ? make_desc(sb + k * E::MN_KSTEP, E::CHUNK_BYTES, E::MN_SBO, E::MN_LAYOUT)
+                                     : make_desc(sb + k * 32, 16, 1024, 2);
+            umma_2sm<EB>(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_2sm(&empty[stage]);
+          if (++stage == STAGES2) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_2sm(&tfull[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (both CTAs): own 128 rows x 256 columns =====================
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = pair; t < num_tiles; t += num_pairs) {
+      const long long m = (long long)(t % p.num_m) * (2 * TM) + (long long)rank * TM + q * 32 + lane;
+      const long long n0 = (long long)(t / p.num_m) * TN2;
+      mbar_wait(&tfull[acc], acc_phase);
+      tcgen05_fence_after();
+      float* crow = p.C + m + n0 * p.ldc;
+#pragma unroll 1
+      for (int c = 0; c < TN2 / 32; c++) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + (uint32_t)(acc * TN2 + c * 32) + ((uint32_t)(q * 32) << 16);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float* cp = crow + (long long)(c * 32) * p.ldc;
+        if (p.accumulate) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) cp[j * p.ldc] = __uint_as_float(v[j]) + cp[j * p.ldc];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j++) cp[j * p.ldc] = __uint_as_float(v[j]);
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive_remote(&tempty[acc], 0);  // the leader's MMA warp waits for both CTAs' epilogues
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's smem / TMEM may still be read by the leader's MMAs until here
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * TN2) : "memory");
+  }
+}
+
+template <bool A_MN, bool B_MN, int EB>
+static int launch2(const GemmArgs& g, const CUtensorMap& ma, const CUtensorMap& mb, int sm_count, cudaStream_t s) {
+  static bool attr = false;
+  auto kern = gemm_tc2_kernel<A_MN, B_MN, EB>;
+  if (!attr) {
+    YOTA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem2::TOTAL));
+    attr = true;
+  }
+  Params p;
+  p.M = g.M;
+  p.N = g.N;
+  p.K = g.K;
+  p.C = g.C;
+  p.ldc = g.ldc;
+  p.accumulate = g.accumulate;
+  p.spread = 1;
+  p.num_m = (int)(g.M / (2 * TM));
+  p.num_n = (int)(g.N / TN2);
+  const int tiles = p.num_m * p.num_n;
+  int pairs = sm_count / 2;
+  if (tiles < pairs) pairs = tiles;
+  kern<<<2 * pairs, THREADS, Smem2::TOTAL, s>>>(ma, mb, p);
   YOTA_CUDA(cudaGetLastError());
   return YOTA_OK;
 }
@@ -412,9 +716,24 @@ int launch_gemm_tc(yota_ctx* ctx, const GemmArgs& g, cudaStream_t s) {
   if (!gemm_tc_eligible(g)) YOTA_FAIL(YOTA_E_UNSUPPORTED_OP, "gemm: shape not eligible for the tensor-core kernel");
   const bool A_MN = !g.transA;      // A stored M x K column-major: M contiguous
   const bool B_MN = g.transB != 0;  // B stored N x K column-major: N contiguous
-  const int TN = (g.N % 256 == 0 && (g.M / tc::TM) * (g.N / 256) >= ctx->sm_count / 2) ? 256 : 128;
   const int eb = g.mode == 1 ? 4 : 2;
   CUtensorMap ma, mb;
+  const bool two_cta = !getenv("YOTA_GEMM_1CTA") && g.M % 256 == 0 && g.N % 256 == 0 &&
+                       (g.M / 256) * (g.N / 256) >= ctx->sm_count / 4;
+  if (two_cta) {
+    // each CTA of a pair loads a 128-row box of A and a 128-column box of B
+    YOTA_TRY(tc::make_map(&ma, g.A, g.M, g.K, g.lda, A_MN, tc::TM, eb));
+    YOTA_TRY(tc::make_map(&mb, g.B, g.N, g.K, g.ldb, B_MN, tc::TN2 / 2, eb));
+#define GO2(a, b)                                                        \
+  return eb == 4 ? tc::launch2<a, b, 4>(g, ma, mb, ctx->sm_count, s)     \
+                 : tc::launch2<a, b, 2>(g, ma, mb, ctx->sm_count, s)
+    if (A_MN && B_MN) GO2(true, true);
+    if (A_MN && !B_MN) GO2(true, false);
+    if (!A_MN && B_MN) GO2(false, true);
+    GO2(false, false);
+#undef GO2
+  }
+  const int TN = (g.N % 256 == 0 && (g.M / tc::TM) * (g.N / 256) >= ctx->sm_count / 2) ? 256 : 128;
   YOTA_TRY(tc::make_map(&ma, g.A, g.M, g.K, g.lda, A_MN, tc::TM, eb));
   YOTA_TRY(tc::make_map(&mb, g.B, g.N, g.K, g.ldb, B_MN, TN, eb));
 #define GO(TNv, a, b)                                                          \
