@@ -1,6 +1,6 @@
 """GEMM micro-benchmark (GPU): the three C3 contractions in every mode / kernel variant, timed
 with CUDA events on the context stream.  A/B switches are environment variables read at launch:
-YOTA_GEMM_1CTA (force the single-CTA tcgen05 kernel), YOTA_TMA_1LANE (one lane issues all TMA
+YOTA_GEMM_1CTA (force the single-CTA tcgen05 kernel), YOTA_TMA_SPREAD (one lane issues all TMA
 boxes).  Usage: python tests/gemm_bench.py [reps]"""
 import ctypes as C
 import os
@@ -28,7 +28,8 @@ e0, e1 = ev(), ev()
 rng = np.random.default_rng(0)
 shapes = [("NN fwd  W*H", 0, 0, 4096, 8192, 4096), ("NT dW  dZ*H'", 0, 1, 4096, 4096, 8192), ("TN dH  W'*dZ", 1, 0, 4096, 8192, 4096),
           ("NN n=1024", 0, 0, 4096, 1024, 4096), ("NT k=1024", 0, 1, 4096, 4096, 1024)]
-variants = [("2cta", {}), ("1cta", {"YOTA_GEMM_1CTA": "1"}), ("1cta-1lane", {"YOTA_GEMM_1CTA": "1", "YOTA_TMA_1LANE": "1"})]
+variants = [("2cta", {}), ("2cta-spread", {"YOTA_TMA_SPREAD": "1"}), ("1cta", {"YOTA_GEMM_1CTA": "1"}),
+            ("1cta-spread", {"YOTA_GEMM_1CTA": "1", "YOTA_TMA_SPREAD": "1"})]
 for name, tA, tB, m, n, k in shapes:
     A = Y.cu(rng.standard_normal((k, m) if tA else (m, k), dtype=np.float32))
     B = Y.cu(rng.standard_normal((n, k) if tB else (k, n), dtype=np.float32))
@@ -36,7 +37,7 @@ for name, tA, tB, m, n, k in shapes:
     ref = None
     for mode, mname in ((1, "tf32"), (2, "bf16")):
         for vname, env in variants:
-            for kk in ("YOTA_GEMM_1CTA", "YOTA_TMA_1LANE"):
+            for kk in ("YOTA_GEMM_1CTA", "YOTA_TMA_SPREAD"):
                 os.environ.pop(kk, None)
             os.environ.update(env)
             args = (ctx.h, mode, tA, tB, m, n, k, A.ptr, A.dims[0], B.ptr, B.dims[0], Cd.ptr, m, 0)

@@ -204,8 +204,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int m0 = (t % p.num_m) * TM, n0 = (t / p.num_m) * TN;
       for (int kb = 0; kb < nkb; kb++) {
-        mbar_wait(&empty[stage], phase ^ 1);
-        if (lane == 0) mbar_expect_tx(&full[stage], S::STAGE_BYTES);
+        if (lane == 0) {  // one poller per warp; the other lanes are released by the warp barrier
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], S::STAGE_BYTES);
+        }
         __syncwarp();
         unsigned char* sa = smem + stage * S::STAGE_BYTES;
         unsigned char* sb = sa + S::A_BYTES;
@@ -400,7 +402,7 @@ static int launch(const GemmArgs& g, const CUtensorMap& ma, const CUtensorMap& m
   p.C = g.C;
   p.ldc = g.ldc;
   p.accumulate = g.accumulate;
-  p.spread = getenv("YOTA_TMA_1LANE") ? 0 : 1;
+  p.spread = getenv("YOTA_TMA_SPREAD") ? 1 : 0;
   p.num_m = (int)(g.M / TM);
   p.num_n = (int)(g.N / TN);
   const int tiles = p.num_m * p.num_n;
@@ -551,8 +553,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const int m0 = (t % p.num_m) * (2 * TM) + (int)rank * TM;
       const int n0 = (t / p.num_m) * TN2 + (int)rank * TNH;
       for (int kb = 0; kb < nkb; kb++) {
-        mbar_wait(&empty[stage], phase ^ 1);
         if (lane == 0) {
+          mbar_wait(&empty[stage], phase ^ 1);
           if (leader)
             mbar_expect_tx(&full[stage], 2 * S::STAGE_BYTES);
           else
@@ -562,7 +564,22 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         unsigned char* sa = smem + stage * S::STAGE_BYTES;
         unsigned char* sb = sa + S::A_BYTES;
         const int k0 = kb * TK;
-        if (lane < NA) {
+        if (!p.spread) {
+          if (lane == 0) {
+            if (A_MN) {
+#pragma unroll
+              for (int c = 0; c < NA; c++)
+                tma_load_2d_2sm(sa + c * E::CHUNK_BYTES, &map_a, &full[stage], m0 + E::CHUNK * c, k0);
+            } else
+              tma_load_2d_2sm(sa, &map_a, &full[stage], k0, m0);
+            if (B_MN) {
+#pragma unroll
+              for (int c = 0; c < NB; c++)
+                tma_load_2d_2sm(sb + c * E::CHUNK_BYTES, &map_b, &full[stage], n0 + E::CHUNK * c, k0);
+            } else
+              tma_load_2d_2sm(sb, &map_b, &full[stage], k0, n0);
+          }
+        } else if (lane < NA) {
           if (A_MN)
             tma_load_2d_2sm(sa + lane * E::CHUNK_BYTES, &map_a, &full[stage], m0 + E::CHUNK * lane, k0);
           else
@@ -687,7 +704,7 @@ static int launch2(const GemmArgs& g, const CUtensorMap& ma, const CUtensorMap& 
   p.C = g.C;
   p.ldc = g.ldc;
   p.accumulate = g.accumulate;
-  p.spread = 1;
+  p.spread = getenv("YOTA_TMA_SPREAD") ? 1 : 0;
   p.num_m = (int)(g.M / (2 * TM));
   p.num_n = (int)(g.N / TN2);
   const int tiles = p.num_m * p.num_n;
