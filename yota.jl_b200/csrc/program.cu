@@ -436,12 +436,17 @@ struct Fuser {
         const TInfo& a = P.T[P.ops[gi].in[j]];
         if (a.region >= 0 && same_dims(a, out.dims, out.nd) && a.region > best) best = a.region;
       }
-    if (best >= 0 && can_join(g, best)) {
-      do_join(g, best);
+    // Consumer-driven fusion: an op stays unplaced as long as nothing forces its value into
+    // memory; it is placed together with the first consumer that must be (an output, the
+    // operand of a GEMM / reduction / gather).  A value that is needed in memory anyway (the
+    // layer activation H) is then never accompanied by stored derivatives of itself (1 - H^2 is
+    // recomputed inside the pullback pass that consumes it).
+    if (allow_float && group_inputs(g) <= RG_MAX_IN - 2 && g.size() <= 32) {
+      out.region = FLOATING;
       return;
     }
-    if (best < 0 && allow_float && group_inputs(g) <= RG_MAX_IN - 2 && g.size() <= 32) {
-      out.region = FLOATING;
+    if (best >= 0 && can_join(g, best)) {
+      do_join(g, best);
       return;
     }
     // sibling fusion: the latest region of this shape that already has every operand
