@@ -97,3 +97,51 @@ def test_mlp_gradients_in_bf16_mode():
     for a, b in zip(g[1:], g64[1:]):
         a = a.to_host()
         assert np.max(np.abs(a - b)) <= 3e-2 * np.max(np.abs(b)), np.max(np.abs(a - b)) / np.max(np.abs(b))
+
+
+# ---- 2-CTA (cta_group::2) kernel and fused epilogues at test-sized shapes -------------------
+@pytest.fixture
+def force_2cta(monkeypatch):
+    monkeypatch.setenv("YOTA_GEMM_FORCE_2CTA", "1")
+    Y.reset()
+    yield
+    Y.reset()
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("tA,tB", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_2cta_exact_on_small_integers(force_2cta, mode, tA, tB):
+    r = cases.rng(24)
+    for m, n, k in [(256, 256, 64), (512, 768, 192), (1024, 512, 320)]:
+        A = r.integers(-3, 4, size=(k, m) if tA else (m, k)).astype(F32)
+        B = r.integers(-3, 4, size=(n, k) if tB else (k, n)).astype(F32)
+        ref = (A.T if tA else A).astype(np.float64) @ (B.T if tB else B).astype(np.float64)
+        got = U.gemm(mode, tA, tB, np.asfortranarray(A), np.asfortranarray(B))
+        assert np.array_equal(got, ref), (m, n, k)
+        C0 = np.asfortranarray(r.integers(-5, 6, size=(m, n)).astype(F32))
+        assert np.array_equal(U.gemm(mode, tA, tB, np.asfortranarray(A), np.asfortranarray(B), C0), ref + C0)
+
+
+@pytest.mark.parametrize("flags,tol", [(ffi.FLAG_GEMM_TF32, 5e-3), (ffi.FLAG_GEMM_BF16, 3e-2)])
+def test_fused_epilogues_match_unfused(force_2cta, monkeypatch, flags, tol):
+    """bias+tanh and tanh'*delta+db run inside the GEMM epilogue: same elementwise arithmetic on
+    the same accumulators as the separate region pass, so activations-derived gradients agree
+    to FP32 summation order (db) / exactly (everything elementwise)."""
+    f, args = cases.make_c3(4, 512), cases.c3_args(4, 256, 512)
+    dargs = [Y.cu(a) for a in args]
+    gf = Y.CompiledGrad(Y.gradtape(f, *dargs), flags=flags)
+    assert "epilogue{region[add,tanh]}" in gf.describe() and "epilogue{region[square,rsubc,mul]+sum}" in gf.describe()
+    v1, g1 = gf.run(dargs)
+    g1 = [x.to_host() for x in g1]
+    v1 = float(v1.to_host())
+    monkeypatch.setenv("YOTA_NO_EPILOGUE", "1")
+    gu = Y.CompiledGrad(Y.gradtape(f, *dargs), flags=flags)
+    assert "epilogue" not in gu.describe()
+    v2, g2 = gu.run(dargs)
+    assert abs(v1 - float(v2.to_host())) <= 1e-6 * abs(v1)
+    for a, b in zip(g1, g2):
+        b = b.to_host()
+        assert np.max(np.abs(a - b)) <= 2e-5 * np.max(np.abs(b)), np.max(np.abs(a - b)) / np.max(np.abs(b))
+    v64, g64 = O.grad(f, *U.to_f64(args), dtype=np.float64)
+    for a, b in zip(g1, g64[1:]):
+        assert np.max(np.abs(a - b)) <= tol * np.max(np.abs(b))

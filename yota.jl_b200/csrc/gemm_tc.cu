@@ -32,6 +32,7 @@
 #include <stdlib.h>
 
 #include "common.h"
+#include "ew_chain.cuh"
 
 namespace yota {
 
@@ -494,9 +495,74 @@ __device__ __forceinline__ void umma_2sm(uint32_t d_tmem, uint64_t a_desc, uint6
         : "memory");
 }
 
-template <bool A_MN, bool B_MN, int EB>
+
+// ---- fused epilogues -------------------------------------------------------------------------
+// The consumer region of a GEMM output (bias [+ tanh] after W*h; tanh'(h) * delta + db after
+// W'*dz) runs on the accumulator tile instead of as a separate pass: the SAME ahead-of-time
+// micro-program (ChainOf<ID>) the region kernel would execute, with the accumulator element
+// standing in for the region's FULL operand `z_in`.  The epilogue's thread mapping (thread =
+// row m, walking the tile's columns) is the region kernel's mapping, so ROWVEC operands (bias)
+// are loaded once per tile and row sums (db) accumulate per thread in column order and leave
+// as partial[tile_n][m] for the same fixed-order finisher.
+#define YCE(field, i) (ChainOf<ID>::value.field[decltype(i)::value])
+template <int ID>
+struct Epilogue {
+  static constexpr int N_IN = ChainOf<ID>::value.n_in, N_OPS = ChainOf<ID>::value.n_ops, N_OUT = ChainOf<ID>::value.n_out;
+  static constexpr int NS = ChainOf<ID>::value.n_slots > 0 ? ChainOf<ID>::value.n_slots : 1;
+  static constexpr int NO = N_OUT > 0 ? N_OUT : 1;
+
+  __device__ __forceinline__ static void begin_tile(const RegionParams& rp, long long m, float (&base)[NS],
+                                                    float (&accs)[NO]) {
+    static_for<NS>([&](auto s) { base[decltype(s)::value] = 0.f; });
+    static_for<NO>([&](auto k) { accs[decltype(k)::value] = 0.f; });
+    static_for<N_IN>([&](auto k) {
+      constexpr int cls = YCE(in_cls, k), slot = YCE(in_slot, k);
+      if constexpr (cls == CLS_ROWVEC) base[slot] = __ldg(rp.in[decltype(k)::value].ptr + m);
+      if constexpr (cls == CLS_SCALAR) base[slot] = __ldg(rp.in[decltype(k)::value].ptr);
+    });
+  }
+  // one element: accumulator value z at (m, n)
+  __device__ __forceinline__ static void element(const RegionParams& rp, int z_in, float z, long long m, long long n,
+                                                 long long R, const float (&base)[NS], float (&accs)[NO]) {
+    float v[NS];
+    static_for<NS>([&](auto s) { v[decltype(s)::value] = base[decltype(s)::value]; });
+    const long long off = n * R + m;
+    static_for<N_IN>([&](auto k) {
+      constexpr int cls = YCE(in_cls, k), slot = YCE(in_slot, k);
+      if constexpr (cls == CLS_FULL) v[slot] = (decltype(k)::value == z_in) ? z : __ldg(rp.in[decltype(k)::value].ptr + off);
+      if constexpr (cls == CLS_COLVEC) v[slot] = __ldg(rp.in[decltype(k)::value].ptr + n);
+    });
+    float acc = 0.f;
+    static_for<N_OPS>([&](auto i) {
+      constexpr int OP = YCE(op, i), D = YCE(dst, i), A = YCE(a, i), B = YCE(b, i);
+      float a, b;
+      if constexpr (A == RG_ACC) a = acc; else a = v[A];
+      if constexpr (B == RG_ACC) b = acc; else b = v[B];
+      acc = ew_v<OP>(a, b, rp.ops[decltype(i)::value].imm);
+      if constexpr (D != RG_NONE) v[D] = acc;
+    });
+    static_for<N_OUT>([&](auto k) {
+      constexpr int kind = YCE(out_kind, k), src = YCE(out_src, k);
+      if constexpr (kind == OUT_STORE)
+        rp.out[decltype(k)::value].ptr[off] = v[src];
+      else
+        accs[decltype(k)::value] = __fadd_rn(accs[decltype(k)::value], v[src]);
+    });
+  }
+  __device__ __forceinline__ static void end_tile(const RegionParams& rp, long long m, long long tile_n, long long R,
+                                                  const float (&accs)[NO]) {
+    static_for<N_OUT>([&](auto k) {
+      constexpr int kind = YCE(out_kind, k);
+      if constexpr (kind == OUT_ROWSUM) rp.out[decltype(k)::value].ptr[tile_n * R + m] = accs[decltype(k)::value];
+    });
+  }
+};
+#undef YCE
+
+template <bool A_MN, bool B_MN, int EB, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
-gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p,
+                const __grid_constant__ RegionParams rp, const int z_in) {
   using S = Smem2;
   using E = El<EB>;
   constexpr int TK = E::TK;
@@ -648,6 +714,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       mbar_wait(&tfull[acc], acc_phase);
       tcgen05_fence_after();
       float* crow = p.C + m + n0 * p.ldc;
+      using EP = Epilogue<(EPI >= 0 ? EPI : 0)>;
+      float ebase[EP::NS], eaccs[EP::NO];
+      if constexpr (EPI >= 0) EP::begin_tile(rp, m, ebase, eaccs);
 #pragma unroll 1
       for (int c = 0; c < TN2 / 32; c++) {
         uint32_t v[32];
@@ -663,15 +732,22 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             : "r"(taddr)
             : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        float* cp = crow + (long long)(c * 32) * p.ldc;
-        if (p.accumulate) {
+        if constexpr (EPI >= 0) {
 #pragma unroll
-          for (int j = 0; j < 32; j++) cp[j * p.ldc] = __uint_as_float(v[j]) + cp[j * p.ldc];
+          for (int j = 0; j < 32; j++)
+            EP::element(rp, z_in, __uint_as_float(v[j]), m, n0 + c * 32 + j, p.M, ebase, eaccs);
         } else {
+          float* cp = crow + (long long)(c * 32) * p.ldc;
+          if (p.accumulate) {
 #pragma unroll
-          for (int j = 0; j < 32; j++) cp[j * p.ldc] = __uint_as_float(v[j]);
+            for (int j = 0; j < 32; j++) cp[j * p.ldc] = __uint_as_float(v[j]) + cp[j * p.ldc];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j++) cp[j * p.ldc] = __uint_as_float(v[j]);
+          }
         }
       }
+      if constexpr (EPI >= 0) EP::end_tile(rp, m, t / p.num_m, p.M, eaccs);
       tcgen05_fence_before();
       mbar_arrive_remote(&tempty[acc], 0);  // the leader's MMA warp waits for both CTAs' epilogues
       if (++acc == 2) {
@@ -689,10 +765,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   }
 }
 
-template <bool A_MN, bool B_MN, int EB>
-static int launch2(const GemmArgs& g, const CUtensorMap& ma, const CUtensorMap& mb, int sm_count, cudaStream_t s) {
+template <bool A_MN, bool B_MN, int EB, int EPI = -1>
+static int launch2(const GemmArgs& g, const CUtensorMap& ma, const CUtensorMap& mb, int sm_count, cudaStream_t s,
+                   const RegionParams* rp = nullptr, int z_in = -1) {
   static bool attr = false;
-  auto kern = gemm_tc2_kernel<A_MN, B_MN, EB>;
+  auto kern = gemm_tc2_kernel<A_MN, B_MN, EB, EPI>;
   if (!attr) {
     YOTA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem2::TOTAL));
     attr = true;
@@ -710,7 +787,8 @@ static int launch2(const GemmArgs& g, const CUtensorMap& ma, const CUtensorMap& 
   const int tiles = p.num_m * p.num_n;
   int pairs = sm_count / 2;
   if (tiles < pairs) pairs = tiles;
-  kern<<<2 * pairs, THREADS, Smem2::TOTAL, s>>>(ma, mb, p);
+  static const RegionParams no_rp{};
+  kern<<<2 * pairs, THREADS, Smem2::TOTAL, s>>>(ma, mb, p, rp ? *rp : no_rp, z_in);
   YOTA_CUDA(cudaGetLastError());
   return YOTA_OK;
 }
@@ -727,6 +805,50 @@ bool gemm_tc_eligible(const GemmArgs& g) {
   return true;
 }
 
+bool gemm_tc2_eligible(const GemmArgs& g, int sm_count) {
+  if (!gemm_tc_eligible(g) || getenv("YOTA_GEMM_1CTA")) return false;
+  if (g.M % 256 || g.N % 256) return false;
+  const long long tiles = (g.M / 256) * (g.N / 256);
+  return getenv("YOTA_GEMM_FORCE_2CTA") ? tiles >= 1 : tiles >= sm_count / 4;
+}
+
+bool gemm_epilogue_chain_ok(int static_id, int transA, int transB) {
+  // instantiated: forward (A not transposed, B not transposed) and dh (A transposed) GEMMs
+  if (transB) return false;
+  switch (static_id) {
+#define X(ID) \
+  case ID:    \
+    return true;
+    YOTA_EPI_CHAIN_LIST(X)
+#undef X
+  }
+  return false;
+}
+
+// GEMM whose output tile goes straight through the consumer region's micro-program
+int launch_gemm_tc_epilogue(yota_ctx* ctx, const GemmArgs& g, int static_id, const RegionParams& rp, int z_in,
+                            cudaStream_t s) {
+  if (!gemm_tc2_eligible(g, ctx->sm_count) || g.accumulate || !gemm_epilogue_chain_ok(static_id, g.transA, g.transB))
+    YOTA_FAIL(YOTA_E_ARG, "internal: GEMM epilogue fusion planned for an ineligible GEMM");
+  const bool A_MN = !g.transA;
+  const int eb = g.mode == 1 ? 4 : 2;
+  CUtensorMap ma, mb;
+  YOTA_TRY(tc::make_map(&ma, g.A, g.M, g.K, g.lda, A_MN, tc::TM, eb));
+  YOTA_TRY(tc::make_map(&mb, g.B, g.N, g.K, g.ldb, false, tc::TN2 / 2, eb));
+  switch (static_id) {
+#define X(ID)                                                                                              \
+  case ID:                                                                                                 \
+    if (A_MN)                                                                                              \
+      return eb == 4 ? tc::launch2<true, false, 4, ID>(g, ma, mb, ctx->sm_count, s, &rp, z_in)             \
+                     : tc::launch2<true, false, 2, ID>(g, ma, mb, ctx->sm_count, s, &rp, z_in);            \
+    return eb == 4 ? tc::launch2<false, false, 4, ID>(g, ma, mb, ctx->sm_count, s, &rp, z_in)              \
+                   : tc::launch2<false, false, 2, ID>(g, ma, mb, ctx->sm_count, s, &rp, z_in);
+    YOTA_EPI_CHAIN_LIST(X)
+#undef X
+  }
+  YOTA_FAIL(YOTA_E_ARG, "internal: no epilogue kernel for chain %d", static_id);
+}
+
 // mode 1: A/B are the Float32 arrays (read as TF32).  mode 2: A/B point at BF16 shadows with the
 // same dims / leading dimensions (see launch_cast_bf16 and the planner's shadow tensors).
 int launch_gemm_tc(yota_ctx* ctx, const GemmArgs& g, cudaStream_t s) {
@@ -735,8 +857,7 @@ int launch_gemm_tc(yota_ctx* ctx, const GemmArgs& g, cudaStream_t s) {
   const bool B_MN = g.transB != 0;  // B stored N x K column-major: N contiguous
   const int eb = g.mode == 1 ? 4 : 2;
   CUtensorMap ma, mb;
-  const bool two_cta = !getenv("YOTA_GEMM_1CTA") && g.M % 256 == 0 && g.N % 256 == 0 &&
-                       (g.M / 256) * (g.N / 256) >= ctx->sm_count / 4;
+  const bool two_cta = gemm_tc2_eligible(g, ctx->sm_count);
   if (two_cta) {
     // each CTA of a pair loads a 128-row box of A and a 128-column box of B
     YOTA_TRY(tc::make_map(&ma, g.A, g.M, g.K, g.lda, A_MN, tc::TM, eb));

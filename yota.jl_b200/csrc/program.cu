@@ -38,7 +38,8 @@ enum StepKind {
   STEP_TRANSPOSE,
   STEP_CAT,
   STEP_SLICE,
-  STEP_SLICE_ACCUM  // out (aliasing acc) [I...] += dy : in-place form of ADD(UNGETINDEX(dy), acc)
+  STEP_SLICE_ACCUM,  // out (aliasing acc) [I...] += dy : in-place form of ADD(UNGETINDEX(dy), acc)
+  STEP_NOP           // a region that was absorbed as the epilogue of a GEMM
 };
 
 struct TInfo {
@@ -95,6 +96,8 @@ struct Step {
   bool cast[2] = {false, false};  // this step is the first user: cast before the GEMM
   int out_override = -1;  // in-place accumulation: the ADD's output tensor (aliases acc_tensor)
   int acc_tensor = -1;
+  int epi_region = -1;    // GEMM: consumer region executed as the epilogue
+  int epi_z_in = -1;      // index of the region input that is the GEMM output
 };
 
 }  // namespace yota
@@ -989,8 +992,8 @@ static int plan_memory(yota_program& P) {
     for (auto& sh : P.shadows)
       if (sh.first_step == s) sh.arena_off = (long long)fl.alloc((size_t)P.T[sh.tensor].numel * 2);
     for (int t : defs[s]) P.T[t].arena_off = (long long)fl.alloc((size_t)P.T[t].numel * elem_size(P.T[t]));
-    if (st.kind == STEP_REGION) {
-      Region& r = P.regions[st.region];
+    if (st.kind == STEP_REGION || (st.kind == STEP_GEMM && st.epi_region >= 0)) {
+      Region& r = P.regions[st.kind == STEP_REGION ? st.region : st.epi_region];
       const int n_store = r.L.p.n_out - (int)r.sums.size();
       for (size_t q = 0; q < r.sums.size(); q++) {
         Step& fs = P.steps[r.finish_steps[q]];
@@ -1061,6 +1064,85 @@ static int index_spec_of(const yota_program& P, const yota_op_desc& o, const TIn
   }
   sp.nd_x = sp.n;
   *n_sel = nsel;
+  return YOTA_OK;
+}
+
+// GEMM -> consumer-region fusion: when the only reader of a tensor-core GEMM's output is one
+// fused region whose micro-program exists as an epilogue variant (bias [+ tanh]; tanh' * delta
+// + db), the region runs inside the GEMM's epilogue and the GEMM output never touches HBM.
+static int plan_gemm_epilogues(yota_program& P) {
+  if (P.flags & YOTA_FLAG_NO_FUSE) return YOTA_OK;
+  const int mode = (P.flags & YOTA_FLAG_GEMM_TF32) ? 1 : (P.flags & YOTA_FLAG_GEMM_BF16) ? 2 : 0;
+  if (mode == 0 || getenv("YOTA_NO_EPILOGUE")) return YOTA_OK;
+  for (size_t si = 0; si < P.steps.size(); si++) {
+    Step& gs = P.steps[si];
+    if (gs.kind != STEP_GEMM || gs.acc_tensor >= 0) continue;
+    const yota_op_desc& o = P.ops[gs.op];
+    const int z = o.out;
+    const TInfo& zt = P.T[z];
+    if (zt.d.kind != YOTA_T_TEMP || zt.alias_of >= 0) continue;
+    GemmArgs g{};
+    g.mode = mode;
+    g.transA = (int)o.iattr[0];
+    g.transB = (int)o.iattr[1];
+    gemm_dims(P, o, &g.M, &g.N, &g.K, &g.lda, &g.ldb);
+    if (!gemm_tc2_eligible(g, P.ctx->sm_count)) continue;
+    // every needed consumer of z is an elementwise op of one region
+    int ri = -1;
+    bool ok = true;
+    for (int c : zt.consumers) {
+      if (!P.op_needed[c]) continue;
+      const yota_op_desc& co = P.ops[c];
+      if (!is_ew(co.opcode) || P.T[co.out].region < 0) ok = false;
+      else if (ri < 0) ri = P.T[co.out].region;
+      else if (ri != P.T[co.out].region) ok = false;
+    }
+    if (!ok || ri < 0) continue;
+    for (size_t q = 0; q < P.T.size(); q++)  // an alias (reshape) of z read elsewhere keeps it in memory
+      if (P.T[q].alias_of == z && P.T[q].needed) ok = false;
+    Region& r = P.regions[ri];
+    const RegionParams& rp = r.L.p;
+    if (!ok || r.L.static_id < 0 || r.step <= (int)si || P.steps[r.step].kind != STEP_REGION) continue;
+    if (!gemm_epilogue_chain_ok(r.L.static_id, g.transA, g.transB)) continue;
+    if (r.k != 1 || rp.R != g.M || rp.C != g.N) continue;
+    int z_in = -1;
+    for (int q = 0; q < rp.n_in; q++) {
+      if (r.in_tensors[q] == z) {
+        z_in = q;
+        if (rp.in[q].cls != CLS_FULL) ok = false;
+      } else if (step_of_tensor(P, r.in_tensors[q]) >= (int)si) {
+        ok = false;  // another operand of the region is not ready when the GEMM runs
+      }
+    }
+    if (!ok || z_in < 0) continue;
+    // absorb
+    gs.epi_region = ri;
+    gs.epi_z_in = z_in;
+    gs.label += " + epilogue{" + P.steps[r.step].label.substr(0, P.steps[r.step].label.find(' ')) + "}";
+    for (int t : r.in_tensors)
+      if (t != z) gs.reads.push_back(t);
+    Step& rs = P.steps[r.step];
+    rs.kind = STEP_NOP;
+    rs.label = "(absorbed into step " + std::to_string(si) + ")";
+    rs.reads.clear();
+    const int n_store = rp.n_out - (int)r.sums.size();
+    for (int q = 0; q < n_store; q++) {
+      P.T[r.out_tensors[q]].def_step = (int)si;
+      gs.writes.push_back(r.out_tensors[q]);
+    }
+    rs.writes.clear();
+    P.T[z].materialized = false;
+    // row-sum partials: one row per 256-column tile of the GEMM
+    const int P_tiles = (int)(g.N / 256);
+    for (size_t q = 0; q < r.sums.size(); q++) {
+      Step& fs = P.steps[r.finish_steps[q]];
+      if (fs.kind != STEP_ROWSUM_FINISH) return YOTA_E_ARG;
+      fs.P = P_tiles;
+      fs.ws_bytes = (size_t)P_tiles * g.M * sizeof(float);
+      fs.ws_owner_step = (int)si;
+    }
+    r.step = (int)si;  // workspaces are allocated when the GEMM runs
+  }
   return YOTA_OK;
 }
 
@@ -1165,6 +1247,7 @@ extern "C" int yota_program_build(yota_ctx* ctx, const yota_op_desc* ops, int64_
   if ((st = plan_fusion(P))) return fail(st);
   for (size_t r = 0; r < P.regions.size(); r++)
     if ((st = codegen_region(P, (int)r))) return fail(st);
+  if ((st = plan_gemm_epilogues(P))) return fail(st);
   if ((st = finish_steps(P))) return fail(st);
   if ((st = plan_bf16_shadows(P))) return fail(st);
   if ((st = plan_memory(P))) return fail(st);
@@ -1254,28 +1337,47 @@ static int ensure_arena(yota_program& P) {
   return YOTA_OK;
 }
 
+static int bind_region(yota_program& P, Region& r, RegionLaunch& L) {
+  const int n_store = L.p.n_out - (int)r.sums.size();
+  for (int q = 0; q < L.p.n_in; q++) {
+    L.p.in[q].ptr = static_cast<const float*>(tensor_ptr(P, r.in_tensors[q]));
+    if (L.V == 4 && (reinterpret_cast<uintptr_t>(L.p.in[q].ptr) & 15) &&
+        (L.p.in[q].cls == CLS_FULL || L.p.in[q].cls == CLS_ROWVEC))
+      YOTA_FAIL(YOTA_E_ARG, "array bound to the program is not 16-byte aligned (use yota_alloc)");
+  }
+  for (int q = 0; q < L.p.n_out; q++) {
+    if (q < n_store) {
+      L.p.out[q].ptr = static_cast<float*>(tensor_ptr(P, r.out_tensors[q]));
+      if (L.V == 4 && (reinterpret_cast<uintptr_t>(L.p.out[q].ptr) & 15))
+        YOTA_FAIL(YOTA_E_ARG, "array bound to the program is not 16-byte aligned (use yota_alloc)");
+    } else
+      L.p.out[q].ptr = reinterpret_cast<float*>(P.arena + r.ws_off[q]);
+  }
+  return YOTA_OK;
+}
+
+static int run_gemm_epilogue(yota_program& P, Step& st, const GemmArgs& g, cudaStream_t s) {
+  Region& r = P.regions[st.epi_region];
+  RegionLaunch L = r.L;
+  L.p.in[st.epi_z_in].ptr = nullptr;  // the accumulator stands in for this operand
+  for (int q = 0; q < L.p.n_in; q++)
+    if (q != st.epi_z_in) L.p.in[q].ptr = static_cast<const float*>(tensor_ptr(P, r.in_tensors[q]));
+  const int n_store = L.p.n_out - (int)r.sums.size();
+  for (int q = 0; q < L.p.n_out; q++)
+    L.p.out[q].ptr = q < n_store ? static_cast<float*>(tensor_ptr(P, r.out_tensors[q]))
+                                 : reinterpret_cast<float*>(P.arena + r.ws_off[q]);
+  return launch_gemm_tc_epilogue(P.ctx, g, L.static_id, L.p, st.epi_z_in, s);
+}
+
 static int run_step(yota_program& P, Step& st, cudaStream_t s) {
   switch (st.kind) {
     case STEP_REGION: {
       Region& r = P.regions[st.region];
       RegionLaunch L = r.L;
-      const int n_store = L.p.n_out - (int)r.sums.size();
-      for (int q = 0; q < L.p.n_in; q++) {
-        L.p.in[q].ptr = static_cast<const float*>(tensor_ptr(P, r.in_tensors[q]));
-        if (L.V == 4 && (reinterpret_cast<uintptr_t>(L.p.in[q].ptr) & 15) &&
-            (L.p.in[q].cls == CLS_FULL || L.p.in[q].cls == CLS_ROWVEC))
-          YOTA_FAIL(YOTA_E_ARG, "array bound to the program is not 16-byte aligned (use yota_alloc)");
-      }
-      for (int q = 0; q < L.p.n_out; q++) {
-        if (q < n_store) {
-          L.p.out[q].ptr = static_cast<float*>(tensor_ptr(P, r.out_tensors[q]));
-          if (L.V == 4 && (reinterpret_cast<uintptr_t>(L.p.out[q].ptr) & 15))
-            YOTA_FAIL(YOTA_E_ARG, "array bound to the program is not 16-byte aligned (use yota_alloc)");
-        } else
-          L.p.out[q].ptr = reinterpret_cast<float*>(P.arena + r.ws_off[q]);
-      }
+      YOTA_TRY(bind_region(P, r, L));
       return launch_region(L, s);
     }
+    case STEP_NOP: return YOTA_OK;
     case STEP_ROWSUM_FINISH:
       return launch_rowsum_finish(static_cast<float*>(tensor_ptr(P, st.out_tensor)),
                                   reinterpret_cast<const float*>(P.arena + st.ws_off), st.R, st.P, st.scale, s);
@@ -1338,8 +1440,10 @@ static int run_step(yota_program& P, Step& st, cudaStream_t s) {
         }
         g.A = sh[0];
         g.B = sh[1];
+        if (st.epi_region >= 0) return run_gemm_epilogue(P, st, g, s);
         return launch_gemm_tc(P.ctx, g, s);
       }
+      if (st.epi_region >= 0) return run_gemm_epilogue(P, st, g, s);
       if (g.mode == 1 && gemm_tc_eligible(g)) return launch_gemm_tc(P.ctx, g, s);
       g.mode = 0;
       return launch_gemm_ffma(g, s);
