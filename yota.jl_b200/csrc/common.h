@@ -162,7 +162,7 @@ int launch_gemm_ffma(const GemmArgs& g, cudaStream_t s);
 int launch_gemm_tc(yota_ctx* ctx, const GemmArgs& g, cudaStream_t s);  // returns YOTA_E_UNSUPPORTED_OP if shape not eligible
 bool gemm_tc_eligible(const GemmArgs& g);
 bool gemm_tc2_eligible(const GemmArgs& g, int sm_count);
-bool gemm_epilogue_chain_ok(int static_id, int transA, int transB);
+bool gemm_epilogue_chain_ok(int static_id, int transA, int transB, int z_in);
 int launch_gemm_tc_epilogue(yota_ctx* ctx, const GemmArgs& g, int static_id, const RegionParams& rp, int z_in,
                             cudaStream_t s);
 int launch_cast_bf16(void* dst, const float* src, long long n, cudaStream_t s);

@@ -505,7 +505,7 @@ __device__ __forceinline__ void umma_2sm(uint32_t d_tmem, uint64_t a_desc, uint6
 // are loaded once per tile and row sums (db) accumulate per thread in column order and leave
 // as partial[tile_n][m] for the same fixed-order finisher.
 #define YCE(field, i) (ChainOf<ID>::value.field[decltype(i)::value])
-template <int ID>
+template <int ID, int Z_IN>
 struct Epilogue {
   static constexpr int N_IN = ChainOf<ID>::value.n_in, N_OPS = ChainOf<ID>::value.n_ops, N_OUT = ChainOf<ID>::value.n_out;
   static constexpr int NS = ChainOf<ID>::value.n_slots > 0 ? ChainOf<ID>::value.n_slots : 1;
@@ -521,33 +521,55 @@ struct Epilogue {
       if constexpr (cls == CLS_SCALAR) base[slot] = __ldg(rp.in[decltype(k)::value].ptr);
     });
   }
-  // one element: accumulator value z at (m, n)
-  __device__ __forceinline__ static void element(const RegionParams& rp, int z_in, float z, long long m, long long n,
-                                                 long long R, const float (&base)[NS], float (&accs)[NO]) {
-    float v[NS];
-    static_for<NS>([&](auto s) { v[decltype(s)::value] = base[decltype(s)::value]; });
-    const long long off = n * R + m;
+  // one chunk of 32 consecutive columns: accumulator values z[j] at (m, n0 + j).  The other FULL
+  // operands of the chunk are loaded up front (32 independent loads in flight per operand) --
+  // left per element, each load sits between the previous element's store and its own use and
+  // the epilogue runs at one DRAM latency per element.
+  __device__ __forceinline__ static void chunk32(const RegionParams& rp, const uint32_t (&z)[32], long long m,
+                                                 long long n0, long long R, const float (&base)[NS], float (&accs)[NO]) {
+    constexpr int NI = N_IN > 0 ? N_IN : 1;
+    float pre[NI][32];
     static_for<N_IN>([&](auto k) {
-      constexpr int cls = YCE(in_cls, k), slot = YCE(in_slot, k);
-      if constexpr (cls == CLS_FULL) v[slot] = (decltype(k)::value == z_in) ? z : __ldg(rp.in[decltype(k)::value].ptr + off);
-      if constexpr (cls == CLS_COLVEC) v[slot] = __ldg(rp.in[decltype(k)::value].ptr + n);
+      constexpr int K = decltype(k)::value, cls = YCE(in_cls, k);
+      if constexpr (cls == CLS_FULL && K != Z_IN) {
+        const float* src = rp.in[K].ptr + n0 * R + m;
+#pragma unroll
+        for (int j = 0; j < 32; j++) pre[K][j] = __ldg(src + (long long)j * R);
+      }
+      if constexpr (cls == CLS_COLVEC) {
+        // lanes read consecutive entries once and broadcast them with shuffles
+        const float mine = __ldg(rp.in[K].ptr + n0 + (threadIdx.x & 31));
+#pragma unroll
+        for (int j = 0; j < 32; j++) pre[K][j] = __shfl_sync(0xffffffffu, mine, j);
+      }
     });
-    float acc = 0.f;
-    static_for<N_OPS>([&](auto i) {
-      constexpr int OP = YCE(op, i), D = YCE(dst, i), A = YCE(a, i), B = YCE(b, i);
-      float a, b;
-      if constexpr (A == RG_ACC) a = acc; else a = v[A];
-      if constexpr (B == RG_ACC) b = acc; else b = v[B];
-      acc = ew_v<OP>(a, b, rp.ops[decltype(i)::value].imm);
-      if constexpr (D != RG_NONE) v[D] = acc;
-    });
-    static_for<N_OUT>([&](auto k) {
-      constexpr int kind = YCE(out_kind, k), src = YCE(out_src, k);
-      if constexpr (kind == OUT_STORE)
-        rp.out[decltype(k)::value].ptr[off] = v[src];
-      else
-        accs[decltype(k)::value] = __fadd_rn(accs[decltype(k)::value], v[src]);
-    });
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+      float v[NS];
+      static_for<NS>([&](auto s) { v[decltype(s)::value] = base[decltype(s)::value]; });
+      const long long off = (n0 + j) * R + m;
+      static_for<N_IN>([&](auto k) {
+        constexpr int K = decltype(k)::value, cls = YCE(in_cls, k), slot = YCE(in_slot, k);
+        if constexpr (cls == CLS_FULL) v[slot] = (K == Z_IN) ? __uint_as_float(z[j]) : pre[K][j];
+        if constexpr (cls == CLS_COLVEC) v[slot] = pre[K][j];
+      });
+      float acc = 0.f;
+      static_for<N_OPS>([&](auto i) {
+        constexpr int OP = YCE(op, i), D = YCE(dst, i), A = YCE(a, i), B = YCE(b, i);
+        float a, b;
+        if constexpr (A == RG_ACC) a = acc; else a = v[A];
+        if constexpr (B == RG_ACC) b = acc; else b = v[B];
+        acc = ew_v<OP>(a, b, rp.ops[decltype(i)::value].imm);
+        if constexpr (D != RG_NONE) v[D] = acc;
+      });
+      static_for<N_OUT>([&](auto k) {
+        constexpr int kind = YCE(out_kind, k), src = YCE(out_src, k);
+        if constexpr (kind == OUT_STORE)
+          rp.out[decltype(k)::value].ptr[off] = v[src];
+        else
+          accs[decltype(k)::value] = __fadd_rn(accs[decltype(k)::value], v[src]);
+      });
+    }
   }
   __device__ __forceinline__ static void end_tile(const RegionParams& rp, long long m, long long tile_n, long long R,
                                                   const float (&accs)[NO]) {
@@ -559,10 +581,10 @@ struct Epilogue {
 };
 #undef YCE
 
-template <bool A_MN, bool B_MN, int EB, int EPI>
+template <bool A_MN, bool B_MN, int EB, int EPI, int ZIN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p,
-                const __grid_constant__ RegionParams rp, const int z_in) {
+                const __grid_constant__ RegionParams rp) {
   using S = Smem2;
   using E = El<EB>;
   constexpr int TK = E::TK;
@@ -714,7 +736,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       mbar_wait(&tfull[acc], acc_phase);
       tcgen05_fence_after();
       float* crow = p.C + m + n0 * p.ldc;
-      using EP = Epilogue<(EPI >= 0 ? EPI : 0)>;
+      using EP = Epilogue<(EPI >= 0 ? EPI : 0), ZIN>;
       float ebase[EP::NS], eaccs[EP::NO];
       if constexpr (EPI >= 0) EP::begin_tile(rp, m, ebase, eaccs);
 #pragma unroll 1
@@ -733,9 +755,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if constexpr (EPI >= 0) {
-#pragma unroll
-          for (int j = 0; j < 32; j++)
-            EP::element(rp, z_in, __uint_as_float(v[j]), m, n0 + c * 32 + j, p.M, ebase, eaccs);
+          EP::chunk32(rp, v, m, n0 + c * 32, p.M, ebase, eaccs);
         } else {
           float* cp = crow + (long long)(c * 32) * p.ldc;
           if (p.accumulate) {
@@ -765,11 +785,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   }
 }
 
-template <bool A_MN, bool B_MN, int EB, int EPI = -1>
+template <bool A_MN, bool B_MN, int EB, int EPI = -1, int ZIN = 0>
 static int launch2(const GemmArgs& g, const CUtensorMap& ma, const CUtensorMap& mb, int sm_count, cudaStream_t s,
-                   const RegionParams* rp = nullptr, int z_in = -1) {
+                   const RegionParams* rp = nullptr) {
   static bool attr = false;
-  auto kern = gemm_tc2_kernel<A_MN, B_MN, EB, EPI>;
+  auto kern = gemm_tc2_kernel<A_MN, B_MN, EB, EPI, ZIN>;
   if (!attr) {
     YOTA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem2::TOTAL));
     attr = true;
@@ -788,7 +808,7 @@ static int launch2(const GemmArgs& g, const CUtensorMap& ma, const CUtensorMap& 
   int pairs = sm_count / 2;
   if (tiles < pairs) pairs = tiles;
   static const RegionParams no_rp{};
-  kern<<<2 * pairs, THREADS, Smem2::TOTAL, s>>>(ma, mb, p, rp ? *rp : no_rp, z_in);
+  kern<<<2 * pairs, THREADS, Smem2::TOTAL, s>>>(ma, mb, p, rp ? *rp : no_rp);
   YOTA_CUDA(cudaGetLastError());
   return YOTA_OK;
 }
@@ -812,23 +832,46 @@ bool gemm_tc2_eligible(const GemmArgs& g, int sm_count) {
   return getenv("YOTA_GEMM_FORCE_2CTA") ? tiles >= 1 : tiles >= sm_count / 4;
 }
 
-bool gemm_epilogue_chain_ok(int static_id, int transA, int transB) {
+// the accumulator may stand in for input 0 or 1 of the chain, if that input is a FULL operand
+template <int ID>
+static constexpr bool epi_z_ok(int z_in) {
+  return z_in >= 0 && z_in < 2 && z_in < ChainOf<ID>::value.n_in && ChainOf<ID>::value.in_cls[z_in] == CLS_FULL;
+}
+
+bool gemm_epilogue_chain_ok(int static_id, int transA, int transB, int z_in) {
   // instantiated: forward (A not transposed, B not transposed) and dh (A transposed) GEMMs
   if (transB) return false;
   switch (static_id) {
 #define X(ID) \
   case ID:    \
-    return true;
+    return epi_z_ok<ID>(z_in);
     YOTA_EPI_CHAIN_LIST(X)
 #undef X
   }
   return false;
 }
 
+namespace tc {
+template <int ID, int ZIN>
+static int launch_epi(const GemmArgs& g, const CUtensorMap& ma, const CUtensorMap& mb, int sm_count, cudaStream_t s,
+                      const RegionParams& rp, bool A_MN, int eb) {
+  if constexpr (epi_z_ok<ID>(ZIN)) {
+    if (A_MN)
+      return eb == 4 ? launch2<true, false, 4, ID, ZIN>(g, ma, mb, sm_count, s, &rp)
+                     : launch2<true, false, 2, ID, ZIN>(g, ma, mb, sm_count, s, &rp);
+    return eb == 4 ? launch2<false, false, 4, ID, ZIN>(g, ma, mb, sm_count, s, &rp)
+                   : launch2<false, false, 2, ID, ZIN>(g, ma, mb, sm_count, s, &rp);
+  } else {
+    YOTA_FAIL(YOTA_E_ARG, "internal: chain %d has no FULL operand %d", ID, ZIN);
+  }
+}
+}  // namespace tc
+
 // GEMM whose output tile goes straight through the consumer region's micro-program
 int launch_gemm_tc_epilogue(yota_ctx* ctx, const GemmArgs& g, int static_id, const RegionParams& rp, int z_in,
                             cudaStream_t s) {
-  if (!gemm_tc2_eligible(g, ctx->sm_count) || g.accumulate || !gemm_epilogue_chain_ok(static_id, g.transA, g.transB))
+  if (!gemm_tc2_eligible(g, ctx->sm_count) || g.accumulate ||
+      !gemm_epilogue_chain_ok(static_id, g.transA, g.transB, z_in))
     YOTA_FAIL(YOTA_E_ARG, "internal: GEMM epilogue fusion planned for an ineligible GEMM");
   const bool A_MN = !g.transA;
   const int eb = g.mode == 1 ? 4 : 2;
@@ -836,13 +879,10 @@ int launch_gemm_tc_epilogue(yota_ctx* ctx, const GemmArgs& g, int static_id, con
   YOTA_TRY(tc::make_map(&ma, g.A, g.M, g.K, g.lda, A_MN, tc::TM, eb));
   YOTA_TRY(tc::make_map(&mb, g.B, g.N, g.K, g.ldb, false, tc::TN2 / 2, eb));
   switch (static_id) {
-#define X(ID)                                                                                              \
-  case ID:                                                                                                 \
-    if (A_MN)                                                                                              \
-      return eb == 4 ? tc::launch2<true, false, 4, ID>(g, ma, mb, ctx->sm_count, s, &rp, z_in)             \
-                     : tc::launch2<true, false, 2, ID>(g, ma, mb, ctx->sm_count, s, &rp, z_in);            \
-    return eb == 4 ? tc::launch2<false, false, 4, ID>(g, ma, mb, ctx->sm_count, s, &rp, z_in)              \
-                   : tc::launch2<false, false, 2, ID>(g, ma, mb, ctx->sm_count, s, &rp, z_in);
+#define X(ID)                                                                                 \
+  case ID:                                                                                    \
+    return z_in == 0 ? tc::launch_epi<ID, 0>(g, ma, mb, ctx->sm_count, s, rp, A_MN, eb)      \
+                     : tc::launch_epi<ID, 1>(g, ma, mb, ctx->sm_count, s, rp, A_MN, eb);
     YOTA_EPI_CHAIN_LIST(X)
 #undef X
   }

@@ -1103,7 +1103,6 @@ static int plan_gemm_epilogues(yota_program& P) {
     Region& r = P.regions[ri];
     const RegionParams& rp = r.L.p;
     if (!ok || r.L.static_id < 0 || r.step <= (int)si || P.steps[r.step].kind != STEP_REGION) continue;
-    if (!gemm_epilogue_chain_ok(r.L.static_id, g.transA, g.transB)) continue;
     if (r.k != 1 || rp.R != g.M || rp.C != g.N) continue;
     int z_in = -1;
     for (int q = 0; q < rp.n_in; q++) {
@@ -1115,6 +1114,7 @@ static int plan_gemm_epilogues(yota_program& P) {
       }
     }
     if (!ok || z_in < 0) continue;
+    if (!gemm_epilogue_chain_ok(r.L.static_id, g.transA, g.transB, z_in)) continue;
     // absorb
     gs.epi_region = ri;
     gs.epi_z_in = z_in;
