@@ -162,6 +162,7 @@ def main():
     ap.add_argument("--no-other-modes", action="store_true", help="skip the short runs of the other GEMM modes")
     ap.add_argument("--small", action="store_true", help="tiny shapes (CI smoke of the bench itself)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="device-resident timing only (tuning sweeps): no e2e, roofline or CPU legs")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl != "reference" else a.warmup
     if a.impl == "reference":
@@ -180,12 +181,18 @@ def main():
     tape = Y.gradtape(f, *dargs)
     gf = Y.CompiledGrad(tape, ctx, flags)
     outs = [Y.B200Array(gf._out_dims[s], "f32", ctx) for s in range(gf.n_out)]
+    ar_impl = None
     if nranks > 1:
         dp.init_comm(ctx)
         slots = dp.param_grad_slots(gf, wl["n_params"]) + [gf.low.val[1]]
         for i in wl.get("ar_args", ()):
             slots.append(gf.low.grads[i][1])
         gf.set_allreduce(slots)
+        # all-reduced outputs live in symmetric memory: reduced by the library's own NVSwitch kernel
+        symm, _symm_base = dp.symmetric_outputs(gf, slots, ctx)
+        for s_, arr in symm.items():
+            outs[s_] = arr
+        ar_impl = "own multimem kernel over NCCL symmetric windows" if symm else "ncclAllReduce"
     stats = gf.stats()
 
     def ev():
@@ -218,6 +225,13 @@ def main():
     ms_step = ms / a.steps
     value = 1e3 / ms_step
     loss = outs[gf.low.val[1]].to_host()
+
+    if a.quick:
+        if rank == 0:
+            print(json.dumps({"metric": "Yota.grad evals/sec", "value": value, "unit": "evals/s", "n_gpus": nranks,
+                              "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step, "quick": True,
+                              "config": {"workload": wl["label"], "gemm_mode": a.gemm}, "clocks": clocks}))
+        return
 
     # ---- end to end: each step uploads its batch from pinned host memory, reads the loss --
     bidx = wl["batch_args"]
@@ -334,7 +348,7 @@ def main():
                 "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32 (f32 storage, f32 accumulate)", "bf16": "bf16 (f32 storage + bf16 operand shadows, f32 accumulate)"}[a.gemm],
                 "data": "synthetic",
                 "config": {"workload": wl["label"], "gemm_mode": a.gemm, "global_batch": 8192 if a.workload == "c3" and not a.small else None,
-                           "parallelism": f"dp{nranks} (batch columns sharded, NCCL all-reduce of parameter grads)",
+                           "parallelism": f"dp{nranks} (batch columns sharded, all-reduce of parameter grads" + (f": {ar_impl})" if ar_impl else ")"),
                            "l2": "working set (>=1 GiB of weights/activations per eval) is far larger than the 126 MB L2; no flush needed",
                            "loss": float(loss)},
                 "clocks": clocks,

@@ -198,6 +198,14 @@ int yota_event_destroy(yota_ctx* ctx, void* ev);
 int yota_program_profile(yota_program* p, void* const* in_ptrs, int64_t n_in,
                          void* const* out_ptrs, int64_t n_out, float seed, float* step_ms,
                          int64_t cap_steps, char* names, int64_t cap_names);
+/* Timeline of one eager run after `reps - 1` untimed ones, both streams: for every launched
+ * step (compute stream) and every all-reduce bucket (communication stream) three floats --
+ * device start, device end (ms since the run's first event) and host enqueue time (ms) -- and
+ * a last record "(whole run)".  Shows how far the reductions overlap the pullback sweep.
+ * Returns the number of records; names: '\n'-joined labels.  Diagnostic only. */
+int yota_program_timeline(yota_program* p, void* const* in_ptrs, int64_t n_in,
+                          void* const* out_ptrs, int64_t n_out, float seed, int reps,
+                          float* rec_ms, int64_t cap_recs, char* names, int64_t cap_names);
 
 /* ---- standalone operators (same kernels the program uses; unit-test / glue entry) ------ */
 /* C[m x n] = op(A) op(B) (+ C if accumulate), column-major, lda/ldb/ldc in elements.
@@ -225,6 +233,15 @@ int yota_comm_destroy(yota_ctx* ctx);
  * last writes it has been issued (overlaps the rest of the pullback sweep). */
 int yota_program_set_allreduce(yota_program* p, const int32_t* out_slots, int64_t n);
 int yota_allreduce_f32(yota_ctx* ctx, float* buf, int64_t n);
+/* Symmetric memory for buffers that are all-reduced: collective (every rank calls it with the
+ * same size, in the same order, after yota_comm_init).  Buffers carved from it are reduced by
+ * the library's own NVSwitch kernel (multimem.ld_reduce / multimem.st over NCCL symmetric
+ * windows, csrc/symm_allreduce.cu) instead of ncclAllReduce.  Needs NCCL >= 2.28;
+ * yota_comm_symm_available: 0 = unavailable, 1 = available (peer pointers), 2 = multicast team
+ * active (known once the first allocation has created the device communicator). */
+int yota_comm_symm_available(yota_ctx* ctx);
+int yota_comm_symm_alloc(yota_ctx* ctx, size_t bytes, void** dptr);
+int yota_comm_symm_free(yota_ctx* ctx, void* dptr);
 
 #ifdef __cplusplus
 }

@@ -25,19 +25,49 @@ for mode, flags, tol in (("fp32", 0, 2e-5), ("tf32", ffi.FLAG_GEMM_TF32, 5e-3)):
     shard[-2], shard[-1] = dp.shard_columns(args[-2], rank, nranks), dp.shard_columns(args[-1], rank, nranks)
     dsh = [Y.cu(a) for a in shard]
     gf = Y.CompiledGrad(Y.gradtape(f, *dsh), ctx, flags)
-    gf.set_allreduce(dp.param_grad_slots(gf, 2 * L) + [gf.low.val[1]])
-    for it in range(3):  # eager + repeated runs
-        val, g = gf.run(dsh)
+
+    def check(variant, val, g):
+        v = float(val.to_host())
+        assert abs(v - fv) <= tol * abs(fv), (mode, variant, v, fv)
+        for i in range(2 * L):
+            a, b = g[i].to_host(), fg[1 + i].to_host()
+            err = np.abs(a - b).max() / np.abs(b).max()
+            assert err <= tol, (mode, variant, i, err)
+        for i in (2 * L, 2 * L + 1):  # data grads stay sharded
+            a, b = g[i].to_host(), dp.shard_columns(fg[1 + i].to_host(), rank, nranks)
+            assert np.abs(a - b).max() <= tol * np.abs(b).max(), (mode, variant, i)
+
+    slots = dp.param_grad_slots(gf, 2 * L) + [gf.low.val[1]]
+    gf.set_allreduce(slots)
+    for variant in ("nccl", "symmetric"):
+        outs = [Y.B200Array(gf._out_dims[s], "f32", ctx) for s in range(gf.n_out)]
+        base = None
+        if variant == "symmetric":  # the library's own NVSwitch all-reduce kernel
+            symm, base = dp.symmetric_outputs(gf, slots, ctx)
+            if not symm:
+                break
+            for s_, arr in symm.items():
+                outs[s_] = arr
+        for it in range(3):  # eager + repeated runs
+            val, g = gf.run(dsh, out=outs)
+            ctx.sync()
+        check(variant, val, g)
+        first = [x.to_host() for x in g[:2 * L]]
+        val, g = gf.run(dsh, out=outs)
         ctx.sync()
-    v = float(val.to_host())
-    assert abs(v - fv) <= tol * abs(fv), (mode, v, fv)
-    for i in range(2 * L):
-        a, b = g[i].to_host(), fg[1 + i].to_host()
-        err = np.abs(a - b).max() / np.abs(b).max()
-        assert err <= tol, (mode, i, err)
-    for i in (2 * L, 2 * L + 1):  # data grads stay sharded
-        a, b = g[i].to_host(), dp.shard_columns(fg[1 + i].to_host(), rank, nranks)
-        assert np.abs(a - b).max() <= tol * np.abs(b).max(), (mode, i)
-    dp.barrier()
-    if rank == 0:
-        print(f"DP_GPU_OK mode={mode} nranks={nranks} loss={v:.6f}", flush=True)
+        for a, b in zip(first, g[:2 * L]):  # run to run, and rank to rank below: bit-identical sums
+            assert variant == "nccl" or np.array_equal(a.view(np.uint32), b.to_host().view(np.uint32)), (mode, "run-to-run")
+        if variant == "symmetric":
+            import torch
+            import torch.distributed as dist
+            h = torch.from_numpy(first[0].copy())
+            ref = h.clone()
+            dist.broadcast(ref, src=0)
+            assert torch.equal(h.view(torch.int32), ref.view(torch.int32)), (mode, "ranks hold different sums")
+        del outs, g, val
+        if base is not None:
+            ffi.check(ffi.lib().yota_comm_symm_free(ctx.h, base))
+        dp.barrier()
+        if rank == 0:
+            print(f"DP_GPU_OK mode={mode} allreduce={variant} nranks={nranks} symm={ffi.lib().yota_comm_symm_available(ctx.h)}", flush=True)
+

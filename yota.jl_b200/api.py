@@ -146,6 +146,20 @@ class CompiledGrad:
         labels = names.value.decode().split("\n")
         return [(labels[i] if i < len(labels) else "?", ms[i]) for i in range(n)]
 
+    def timeline(self, args, seed=None, out=None, reps=3):
+        """Both-stream timeline of one eager run: [(label, dev_start_ms, dev_end_ms, host_enqueue_ms), ...]."""
+        self.run(args, seed, out)  # binds pointers
+        cap = 8192
+        rec = (C.c_float * (3 * cap))()
+        names = C.create_string_buffer(1 << 20)
+        n = ffi.lib().yota_program_timeline(self.h, self._in, self.n_in, self._out, self.n_out,
+                                            self.default_seed if seed is None or self.low.seed_slot is not None else float(seed),
+                                            reps, rec, cap, names, len(names))
+        if n < 0:
+            ffi.check(n)
+        labels = names.value.decode().split("\n")
+        return [(labels[i] if i < len(labels) else "?", rec[3 * i], rec[3 * i + 1], rec[3 * i + 2]) for i in range(n)]
+
     def set_allreduce(self, out_slots):
         arr = (C.c_int32 * max(1, len(out_slots)))(*out_slots)
         ffi.check(ffi.lib().yota_program_set_allreduce(self.h, arr, len(out_slots)))

@@ -5,6 +5,8 @@
 // NCCL is loaded with dlopen so the library also loads where NCCL is absent; any
 // communication entry then fails loudly.
 #include <dlfcn.h>
+#include <limits.h>
+#include <stdlib.h>
 
 #include "common.h"
 
@@ -14,11 +16,25 @@ typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 typedef int ncclResult_t;
 enum { ncclFloat32 = 7, ncclSum = 0 };
+// ncclConfig_t as of NCCL 2.27 (a newer library accepts the older, shorter struct by its
+// size / version fields)
+struct ncclConfig27 {
+  size_t size;
+  unsigned int magic, version;
+  int blocking, cgaClusterSize, minCTAs, maxCTAs;
+  const char* netName;
+  int splitShare, trafficClass;
+  const char* commName;
+  int collnetEnable, CTAPolicy, shrinkShare, nvlsCTAs;
+};
+constexpr int kUndef = INT_MIN;
 
 struct NcclApi {
   void* h = nullptr;
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommInitRankConfig)(ncclComm_t*, int, ncclUniqueId, int, ncclConfig27*) = nullptr;  // optional
+  ncclResult_t (*GetVersion)(int*) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
@@ -46,7 +62,9 @@ static int nccl_load() {
   SYM(GroupStart, "ncclGroupStart");
   SYM(GroupEnd, "ncclGroupEnd");
   SYM(GetErrorString, "ncclGetErrorString");
+  SYM(GetVersion, "ncclGetVersion");
 #undef SYM
+  *(void**)(&g_nccl.CommInitRankConfig) = dlsym(g_nccl.h, "ncclCommInitRankConfig");
   return YOTA_OK;
 }
 
@@ -62,6 +80,45 @@ int comm_allreduce(yota_ctx* ctx, float* buf, long long n, cudaStream_t s) {
   YOTA_NCCL(g_nccl.AllReduce(buf, buf, (size_t)n, ncclFloat32, ncclSum, (ncclComm_t)ctx->nccl_comm, s));
   return YOTA_OK;
 }
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
+// SMs the persistent GEMM grids leave free while reductions are in flight: as many as the
+// communicator may use CTAs (YOTA_COMM_SM_RESERVE overrides), rounded up to whole CTA pairs.
+int comm_reserved_sms(yota_ctx* ctx) {
+  if (!ctx->nccl_comm) return 0;
+  const int ctas = symm_ctas(ctx) > 0 ? symm_ctas(ctx) : ctx->comm_ctas;
+  int r = env_int("YOTA_COMM_SM_RESERVE", ctas);
+  if (r < 0) r = 0;
+  return (r + 1) & ~1;
+}
+
+int comm_allreduce_bucket(yota_ctx* ctx, float* const* bufs, const long long* numel, int n, cudaStream_t s) {
+  if (!ctx->nccl_comm) YOTA_FAIL(YOTA_E_NCCL, "yota_comm_init has not been called");
+  std::vector<float*> sb, nb;
+  std::vector<long long> sn, nn;
+  for (int i = 0; i < n; i++) {
+    if (numel[i] == 0) continue;
+    if (symm_contains(ctx, bufs[i], (size_t)numel[i] * 4)) {
+      sb.push_back(bufs[i]);
+      sn.push_back(numel[i]);
+    } else {
+      nb.push_back(bufs[i]);
+      nn.push_back(numel[i]);
+    }
+  }
+  if (!sb.empty()) YOTA_TRY(symm_allreduce(ctx, sb.data(), sn.data(), (int)sb.size(), s));
+  if (!nb.empty()) {
+    YOTA_NCCL(g_nccl.GroupStart());
+    for (size_t i = 0; i < nb.size(); i++)
+      YOTA_NCCL(g_nccl.AllReduce(nb[i], nb[i], (size_t)nn[i], ncclFloat32, ncclSum, (ncclComm_t)ctx->nccl_comm, s));
+    YOTA_NCCL(g_nccl.GroupEnd());
+  }
+  return YOTA_OK;
+}
+
 int comm_group_start(yota_ctx* ctx) {
   (void)ctx;
   YOTA_TRY(nccl_load());
@@ -96,7 +153,25 @@ int yota_comm_init(yota_ctx* ctx, int rank, int nranks, const void* id128) {
   ncclUniqueId id;
   memcpy(&id, id128, sizeof(id));
   ncclComm_t comm;
-  YOTA_NCCL(g_nccl.CommInitRank(&comm, nranks, id, rank));
+  // The reductions run beside the tensor-core sweep, so the communicator is capped to a few
+  // CTAs (NVSwitch does the arithmetic; 16 CTAs drive the links) and the GEMM grids leave
+  // exactly those SMs free (comm_reserved_sms).  YOTA_NCCL_MAX_CTAS=0 keeps NCCL's default.
+  const int max_ctas = env_int("YOTA_NCCL_MAX_CTAS", 16);
+  int version = 0;
+  g_nccl.GetVersion(&version);
+  if (max_ctas > 0 && g_nccl.CommInitRankConfig && version >= 22700) {
+    ncclConfig27 cfg = {sizeof(ncclConfig27), 0xcafebeefu, 22703u, kUndef, kUndef, kUndef, kUndef, nullptr,
+                        kUndef, kUndef, nullptr, kUndef, kUndef, kUndef, kUndef};
+    cfg.maxCTAs = max_ctas;
+    cfg.minCTAs = env_int("YOTA_NCCL_MIN_CTAS", kUndef);
+    cfg.CTAPolicy = env_int("YOTA_NCCL_CTA_POLICY", kUndef);
+    cfg.nvlsCTAs = env_int("YOTA_NCCL_NVLS_CTAS", kUndef);
+    YOTA_NCCL(g_nccl.CommInitRankConfig(&comm, nranks, id, rank, &cfg));
+    ctx->comm_ctas = max_ctas;
+  } else {
+    YOTA_NCCL(g_nccl.CommInitRank(&comm, nranks, id, rank));
+    ctx->comm_ctas = 0;
+  }
   ctx->nccl_comm = comm;
   ctx->rank = rank;
   ctx->nranks = nranks;
@@ -105,6 +180,7 @@ int yota_comm_init(yota_ctx* ctx, int rank, int nranks, const void* id128) {
 
 int yota_comm_destroy(yota_ctx* ctx) {
   if (ctx && ctx->nccl_comm) {
+    symm_shutdown(ctx);
     g_nccl.CommDestroy((ncclComm_t)ctx->nccl_comm);
     ctx->nccl_comm = nullptr;
   }
@@ -114,7 +190,8 @@ int yota_comm_destroy(yota_ctx* ctx) {
 int yota_allreduce_f32(yota_ctx* ctx, float* buf, int64_t n) {
   if (!ctx) YOTA_FAIL(YOTA_E_ARG, "null ctx");
   YOTA_TRY(ctx_ensure_device(ctx));
-  return comm_allreduce(ctx, buf, n, ctx->stream);
+  const long long nn = n;
+  return comm_allreduce_bucket(ctx, &buf, &nn, 1, ctx->stream);
 }
 
 }  // extern "C"

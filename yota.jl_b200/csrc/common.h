@@ -57,6 +57,12 @@ struct yota_ctx {
   // NCCL
   void* nccl_comm = nullptr;
   int rank = 0, nranks = 1;
+  // SMs left to the communication kernels while all-reduces overlap the pullback sweep: the
+  // persistent GEMM grids shrink by this many so that NCCL's CTAs find free SMs at once
+  // instead of waiting for (and then delaying) a GEMM wave.  Set by run_all_steps.
+  int sm_reserved = 0;
+  int comm_ctas = 0;  // CTAs the communicator was configured with (0: NCCL default)
+  void* symm = nullptr;  // symmetric-memory state of the NVSwitch all-reduce (symm_allreduce.cu)
   // scratch for standalone ops
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
@@ -200,5 +206,19 @@ int launch_axpy(float* x, const float* g, long long n, float lr, cudaStream_t s)
 int comm_allreduce(yota_ctx* ctx, float* buf, long long n, cudaStream_t s);
 int comm_group_start(yota_ctx* ctx);
 int comm_group_end(yota_ctx* ctx);
+int comm_reserved_sms(yota_ctx* ctx);
+// all-reduce (sum) of a bucket of buffers: the NVSwitch multimem kernel for buffers in symmetric
+// memory, one grouped ncclAllReduce launch for the others
+int comm_allreduce_bucket(yota_ctx* ctx, float* const* bufs, const long long* numel, int n, cudaStream_t s);
+
+// ---- NVSwitch all-reduce over symmetric memory (symm_allreduce.cu) ------------------------
+bool symm_available(yota_ctx* ctx);
+int symm_alloc(yota_ctx* ctx, size_t bytes, void** out);
+int symm_free(yota_ctx* ctx, void* ptr);
+void symm_shutdown(yota_ctx* ctx);
+bool symm_contains(yota_ctx* ctx, const void* ptr, size_t bytes);
+int symm_ctas(yota_ctx* ctx);
+bool symm_multimem(yota_ctx* ctx);
+int symm_allreduce(yota_ctx* ctx, float* const* bufs, const long long* numel, int n, cudaStream_t s);
 
 }  // namespace yota

@@ -815,6 +815,12 @@ static int launch2(const GemmArgs& g, const CUtensorMap& ma, const CUtensorMap& 
 
 }  // namespace tc
 
+// SMs a persistent GEMM grid may occupy right now (see yota_ctx::sm_reserved)
+static inline int grid_sms(const yota_ctx* ctx) {
+  const int n = ctx->sm_count - ctx->sm_reserved;
+  return n < 2 ? 2 : n;
+}
+
 bool gemm_tc_eligible(const GemmArgs& g) {
   if (g.mode != 1 && g.mode != 2) return false;
   const int tk = g.mode == 1 ? 32 : 64;
@@ -881,8 +887,8 @@ int launch_gemm_tc_epilogue(yota_ctx* ctx, const GemmArgs& g, int static_id, con
   switch (static_id) {
 #define X(ID)                                                                                 \
   case ID:                                                                                    \
-    return z_in == 0 ? tc::launch_epi<ID, 0>(g, ma, mb, ctx->sm_count, s, rp, A_MN, eb)      \
-                     : tc::launch_epi<ID, 1>(g, ma, mb, ctx->sm_count, s, rp, A_MN, eb);
+    return z_in == 0 ? tc::launch_epi<ID, 0>(g, ma, mb, grid_sms(ctx), s, rp, A_MN, eb)      \
+                     : tc::launch_epi<ID, 1>(g, ma, mb, grid_sms(ctx), s, rp, A_MN, eb); 
     YOTA_EPI_CHAIN_LIST(X)
 #undef X
   }
@@ -903,8 +909,8 @@ int launch_gemm_tc(yota_ctx* ctx, const GemmArgs& g, cudaStream_t s) {
     YOTA_TRY(tc::make_map(&ma, g.A, g.M, g.K, g.lda, A_MN, tc::TM, eb));
     YOTA_TRY(tc::make_map(&mb, g.B, g.N, g.K, g.ldb, B_MN, tc::TN2 / 2, eb));
 #define GO2(a, b)                                                        \
-  return eb == 4 ? tc::launch2<a, b, 4>(g, ma, mb, ctx->sm_count, s)     \
-                 : tc::launch2<a, b, 2>(g, ma, mb, ctx->sm_count, s)
+  return eb == 4 ? tc::launch2<a, b, 4>(g, ma, mb, grid_sms(ctx), s)     \
+                 : tc::launch2<a, b, 2>(g, ma, mb, grid_sms(ctx), s)
     if (A_MN && B_MN) GO2(true, true);
     if (A_MN && !B_MN) GO2(true, false);
     if (!A_MN && B_MN) GO2(false, true);
@@ -915,8 +921,8 @@ int launch_gemm_tc(yota_ctx* ctx, const GemmArgs& g, cudaStream_t s) {
   YOTA_TRY(tc::make_map(&ma, g.A, g.M, g.K, g.lda, A_MN, tc::TM, eb));
   YOTA_TRY(tc::make_map(&mb, g.B, g.N, g.K, g.ldb, B_MN, TN, eb));
 #define GO(TNv, a, b)                                                          \
-  return eb == 4 ? tc::launch<TNv, a, b, 4>(g, ma, mb, ctx->sm_count, s)       \
-                 : tc::launch<TNv, a, b, 2>(g, ma, mb, ctx->sm_count, s)
+  return eb == 4 ? tc::launch<TNv, a, b, 4>(g, ma, mb, grid_sms(ctx), s)       \
+                 : tc::launch<TNv, a, b, 2>(g, ma, mb, grid_sms(ctx), s)
   if (TN == 256) {
     if (A_MN && B_MN) GO(256, true, true);
     if (A_MN && !B_MN) GO(256, true, false);

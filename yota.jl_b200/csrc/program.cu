@@ -16,6 +16,7 @@
 //   4. liveness-based arena planning for materialised intermediates and workspaces
 #include <algorithm>
 #include <cstring>
+#include <chrono>
 #include <string>
 
 #include "common.h"
@@ -1519,10 +1520,37 @@ static int run_step(yota_program& P, Step& st, cudaStream_t s) {
   YOTA_FAIL(YOTA_E_UNSUPPORTED_OP, "internal: unknown step kind %d", st.kind);
 }
 
-static int run_all_steps(yota_program& P, cudaStream_t s, bool with_comm) {
+// optional timeline of one eager run: device start/end of every step (compute stream) and of
+// every all-reduce bucket (comm stream), plus the host time at which each was enqueued
+struct Timeline {
+  struct Rec {
+    std::string label;
+    cudaEvent_t e0, e1;
+    double host_us;
+  };
+  std::vector<Rec> recs;
+  cudaEvent_t base = nullptr;
+  std::chrono::steady_clock::time_point t0;
+  int open(const std::string& label, cudaStream_t s) {
+    Rec r;
+    r.label = label;
+    YOTA_CUDA(cudaEventCreate(&r.e0));
+    YOTA_CUDA(cudaEventCreate(&r.e1));
+    r.host_us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+    YOTA_CUDA(cudaEventRecord(r.e0, s));
+    recs.push_back(r);
+    return YOTA_OK;
+  }
+  int close(cudaStream_t s) {
+    YOTA_CUDA(cudaEventRecord(recs.back().e1, s));
+    return YOTA_OK;
+  }
+};
+
+static int run_all_steps(yota_program& P, cudaStream_t s, bool with_comm, Timeline* tl = nullptr) {
   // which step last writes each all-reduced output
-  std::vector<int> ar_after(P.steps.size(), 0);
   std::vector<std::vector<int>> ar_at(P.steps.size());
+  P.ctx->sm_reserved = 0;
   if (with_comm) {
     for (int slot : P.allreduce_slots) {
       int last = -1;
@@ -1533,11 +1561,32 @@ static int run_all_steps(yota_program& P, cudaStream_t s, bool with_comm) {
     }
   }
   size_t ev = 0;
+  // Buckets: outputs finished by a step wait until at least kBucketBytes are pending (a
+  // layer's 16 KiB bias gradient rides with the next weight gradient instead of paying a
+  // launch and two cross-GPU barriers of its own); the last step flushes the rest.
+  constexpr long long kBucketBytes = 1 << 20;
+  std::vector<float*> pend_buf;
+  std::vector<long long> pend_n;
+  long long pend_bytes = 0;
+  size_t last_ar_step = 0;
+  for (size_t q = 0; q < P.steps.size(); q++)
+    if (!ar_at[q].empty()) last_ar_step = q;
   for (size_t q = 0; q < P.steps.size(); q++) {
+    if (tl && P.steps[q].kind != STEP_NOP) YOTA_TRY(tl->open(P.steps[q].label, s));
     YOTA_TRY(run_step(P, P.steps[q], s));
+    if (tl && P.steps[q].kind != STEP_NOP) YOTA_TRY(tl->close(s));
     if (with_comm && !ar_at[q].empty()) {
-      // bucket = the outputs finished by this step; all-reduce them on the comm stream while
-      // the compute stream continues with the rest of the pullback sweep
+      for (int slot : ar_at[q]) {
+        long long n = 0;
+        for (auto& t : P.T)
+          if (t.d.kind == YOTA_T_OUTPUT && t.d.slot == slot) n = t.numel;
+        pend_buf.push_back(static_cast<float*>(P.bound_out[slot]));
+        pend_n.push_back(n);
+        pend_bytes += n * 4;
+      }
+      if (pend_bytes < kBucketBytes && q != last_ar_step) continue;
+      // all-reduce the bucket on the comm stream while the compute stream continues with the
+      // rest of the pullback sweep
       if (ev >= P.ar_events.size()) {
         cudaEvent_t e;
         YOTA_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1546,16 +1595,20 @@ static int run_all_steps(yota_program& P, cudaStream_t s, bool with_comm) {
       YOTA_CUDA(cudaEventRecord(P.ar_events[ev], s));
       YOTA_CUDA(cudaStreamWaitEvent(P.ctx->comm_stream, P.ar_events[ev], 0));
       ev++;
-      YOTA_TRY(comm_group_start(P.ctx));
-      for (int slot : ar_at[q]) {
-        long long n = 0;
-        for (auto& t : P.T)
-          if (t.d.kind == YOTA_T_OUTPUT && t.d.slot == slot) n = t.numel;
-        YOTA_TRY(comm_allreduce(P.ctx, static_cast<float*>(P.bound_out[slot]), n, P.ctx->comm_stream));
-      }
-      YOTA_TRY(comm_group_end(P.ctx));
+      if (tl)
+        YOTA_TRY(tl->open("allreduce " + std::to_string(pend_bytes) + " B (" + std::to_string(pend_buf.size()) +
+                              " buffers) after step " + std::to_string(q),
+                          P.ctx->comm_stream));
+      YOTA_TRY(comm_allreduce_bucket(P.ctx, pend_buf.data(), pend_n.data(), (int)pend_buf.size(), P.ctx->comm_stream));
+      if (tl) YOTA_TRY(tl->close(P.ctx->comm_stream));
+      pend_buf.clear();
+      pend_n.clear();
+      pend_bytes = 0;
+      // from here on reductions are in flight beside the sweep: leave their CTAs some SMs
+      P.ctx->sm_reserved = comm_reserved_sms(P.ctx);
     }
   }
+  P.ctx->sm_reserved = 0;
   if (with_comm && ev > 0) {
     // the compute stream (and therefore yota_d2h / yota_sync) waits for the reductions
     if (ev >= P.ar_events.size()) {
@@ -1689,6 +1742,67 @@ extern "C" int yota_program_profile(yota_program* p, void* const* in_ptrs, int64
     names[m] = 0;
   }
   return (int)std::min<int64_t>((int64_t)n, cap_steps);
+}
+
+// Timeline of `reps` back-to-back eager runs (the last one is reported): for every launched
+// step and every all-reduce bucket its device start / end (ms since the run's first event) and
+// the host enqueue time (ms since the run began).  out: 3 floats per record.
+extern "C" int yota_program_timeline(yota_program* p, void* const* in_ptrs, int64_t n_in, void* const* out_ptrs,
+                                     int64_t n_out, float seed, int reps, float* rec_ms, int64_t cap_recs, char* names,
+                                     int64_t cap_names) {
+  if (!p) YOTA_FAIL(YOTA_E_ARG, "null program");
+  yota_program& P = *p;
+  YOTA_TRY(ensure_arena(P));
+  bool changed = false;
+  YOTA_TRY(bind(P, in_ptrs, n_in, out_ptrs, n_out, &changed));
+  YOTA_TRY(set_seed(P, seed));
+  cudaStream_t s = P.ctx->stream;
+  const bool with_comm = !P.allreduce_slots.empty() && P.ctx->nccl_comm;
+  for (int r = 0; r + 1 < reps; r++) YOTA_TRY(run_all_steps(P, s, with_comm));
+  Timeline tl;
+  YOTA_CUDA(cudaEventCreate(&tl.base));
+  tl.t0 = std::chrono::steady_clock::now();
+  YOTA_CUDA(cudaEventRecord(tl.base, s));
+  const int st = run_all_steps(P, s, with_comm, &tl);
+  cudaEvent_t end;
+  YOTA_CUDA(cudaEventCreate(&end));
+  YOTA_CUDA(cudaEventRecord(end, s));
+  YOTA_CUDA(cudaStreamSynchronize(s));
+  YOTA_CUDA(cudaStreamSynchronize(P.ctx->comm_stream));
+  std::string nm;
+  int64_t n = 0;
+  for (auto& r : tl.recs) {
+    float a = 0.f, b = 0.f;
+    cudaEventElapsedTime(&a, tl.base, r.e0);
+    cudaEventElapsedTime(&b, tl.base, r.e1);
+    if (n < cap_recs && rec_ms) {
+      rec_ms[3 * n] = a;
+      rec_ms[3 * n + 1] = b;
+      rec_ms[3 * n + 2] = (float)(r.host_us * 1e-3);
+    }
+    nm += r.label + "\n";
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+    n++;
+  }
+  float total = 0.f;
+  cudaEventElapsedTime(&total, tl.base, end);
+  if (n < cap_recs && rec_ms) {
+    rec_ms[3 * n] = 0.f;
+    rec_ms[3 * n + 1] = total;
+    rec_ms[3 * n + 2] = (float)std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tl.t0).count();
+  }
+  nm += "(whole run)";
+  n++;
+  cudaEventDestroy(tl.base);
+  cudaEventDestroy(end);
+  if (names && cap_names > 0) {
+    const size_t m = std::min((size_t)cap_names - 1, nm.size());
+    memcpy(names, nm.data(), m);
+    names[m] = 0;
+  }
+  if (st != YOTA_OK) return st;
+  return (int)std::min<int64_t>(n, cap_recs);
 }
 
 extern "C" int yota_program_set_allreduce(yota_program* p, const int32_t* out_slots, int64_t n) {

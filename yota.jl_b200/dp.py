@@ -64,6 +64,29 @@ def param_grad_slots(compiled, n_params):
     return [g[1] for g in compiled.low.grads[:n_params] if isinstance(g, tuple) and g[0] == "out"]
 
 
+def symmetric_outputs(compiled, slots, ctx=None):
+    """Output arrays for the all-reduced slots carved from ONE symmetric allocation
+    (yota_comm_symm_alloc: collective), so that the library's NVSwitch all-reduce kernel is
+    used instead of ncclAllReduce.  Returns ({slot: B200Array view}, base pointer) or
+    ({}, None) when symmetric memory is unavailable (single rank, NCCL < 2.28)."""
+    from .device import B200Array
+
+    ctx = ctx or context()
+    rank, nranks, _ = world()
+    if nranks == 1 or not ffi.lib().yota_comm_symm_available(ctx.h):
+        return {}, None
+    offs, total = {}, 0
+    for s in slots:
+        dims = compiled._out_dims[s]
+        nbytes = 4 * int(np.prod(dims, dtype=np.int64)) if dims else 4
+        offs[s] = total
+        total += (nbytes + 255) & ~255
+    base = C.c_void_p()
+    ffi.check(ffi.lib().yota_comm_symm_alloc(ctx.h, total, C.byref(base)))
+    ffi.check(ffi.lib().yota_memset(ctx.h, base, 0, total))
+    return {s: B200Array(compiled._out_dims[s], "f32", ctx, ptr=base.value + offs[s], owner=False) for s in slots}, base
+
+
 def allreduce_host_max(x):
     """max over ranks of a Python float (timing: max over ranks, never the wall clock)."""
     import torch

@@ -58,6 +58,7 @@ SYMBOLS = {
     "yota_event_elapsed_ms": (_i, [_vp, _vp, _vp, C.POINTER(_f)]),
     "yota_event_destroy": (_i, [_vp, _vp]),
     "yota_program_profile": (_i, [_vp, _pp, _i64, _pp, _i64, _f, C.POINTER(_f), _i64, C.c_char_p, _i64]),
+    "yota_program_timeline": (_i, [_vp, _pp, _i64, _pp, _i64, _f, _i, C.POINTER(_f), _i64, C.c_char_p, _i64]),
     "yota_gemm": (_i, [_vp, _i, _i, _i, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i]),
     "yota_scatter_add_cols": (_i, [_vp, _vp, _i64, _i64, _vp, _vp, _i64]),
     "yota_gather_cols": (_i, [_vp, _vp, _vp, _i64, _i64, _vp, _i64]),
@@ -67,6 +68,9 @@ SYMBOLS = {
     "yota_comm_destroy": (_i, [_vp]),
     "yota_program_set_allreduce": (_i, [_vp, C.POINTER(C.c_int32), _i64]),
     "yota_allreduce_f32": (_i, [_vp, _vp, _i64]),
+    "yota_comm_symm_available": (_i, [_vp]),
+    "yota_comm_symm_alloc": (_i, [_vp, _sz, _pp]),
+    "yota_comm_symm_free": (_i, [_vp, _vp]),
 }
 
 FLAG_NO_FUSE, FLAG_NO_GRAPH, FLAG_GEMM_TF32, FLAG_GEMM_BF16, FLAG_NO_STATIC = 0x1, 0x2, 0x10, 0x20, 0x40
