@@ -17,7 +17,7 @@ mode = sys.argv[1] if len(sys.argv) > 1 else "tf32"
 rank, nranks, local = dp.world()
 ctx = Y.context(local)
 lib = ffi.lib()
-L, W, B = 8, 4096, 8192
+L, W, B = 8, 4096, int(os.environ.get("BATCH", 8192))
 args = list(cases.c3_args(L, W, B))
 args[-2], args[-1] = dp.shard_columns(args[-2], rank, nranks), dp.shard_columns(args[-1], rank, nranks)
 dargs = [Y.cu(a) for a in args]

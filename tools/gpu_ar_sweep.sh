@@ -1,11 +1,11 @@
 #!/bin/bash
-# N-GPU sweep of the all-reduce kernel's CTA count (= SMs the GEMM grids leave free)
+# N-GPU sweep of the all-reduce kernel's threads per CTA (request pressure on the memory system)
 N=${1:-8}
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1 --nproc-per-node $N"
 port=29700
-for cfg in "24 tf32" "32 tf32" "32 bf16" "24 bf16"; do
+for cfg in "256 tf32" "512 tf32" "256 bf16"; do
   set -- $cfg; c=$1; m=$2; port=$((port+1))
-  YOTA_AR_CTAS=$c timeout 200 $TR --master-port $port bench.py --gpus $N --gemm $m --steps 20 --warmup 5 --quick > gpurun_out/ar_c${c}_${m}_n$N.json 2> gpurun_out/ar_c${c}_${m}_n$N.err
-  echo "ctas=$c $m rc=$? $(tail -1 gpurun_out/ar_c${c}_${m}_n$N.json | cut -c1-160)"
+  YOTA_AR_THREADS=$c timeout 200 $TR --master-port $port bench.py --gpus $N --gemm $m --steps 20 --warmup 5 --quick > gpurun_out/ar_t${c}_${m}_n$N.json 2> gpurun_out/ar_t${c}_${m}_n$N.err
+  echo "threads=$c $m rc=$? $(tail -1 gpurun_out/ar_t${c}_${m}_n$N.json | cut -c1-160)"
 done

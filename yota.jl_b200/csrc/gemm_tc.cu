@@ -817,7 +817,8 @@ static int launch2(const GemmArgs& g, const CUtensorMap& ma, const CUtensorMap& 
 
 // SMs a persistent GEMM grid may occupy right now (see yota_ctx::sm_reserved)
 static inline int grid_sms(const yota_ctx* ctx) {
-  const int n = ctx->sm_count - ctx->sm_reserved;
+  const char* e = getenv("YOTA_GEMM_GRID_SMS");  // diagnostic override (tests/occupy_probe.cu)
+  const int n = e && *e ? atoi(e) : ctx->sm_count - ctx->sm_reserved;
   return n < 2 ? 2 : n;
 }
 

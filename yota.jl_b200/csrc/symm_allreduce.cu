@@ -75,7 +75,11 @@ static bool symm_load() {
   } while (0)
 
 constexpr int AR_MAX_SEG = 8;
-constexpr int AR_THREADS = 1024;
+// 256 threads x 8 vectors in flight: enough to keep NVLink busy (the reduction is link-bound at
+// ~180 us per 64 MiB on 8 GPUs), few enough that the requests do not crowd the GEMM's TMA loads
+// out of the memory system -- with 1024 threads the overlapped GEMM stretched to the length of
+// the reduction (measured, tools/gpu_ar_diag.sh; 8 GPUs: 415 -> 476 evals/s).
+constexpr int AR_THREADS = 256;
 constexpr int AR_UNROLL = 8;
 
 struct ArSegs {
@@ -131,14 +135,18 @@ __device__ __forceinline__ void st_sys(float4* p, float4 v) {
                : "memory");
 }
 
+// Launched as clusters of 2 CTAs: a cluster of two lands on the two SMs of ONE TPC, so k CTAs
+// take k/2 whole TPCs and leave the others whole for the GEMM's CTA pairs (cta_group::2 needs
+// both SMs of a TPC; CTAs sprinkled one per TPC would block that many pairs for the whole
+// reduction -- measured: the overlapped dh GEMM went from 62 us to 170 us).
 template <bool MC>
-__global__ void __launch_bounds__(AR_THREADS, 1) symm_allreduce_kernel(const ncclDevComm dc, const ArSegs segs) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(1024, 1) symm_allreduce_kernel(const ncclDevComm dc, const ArSegs segs, const int phases) {
   ncclLsaBarrierSession<ncclCoopCta> bar(ncclCoopCta(), dc, ncclTeamTagLsa(), blockIdx.x, MC);
   // every rank's producer kernel (the dW GEMM) has finished once its CTA arrives here
   bar.sync(ncclCoopCta(), cuda::memory_order_acq_rel);
   const int nr = dc.lsaSize, r = dc.lsaRank;
-  const long long tid = (long long)blockIdx.x * AR_THREADS + threadIdx.x;
-  const long long nthreads = (long long)gridDim.x * AR_THREADS;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
   for (int sidx = 0; sidx < segs.n; sidx++) {
     const long long numel = segs.numel[sidx];
     const long long nv = numel >> 2;
@@ -146,16 +154,16 @@ __global__ void __launch_bounds__(AR_THREADS, 1) symm_allreduce_kernel(const ncc
     if (MC) {
       float4* mm = reinterpret_cast<float4*>(ncclGetLsaMultimemPointer(segs.win[sidx], segs.off[sidx], dc));
       for (long long i0 = lo + tid; i0 < hi; i0 += nthreads * AR_UNROLL) {
-        float4 v[AR_UNROLL];
+        float4 v[AR_UNROLL] = {};
 #pragma unroll
         for (int u = 0; u < AR_UNROLL; u++) {
           const long long i = i0 + (long long)u * nthreads;
-          if (i < hi) v[u] = mc_ld_reduce(mm + i);
+          if (i < hi && (phases & 1)) v[u] = mc_ld_reduce(mm + i);
         }
 #pragma unroll
         for (int u = 0; u < AR_UNROLL; u++) {
           const long long i = i0 + (long long)u * nthreads;
-          if (i < hi) mc_st(mm + i, v[u]);
+          if (i < hi && (phases & 2)) mc_st(mm + i, v[u]);
         }
       }
       if (r == 0 && tid < (numel & 3)) {  // ragged tail (numel not a multiple of 4): scalar form
@@ -219,8 +227,8 @@ static int symm_ensure_devcomm(yota_ctx* ctx) {
   if (!ctx->symm) ctx->symm = new SymmState();
   SymmState* S = symm_state(ctx);
   if (S->have_dev) return YOTA_OK;
-  S->ctas = env_int2("YOTA_AR_CTAS", 16);
-  if (S->ctas < 1) S->ctas = 1;
+  S->ctas = (env_int2("YOTA_AR_CTAS", 16) + 1) & ~1;
+  if (S->ctas < 2) S->ctas = 2;
   ncclDevCommRequirements reqs;
   memset(&reqs, 0, sizeof(reqs));
   reqs.lsaBarrierCount = S->ctas;
@@ -325,11 +333,15 @@ int symm_allreduce(yota_ctx* ctx, float* const* bufs, const long long* numel, in
     int ctas = S->ctas;
     const long long per_rank_vec = total / 4 / ctx->nranks + 1;
     const long long want = (per_rank_vec + AR_THREADS * AR_UNROLL - 1) / (AR_THREADS * AR_UNROLL);
+    // (sized before the diagnostic thread-count override below: only large buckets are affected)
     if (want < ctas) ctas = (int)(want < 1 ? 1 : want);
+    ctas = (ctas + 1) & ~1;  // whole clusters
+    const int phases = env_int2("YOTA_AR_PHASES", 3);    // diagnostics: 1 = reduce only, 2 = broadcast only, 0 = barriers only
+    const int threads = env_int2("YOTA_AR_THREADS", AR_THREADS);
     if (S->multimem)
-      symm_allreduce_kernel<true><<<ctas, AR_THREADS, 0, s>>>(S->dev, segs);
+      symm_allreduce_kernel<true><<<ctas, threads, 0, s>>>(S->dev, segs, phases);
     else
-      symm_allreduce_kernel<false><<<ctas, AR_THREADS, 0, s>>>(S->dev, segs);
+      symm_allreduce_kernel<false><<<ctas, threads, 0, s>>>(S->dev, segs, phases);
     YOTA_CUDA(cudaGetLastError());
   }
   return YOTA_OK;
