@@ -98,7 +98,9 @@ def workload(name, rank, nranks, small=False):
         E, idx, V = cases.c5_args(rows, nt, ni)
         return dict(f=cases.c5_embed, args=[E, idx, V], n_params=0, batch_args=(),
                     label=f"C5: sum(E[:, idx] .* V), E {rows}x{nt}, {ni} Int64 indices (bit-exact scatter-add pullback)",
-                    gemm_flops=0, hbm_bytes=V.nbytes + idx.nbytes + E.nbytes)
+                    gemm_flops=0, hbm_bytes=V.nbytes + idx.nbytes + E.nbytes, hbm_step="ungetindex",
+                    # algorithmic bytes of the other steps of the eval (reported beside the scatter-add pullback)
+                    hbm_other={"region": 4 * V.nbytes, "getindex": idx.nbytes + 2 * V.nbytes})
     if name == "c1":
         return dict(f=cases.c1_mlp, args=list(cases.c1_args()), n_params=4, batch_args=(4, 5),
                     label="C1: MLP 784-128-10 tanh, batch 64", gemm_flops=3.9e7, hbm_bytes=None)
@@ -306,11 +308,15 @@ def main():
                 "peak_source": f"{pk['src']} bf16 sustained" + (" x 0.5 (TF32 runs at half the BF16 rate)" if a.gemm == "tf32" else "")
                                + ("; strict-FP32 FFMA kernel, not a tensor-core kernel" if a.gemm == "fp32" else "")}
     elif wl.get("hbm_bytes"):
+        dom = wl.get("hbm_step", dom)  # the kernel BASELINE.json names for this workload
         t_dom = groups[dom][0]
         ach = wl["hbm_bytes"] / (t_dom * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
                 "traffic": traffic_tab.get(f"{dom}:{a.workload}") if not a.small else None, "avg_launch_ms": t_dom / groups[dom][1], "launches_per_step": groups[dom][1],
                 "share_of_step": t_dom / total_prof, "peak_source": f"{pk['src']} HBM copy"}
+        if wl.get("hbm_other"):
+            roof["other_steps"] = {k: {"achieved": b / (groups[k][0] * 1e-3) / 1e9, "frac": b / (groups[k][0] * 1e-3) / 1e9 / pk["hbm"]}
+                                   for k, b in wl["hbm_other"].items() if k in groups}
 
     # ---- CPU baseline (rank 0, N = 1 only): the oracle on a bounded sample -----------------
     cpu = None

@@ -1253,7 +1253,8 @@ extern "C" int yota_program_build(yota_ctx* ctx, const yota_op_desc* ops, int64_
   if ((st = plan_bf16_shadows(P))) return fail(st);
   if ((st = plan_memory(P))) return fail(st);
   P.n_launches = 0;
-  for (auto& s : P.steps) P.n_launches += (s.kind == STEP_UNGETINDEX) ? 8 : 1;
+  for (auto& s : P.steps)  // absorbed regions launch nothing; BF16 operand casts are launches of their GEMM step
+    P.n_launches += s.kind == STEP_NOP ? 0 : (s.kind == STEP_UNGETINDEX ? 8 : 1) + (s.cast[0] ? 1 : 0) + (s.cast[1] ? 1 : 0);
   *out = Pp;
   return YOTA_OK;
 }

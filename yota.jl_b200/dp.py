@@ -54,7 +54,16 @@ def init_comm(ctx=None):
     t = torch.tensor(list(bytes(buf)), dtype=torch.uint8)
     dist.broadcast(t, src=0)
     idb = (C.c_ubyte * 128)(*t.tolist())
-    ffi.check(ffi.lib().yota_comm_init(ctx.h, rank, nranks, idb))
+    # NCCL prints its version banner on stdout when NCCL_DEBUG is set; keep stdout for results
+    import sys
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        ffi.check(ffi.lib().yota_comm_init(ctx.h, rank, nranks, idb))
+    finally:
+        os.dup2(saved, 1)
+        os.close(saved)
     return rank, nranks
 
 
