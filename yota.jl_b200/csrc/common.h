@@ -163,6 +163,10 @@ struct GemmArgs {
   float* C;
   long long ldc;
   int accumulate;
+  // fused-epilogue GEMMs only: second, transposed store of chain output `tsh_out` (gemm_tc.cu)
+  float* tsh = nullptr;
+  long long tsh_ld = 0;
+  int tsh_out = -1;
 };
 int launch_gemm_ffma(const GemmArgs& g, cudaStream_t s);
 int launch_gemm_tc(yota_ctx* ctx, const GemmArgs& g, cudaStream_t s);  // returns YOTA_E_UNSUPPORTED_OP if shape not eligible

@@ -137,6 +137,12 @@ struct Params {
   int accumulate;
   int num_m, num_n;
   int spread;  // 1: lane c of the producer warp issues TMA box c; 0: lane 0 issues all boxes
+  // fused epilogue: store output `tsh_out` of the chain a second time, transposed (element (m, n)
+  // at tsh[n + m * tsh_ld]): the K-major operand of the dW GEMM that would otherwise read this
+  // tensor MN-major (see plan_transposed_shadows in program.cu)
+  float* tsh;
+  long long tsh_ld;
+  int tsh_out;
 };
 
 template <int TN>
@@ -404,6 +410,9 @@ static int launch(const GemmArgs& g, const CUtensorMap& ma, const CUtensorMap& m
   p.ldc = g.ldc;
   p.accumulate = g.accumulate;
   p.spread = getenv("YOTA_TMA_SPREAD") ? 1 : 0;
+  p.tsh = nullptr;
+  p.tsh_ld = 0;
+  p.tsh_out = -1;
   p.num_m = (int)(g.M / TM);
   p.num_n = (int)(g.N / TN);
   const int tiles = p.num_m * p.num_n;
@@ -434,7 +443,8 @@ struct Smem2 {
   static constexpr int B_BYTES = (TN2 / 2) * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES2 * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+  static constexpr int TSH_OFF = BAR_OFF + 256;           // 4 epilogue warps x (32 x 32 floats): transpose staging
+  static constexpr int TOTAL = TSH_OFF + 4 * 4096 + 1024;  // + slack for 1 KiB alignment
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -526,7 +536,10 @@ struct Epilogue {
   // left per element, each load sits between the previous element's store and its own use and
   // the epilogue runs at one DRAM latency per element.
   __device__ __forceinline__ static void chunk32(const RegionParams& rp, const uint32_t (&z)[32], long long m,
-                                                 long long n0, long long R, const float (&base)[NS], float (&accs)[NO]) {
+                                                 long long n0, long long R, const float (&base)[NS], float (&accs)[NO],
+                                                 float* tsh, long long tsh_ld, int tsh_out, float4* stage) {
+    const int lane = threadIdx.x & 31;
+    float tv[4];
     constexpr int NI = N_IN > 0 ? N_IN : 1;
     float pre[NI][32];
     static_for<N_IN>([&](auto k) {
@@ -564,11 +577,27 @@ struct Epilogue {
       });
       static_for<N_OUT>([&](auto k) {
         constexpr int kind = YCE(out_kind, k), src = YCE(out_src, k);
-        if constexpr (kind == OUT_STORE)
+        if constexpr (kind == OUT_STORE) {
           rp.out[decltype(k)::value].ptr[off] = v[src];
-        else
+          if (decltype(k)::value == tsh_out) tv[j & 3] = v[src];
+        } else
           accs[decltype(k)::value] = __fadd_rn(accs[decltype(k)::value], v[src]);
       });
+      // this thread's 32 columns of row m are one 128-byte line of the transposed copy: staged in
+      // shared memory (16-byte pieces XOR-swizzled by row: conflict-free both ways) ...
+      if ((j & 3) == 3 && tsh) stage[lane * 8 + ((j >> 2) ^ (lane & 7))] = make_float4(tv[0], tv[1], tv[2], tv[3]);
+    }
+    if (tsh) {
+      // ... and written out 4 whole lines per warp instruction (8 lanes x 16 bytes each) instead of
+      // 32 quarter-sector stores to 32 different lines
+      __syncwarp();
+      float* base_row = tsh + (m - lane) * tsh_ld + n0;
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int rr = 4 * i + (lane >> 3), piece = lane & 7;
+        reinterpret_cast<float4*>(base_row + (long long)rr * tsh_ld)[piece] = stage[rr * 8 + (piece ^ (rr & 7))];
+      }
+      __syncwarp();
     }
   }
   __device__ __forceinline__ static void end_tile(const RegionParams& rp, long long m, long long tile_n, long long R,
@@ -755,7 +784,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if constexpr (EPI >= 0) {
-          EP::chunk32(rp, v, m, n0 + c * 32, p.M, ebase, eaccs);
+          EP::chunk32(rp, v, m, n0 + c * 32, p.M, ebase, eaccs, p.tsh, p.tsh_ld, p.tsh_out,
+                      reinterpret_cast<float4*>(smem + S::TSH_OFF) + q * 256);
         } else {
           float* cp = crow + (long long)(c * 32) * p.ldc;
           if (p.accumulate) {
@@ -802,6 +832,9 @@ static int launch2(const GemmArgs& g, const CUtensorMap& ma, const CUtensorMap& 
   p.ldc = g.ldc;
   p.accumulate = g.accumulate;
   p.spread = getenv("YOTA_TMA_SPREAD") ? 1 : 0;
+  p.tsh = g.tsh;
+  p.tsh_ld = g.tsh_ld;
+  p.tsh_out = g.tsh_out;
   p.num_m = (int)(g.M / (2 * TM));
   p.num_n = (int)(g.N / TN2);
   const int tiles = p.num_m * p.num_n;

@@ -99,6 +99,9 @@ struct Step {
   int acc_tensor = -1;
   int epi_region = -1;    // GEMM: consumer region executed as the epilogue
   int epi_z_in = -1;      // index of the region input that is the GEMM output
+  int tsh_make = -1;      // fused-epilogue GEMM: transposed shadow it also writes ...
+  int tsh_make_out = -1;  // ... of this store output of the chain
+  int tsh_use[2] = {-1, -1};  // GEMM: operand A / B is read from this transposed shadow (K-major)
 };
 
 }  // namespace yota
@@ -136,6 +139,7 @@ struct yota_program {
     int first_step = -1, last_step = -1;
   };
   std::vector<Shadow> shadows;
+  std::vector<Shadow> tshadows;  // transposed Float32 copies written by GEMM epilogues (TF32 mode)
   std::vector<int> allreduce_slots;
   std::vector<cudaEvent_t> ar_events;
 };
@@ -948,6 +952,65 @@ static int plan_bf16_shadows(yota_program& P) {
   return YOTA_OK;
 }
 
+// TF32 mode: the dW GEMM of a layer, dW = dZ * H', reads BOTH operands MN-major (the batch, its
+// K, is the slow axis of dZ and of H) and runs the tensor pipe at 66 % where K-major operands
+// reach 94 % (profiles/README.md).  When such an operand is the stored output of a fused GEMM
+// epilogue (H: forward bias+tanh; dZ: the dH GEMM's tanh' epilogue), that epilogue also writes a
+// transposed copy -- each thread holds 32 consecutive columns of its row, one 128-byte line of
+// the transpose -- and the dW GEMM reads the copy K-major.  Costs one extra store pass hidden
+// behind the mainloop and numel * 4 bytes of arena while the copy is live.
+static int plan_transposed_shadows(yota_program& P) {
+  if (!(P.flags & YOTA_FLAG_GEMM_TF32) || (P.flags & YOTA_FLAG_NO_FUSE) || getenv("YOTA_NO_TSHADOW")) return YOTA_OK;
+  std::map<int, int> shadow_of;
+  for (size_t s = 0; s < P.steps.size(); s++) {
+    Step& st = P.steps[s];
+    if (st.kind != STEP_GEMM || st.epi_region >= 0) continue;
+    const yota_op_desc& o = P.ops[st.op];
+    GemmArgs g{};
+    g.mode = 1;
+    g.transA = (int)o.iattr[0];
+    g.transB = (int)o.iattr[1];
+    gemm_dims(P, o, &g.M, &g.N, &g.K, &g.lda, &g.ldb);
+    if (!gemm_tc2_eligible(g, P.ctx->sm_count)) continue;
+    for (int j = 0; j < 2; j++) {
+      const bool mn_major = j == 0 ? !g.transA : g.transB != 0;
+      if (!mn_major) continue;
+      const int t = o.in[j];
+      const TInfo& ti = P.T[t];
+      if (ti.alias_of >= 0 || ti.d.kind != YOTA_T_TEMP || !ti.materialized || ti.d.ndim != 2) continue;
+      if (ti.dims[1] % 32 || ti.dims[0] % 4) continue;  // 128-byte lines of the transpose, TMA strides
+      const int d = ti.def_step;
+      if (d < 0 || d >= (int)s) continue;
+      Step& ps = P.steps[d];
+      if (ps.kind != STEP_GEMM || ps.epi_region < 0) continue;
+      const Region& r = P.regions[ps.epi_region];
+      const int n_store = r.L.p.n_out - (int)r.sums.size();
+      int q_out = -1;
+      for (int q = 0; q < n_store; q++)
+        if (r.out_tensors[q] == t) q_out = q;
+      if (q_out < 0) continue;
+      auto it = shadow_of.find(t);
+      if (it == shadow_of.end()) {
+        if (ps.tsh_make >= 0) continue;  // one transposed copy per epilogue
+        yota_program::Shadow sh;
+        sh.tensor = t;
+        sh.first_step = d;
+        sh.last_step = (int)s;
+        P.tshadows.push_back(sh);
+        it = shadow_of.insert({t, (int)P.tshadows.size() - 1}).first;
+        ps.tsh_make = it->second;
+        ps.tsh_make_out = q_out;
+        ps.label += " +T";
+      }
+      st.tsh_use[j] = it->second;
+      P.tshadows[it->second].last_step = std::max(P.tshadows[it->second].last_step, (int)s);
+    }
+    if (st.tsh_use[0] >= 0 || st.tsh_use[1] >= 0)
+      st.label += std::string(" [K-major ") + (st.tsh_use[0] >= 0 ? "A" : "") + (st.tsh_use[1] >= 0 ? "B" : "") + "]";
+  }
+  return YOTA_OK;
+}
+
 static int plan_memory(yota_program& P) {
   const int ns = (int)P.steps.size();
   // constants first
@@ -992,6 +1055,8 @@ static int plan_memory(yota_program& P) {
     Step& st = P.steps[s];
     for (auto& sh : P.shadows)
       if (sh.first_step == s) sh.arena_off = (long long)fl.alloc((size_t)P.T[sh.tensor].numel * 2);
+    for (auto& sh : P.tshadows)
+      if (sh.first_step == s) sh.arena_off = (long long)fl.alloc((size_t)P.T[sh.tensor].numel * 4);
     for (int t : defs[s]) P.T[t].arena_off = (long long)fl.alloc((size_t)P.T[t].numel * elem_size(P.T[t]));
     if (st.kind == STEP_REGION || (st.kind == STEP_GEMM && st.epi_region >= 0)) {
       Region& r = P.regions[st.kind == STEP_REGION ? st.region : st.epi_region];
@@ -1010,6 +1075,8 @@ static int plan_memory(yota_program& P) {
     for (auto& w : ws_frees[s]) fl.release(w.first, w.second);
     for (auto& sh : P.shadows)
       if (sh.last_step == s) fl.release((size_t)sh.arena_off, (size_t)P.T[sh.tensor].numel * 2);
+    for (auto& sh : P.tshadows)
+      if (sh.last_step == s) fl.release((size_t)sh.arena_off, (size_t)P.T[sh.tensor].numel * 4);
   }
   P.arena_bytes = fl.end;
   return YOTA_OK;
@@ -1251,6 +1318,7 @@ extern "C" int yota_program_build(yota_ctx* ctx, const yota_op_desc* ops, int64_
   if ((st = plan_gemm_epilogues(P))) return fail(st);
   if ((st = finish_steps(P))) return fail(st);
   if ((st = plan_bf16_shadows(P))) return fail(st);
+  if ((st = plan_transposed_shadows(P))) return fail(st);
   if ((st = plan_memory(P))) return fail(st);
   P.n_launches = 0;
   for (auto& s : P.steps)  // absorbed regions launch nothing; BF16 operand casts are launches of their GEMM step
@@ -1358,7 +1426,14 @@ static int bind_region(yota_program& P, Region& r, RegionLaunch& L) {
   return YOTA_OK;
 }
 
-static int run_gemm_epilogue(yota_program& P, Step& st, const GemmArgs& g, cudaStream_t s) {
+static int run_gemm_epilogue(yota_program& P, Step& st, const GemmArgs& g_in, cudaStream_t s) {
+  GemmArgs g = g_in;
+  if (st.tsh_make >= 0) {
+    const yota_program::Shadow& sh = P.tshadows[st.tsh_make];
+    g.tsh = reinterpret_cast<float*>(P.arena + sh.arena_off);
+    g.tsh_ld = P.T[sh.tensor].dims[1];
+    g.tsh_out = st.tsh_make_out;
+  }
   Region& r = P.regions[st.epi_region];
   RegionLaunch L = r.L;
   L.p.in[st.epi_z_in].ptr = nullptr;  // the accumulator stands in for this operand
@@ -1446,6 +1521,18 @@ static int run_step(yota_program& P, Step& st, cudaStream_t s) {
         return launch_gemm_tc(P.ctx, g, s);
       }
       if (st.epi_region >= 0) return run_gemm_epilogue(P, st, g, s);
+      if (g.mode == 1) {  // operands with a transposed copy are read K-major from it
+        if (st.tsh_use[0] >= 0) {
+          g.A = P.arena + P.tshadows[st.tsh_use[0]].arena_off;
+          g.transA = 1;
+          g.lda = g.K;
+        }
+        if (st.tsh_use[1] >= 0) {
+          g.B = P.arena + P.tshadows[st.tsh_use[1]].arena_off;
+          g.transB = 0;
+          g.ldb = g.K;
+        }
+      }
       if (g.mode == 1 && gemm_tc_eligible(g)) return launch_gemm_tc(P.ctx, g, s);
       g.mode = 0;
       return launch_gemm_ffma(g, s);
