@@ -100,7 +100,8 @@ def workload(name, rank, nranks, small=False):
                     label=f"C5: sum(E[:, idx] .* V), E {rows}x{nt}, {ni} Int64 indices (bit-exact scatter-add pullback)",
                     gemm_flops=0, hbm_bytes=V.nbytes + idx.nbytes + E.nbytes, hbm_step="ungetindex",
                     # algorithmic bytes of the other steps of the eval (reported beside the scatter-add pullback)
-                    hbm_other={"region": 4 * V.nbytes, "getindex": idx.nbytes + 2 * V.nbytes})
+                    # (fused pass: gathers E[:, idx] itself, reads V, writes dV; the loss is a sink)
+                    hbm_other={"region": 3 * V.nbytes + idx.nbytes})
     if name == "c1":
         return dict(f=cases.c1_mlp, args=list(cases.c1_args()), n_params=4, batch_args=(4, 5),
                     label="C1: MLP 784-128-10 tanh, batch 64", gemm_flops=3.9e7, hbm_bytes=None)

@@ -74,7 +74,9 @@ int ctx_ensure_device(yota_ctx* ctx);
 int ctx_scratch(yota_ctx* ctx, size_t bytes, void** out);
 
 // ---- elementwise region (ew_kernels.cu) ------------------------------------------------
-enum : int { CLS_FULL = 0, CLS_ROWVEC = 1, CLS_COLVEC = 2, CLS_SCALAR = 3 };
+// CLS_GATHER: a FULL operand read through a column index, element (r, c) = x[r, idx[c]]
+// (getindex(x, :, idx) fused into its consumer region)
+enum : int { CLS_FULL = 0, CLS_ROWVEC = 1, CLS_COLVEC = 2, CLS_SCALAR = 3, CLS_GATHER = 4 };
 enum : int { OUT_STORE = 0, OUT_ROWSUM = 1, OUT_SCALARSUM = 2 };
 constexpr int RG_MAX_IN = 12;
 constexpr int RG_MAX_OUT = 12;
@@ -88,6 +90,8 @@ struct RegionIn {
   const float* ptr;
   int cls;
   int slot;
+  const long long* idx;  // CLS_GATHER: 1-based Int64 column indices (clamped like the stand-alone gather)
+  long long gather_n;    // CLS_GATHER: number of columns of the gathered array
 };
 struct RegionOut {
   float* ptr;  // STORE: destination; ROWSUM / SCALARSUM: partials workspace
@@ -190,12 +194,15 @@ struct IndexSpec {
 int launch_getindex(const IndexSpec& sp, float* y, const float* x, long long n_out, cudaStream_t s);
 size_t ungetindex_workspace_bytes(const IndexSpec& sp);
 int launch_ungetindex(const IndexSpec& sp, float* dx, const float* dy, void* workspace, size_t ws_bytes,
-                      int sm_count, cudaStream_t s);
+                      int sm_count, cudaStream_t s, const float* scale = nullptr);
 // acc[I...] = acc[I...] + (0.0f + dy) over the selection (no index vectors); other elements untouched
 int launch_slice_accum(const IndexSpec& sp, float* acc, const float* dy, bool scalar_dy, cudaStream_t s);
 size_t scatter_cols_workspace_bytes(long long n_dst, long long n_src);
+// scale != nullptr: folds scale[0] * dy[:, k] (one rounding per product, as if the product had
+// been materialised first): the seed-scaled source of a scatter-add pullback read in place
 int launch_scatter_add_cols(float* dx, long long rows, long long n_dst, const float* dy, const int64_t* idx,
-                            long long n_src, void* workspace, size_t ws_bytes, cudaStream_t s);
+                            long long n_src, void* workspace, size_t ws_bytes, cudaStream_t s,
+                            const float* scale = nullptr);
 int launch_gather_cols(float* y, const float* x, long long rows, long long n_dst, const int64_t* idx,
                        long long n_src, cudaStream_t s);
 

@@ -61,6 +61,12 @@ __device__ __forceinline__ float block_sum_fixed(float t, float* red /* >= 8 flo
   return s;
 }
 
+// column base of a gathered operand: x[:, idx[c]] with the index clamped into range
+__device__ __forceinline__ long long gather_col(const RegionIn& in, long long c) {
+  long long j = __ldg(in.idx + c) - 1;
+  return j < 0 ? 0 : (j >= in.gather_n ? in.gather_n - 1 : j);
+}
+
 template <int V>
 __global__ void __launch_bounds__(RG_THREADS) region_interp_kernel(const __grid_constant__ RegionParams p) {
   using vec = typename VecT<V>::type;
@@ -107,6 +113,8 @@ __global__ void __launch_bounds__(RG_THREADS) region_interp_kernel(const __grid_
           if (k >= 4) S[in.slot * RG_THREADS] = ld_vec<V>(in.ptr + off);
         } else if (in.cls == CLS_COLVEC) {
           S[in.slot * RG_THREADS] = VecT<V>::splat(__ldg(in.ptr + c));
+        } else if (in.cls == CLS_GATHER) {
+          S[in.slot * RG_THREADS] = ld_vec<V>(in.ptr + gather_col(in, c) * p.R + row);
         }
       }
       vec acc = VecT<V>::splat(0.f);

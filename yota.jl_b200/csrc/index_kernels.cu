@@ -472,20 +472,30 @@ struct FV<4> {
   static __device__ __forceinline__ T add(T a, T b) {
     return make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w));
   }
+  static __device__ __forceinline__ T mul(float s, T a) {
+    return make_float4(__fmul_rn(s, a.x), __fmul_rn(s, a.y), __fmul_rn(s, a.z), __fmul_rn(s, a.w));
+  }
 };
 template <>
 struct FV<1> {
   using T = float;
   static __device__ __forceinline__ T zero() { return 0.f; }
   static __device__ __forceinline__ T add(T a, T b) { return __fadd_rn(a, b); }
+  static __device__ __forceinline__ T mul(float s, T a) { return __fmul_rn(s, a); }
 };
 
-template <int V>
+template <int V, bool SCALED>
 __global__ void __launch_bounds__(256) scatter_fold_cols_kernel(typename FV<V>::T* __restrict__ dx,
                                                                 const typename FV<V>::T* __restrict__ dy, int RV,
                                                                 long long n_dst, const unsigned* __restrict__ perm,
-                                                                const unsigned* __restrict__ seg) {
+                                                                const unsigned* __restrict__ seg,
+                                                                const float* __restrict__ scale) {
   using T = typename FV<V>::T;
+  const float sc = SCALED ? __ldg(scale) : 1.f;
+  auto ld = [&](long long off) {
+    const T v = __ldg(dy + off);
+    return SCALED ? FV<V>::mul(sc, v) : v;
+  };
   // TPC threads cooperate on one destination column; a CTA holds 256 / TPC columns
   const int TPC = RV < 256 ? RV : 256;
   const int cpb = 256 / TPC;
@@ -498,20 +508,20 @@ __global__ void __launch_bounds__(256) scatter_fold_cols_kernel(typename FV<V>::
       unsigned p = p0;
       for (; p + 4 <= p1; p += 4) {  // 4 independent loads in flight, folded in source order
         const unsigned k0 = __ldg(perm + p), k1 = __ldg(perm + p + 1), k2 = __ldg(perm + p + 2), k3 = __ldg(perm + p + 3);
-        const T v0 = __ldg(dy + (long long)k0 * RV + rv);
-        const T v1 = __ldg(dy + (long long)k1 * RV + rv);
-        const T v2 = __ldg(dy + (long long)k2 * RV + rv);
-        const T v3 = __ldg(dy + (long long)k3 * RV + rv);
+        const T v0 = ld((long long)k0 * RV + rv);
+        const T v1 = ld((long long)k1 * RV + rv);
+        const T v2 = ld((long long)k2 * RV + rv);
+        const T v3 = ld((long long)k3 * RV + rv);
         acc = FV<V>::add(FV<V>::add(FV<V>::add(FV<V>::add(acc, v0), v1), v2), v3);
       }
-      for (; p < p1; p++) acc = FV<V>::add(acc, __ldg(dy + (long long)__ldg(perm + p) * RV + rv));
+      for (; p < p1; p++) acc = FV<V>::add(acc, ld((long long)__ldg(perm + p) * RV + rv));
       dx[j * RV + rv] = acc;
     }
   }
 }
 
 int launch_scatter_add_cols(float* dx, long long rows, long long n_dst, const float* dy, const int64_t* idx,
-                            long long n_src, void* workspace, size_t ws_bytes, cudaStream_t s) {
+                            long long n_src, void* workspace, size_t ws_bytes, cudaStream_t s, const float* scale) {
   if (rows * n_dst == 0) return YOTA_OK;
   if (n_src >= (1ll << 32) - 1 || n_dst >= (1ll << 32) - 2)
     YOTA_FAIL(YOTA_E_SHAPE, "scatter-add: more than 2^32 sources/destinations are not supported");
@@ -522,14 +532,22 @@ int launch_scatter_add_cols(float* dx, long long rows, long long n_dst, const fl
   if (v4) {
     const int RV = (int)(rows / 4);
     const int TPC = RV < 256 ? RV : 256, cpb = 256 / TPC;
-    scatter_fold_cols_kernel<4><<<grid_for((n_dst + cpb - 1) / cpb, 1, 148 * 32), 256, 0, s>>>(
-        reinterpret_cast<float4*>(dx), reinterpret_cast<const float4*>(dy), RV, n_dst, perm, seg);
+    const unsigned grid = grid_for((n_dst + cpb - 1) / cpb, 1, 148 * 32);
+    if (scale)
+      scatter_fold_cols_kernel<4, true><<<grid, 256, 0, s>>>(reinterpret_cast<float4*>(dx),
+                                                             reinterpret_cast<const float4*>(dy), RV, n_dst, perm, seg, scale);
+    else
+      scatter_fold_cols_kernel<4, false><<<grid, 256, 0, s>>>(reinterpret_cast<float4*>(dx),
+                                                              reinterpret_cast<const float4*>(dy), RV, n_dst, perm, seg, nullptr);
   } else {
     if (rows > 0x7fffffff) YOTA_FAIL(YOTA_E_SHAPE, "scatter-add: too many rows");
     const int RV = (int)rows;
     const int TPC = RV < 256 ? RV : 256, cpb = 256 / TPC;
-    scatter_fold_cols_kernel<1><<<grid_for((n_dst + cpb - 1) / cpb, 1, 148 * 32), 256, 0, s>>>(dx, dy, RV, n_dst, perm,
-                                                                                             seg);
+    const unsigned grid = grid_for((n_dst + cpb - 1) / cpb, 1, 148 * 32);
+    if (scale)
+      scatter_fold_cols_kernel<1, true><<<grid, 256, 0, s>>>(dx, dy, RV, n_dst, perm, seg, scale);
+    else
+      scatter_fold_cols_kernel<1, false><<<grid, 256, 0, s>>>(dx, dy, RV, n_dst, perm, seg, nullptr);
   }
   YOTA_CUDA(cudaGetLastError());
   return YOTA_OK;
@@ -591,7 +609,7 @@ size_t ungetindex_workspace_bytes(const IndexSpec& sp) {
 }
 
 int launch_ungetindex(const IndexSpec& sp, float* dx, const float* dy, void* workspace, size_t ws_bytes, int sm_count,
-                      cudaStream_t s) {
+                      cudaStream_t s, const float* scale) {
   (void)sm_count;
   long long n_x = 1;
   for (int d = 0; d < sp.n; d++) n_x *= sp.xdims[d];
@@ -605,7 +623,9 @@ int launch_ungetindex(const IndexSpec& sp, float* dx, const float* dy, void* wor
   if (nvec > 1) YOTA_FAIL(YOTA_E_UNSUPPORTED_OP, "ungetindex: more than one index vector is not supported");
   // fast path: dx[:, idx] += dy on a matrix
   if (sp.n == 2 && sp.kind[0] == YOTA_IDX_COLON && vec_dim == 1)
-    return launch_scatter_add_cols(dx, sp.xdims[0], sp.xdims[1], dy, sp.vec[1], sp.vlen[1], workspace, ws_bytes, s);
+    return launch_scatter_add_cols(dx, sp.xdims[0], sp.xdims[1], dy, sp.vec[1], sp.vlen[1], workspace, ws_bytes, s,
+                                   scale);
+  if (scale) YOTA_FAIL(YOTA_E_ARG, "internal: scaled source planned for a general ungetindex");
   UngetParams p{};
   p.nd = sp.n;
   p.vec_dim = vec_dim;

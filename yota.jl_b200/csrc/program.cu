@@ -71,6 +71,7 @@ struct Region {
   // codegen results
   int k = 0;
   RegionLaunch L;
+  std::vector<int> gather_x, gather_idx;  // per RegionIn: gathered array / index vector (CLS_GATHER), else -1
   std::vector<int> in_tensors;   // tensor id per RegionIn
   std::vector<int> out_tensors;  // tensor id per RegionOut (for sums: the SUM's output tensor)
   std::vector<int> finish_steps;
@@ -116,6 +117,7 @@ struct yota_program {
   std::vector<Region> regions;
   std::vector<Step> steps;
   std::vector<char> op_needed;
+  std::vector<int> op_scale;  // UNGETINDEX ops: scalar tensor multiplied into the source on load (-1: none)
   int n_in = 0, n_out = 0;
   size_t arena_bytes = 0, const_bytes = 0;
   std::vector<int> const_tensors;  // CONST / SEED tensors, in const-buffer order
@@ -1135,6 +1137,102 @@ static int index_spec_of(const yota_program& P, const yota_op_desc& o, const TIn
   return YOTA_OK;
 }
 
+// Peephole on the op list (before dead-code elimination): the scatter-add pullback of
+// `sum(x[:, idx] .* V)` arrives as  D = copy(seed) (the broadcast-back of the sum's pullback),
+// dG = D .* V,  dx = ungetindex(dG, :, idx).  dG exists only to be scattered, so the fold reads V
+// in place and multiplies by the seed on load -- the same single rounding per product, the same
+// fold order, bit-identical -- and the 4 GiB product (C5) is neither written nor read back.
+static void rewrite_scaled_scatter(yota_program& P) {
+  P.op_scale.assign(P.ops.size(), -1);
+  if ((P.flags & YOTA_FLAG_NO_FUSE) || getenv("YOTA_NO_SCALED_SCATTER")) return;
+  for (size_t u = 0; u < P.ops.size(); u++) {
+    yota_op_desc& U = P.ops[u];
+    if (U.opcode != YOTA_OP_UNGETINDEX || U.iattr[0] != 2) continue;
+    if (U.iattr[1] != YOTA_IDX_COLON || U.iattr[4] != YOTA_IDX_VEC) continue;
+    const int t = U.in[0];
+    const TInfo& tt = P.T[t];
+    if (tt.d.kind != YOTA_T_TEMP || tt.producer < 0 || tt.consumers.size() != 1 || tt.d.ndim != 2) continue;
+    const yota_op_desc& M = P.ops[tt.producer];
+    if (M.opcode != YOTA_EW_MUL) continue;
+    for (int side = 0; side < 2; side++) {
+      const int d = M.in[side], v = M.in[1 - side];
+      const TInfo &td = P.T[d], &tv = P.T[v];
+      if (td.producer < 0 || P.ops[td.producer].opcode != YOTA_EW_COPY) continue;
+      const int sc = P.ops[td.producer].in[0];
+      const TInfo& ts = P.T[sc];
+      if (ts.numel != 1 || (ts.d.kind != YOTA_T_SEED && ts.d.kind != YOTA_T_CONST && ts.d.kind != YOTA_T_INPUT)) continue;
+      if (tv.nd != tt.nd || tv.numel != tt.numel || tv.d.dtype != YOTA_F32) continue;
+      bool same = true;
+      for (int q = 0; q < 4; q++) same &= tv.dims[q] == tt.dims[q];
+      if (!same) continue;
+      U.in[0] = v;
+      P.op_scale[u] = sc;
+      P.T[t].consumers.clear();
+      P.T[v].consumers.push_back((int)u);
+      P.T[sc].consumers.push_back((int)u);
+      break;
+    }
+  }
+}
+
+// getindex(x, :, idx) -> consumer-region fusion: when every reader of the gathered columns is an
+// elementwise op of ONE region in which it is a FULL operand, the region reads x[:, idx[c]]
+// itself (operand class CLS_GATHER) and the gathered copy (C5: 4 GiB written, 4 GiB read back)
+// never exists.
+static int plan_gather_fusion(yota_program& P) {
+  if ((P.flags & YOTA_FLAG_NO_FUSE) || getenv("YOTA_NO_GATHER_FUSION")) return YOTA_OK;
+  for (size_t si = 0; si < P.steps.size(); si++) {
+    Step& gs = P.steps[si];
+    if (gs.kind != STEP_GETINDEX) continue;
+    const yota_op_desc& o = P.ops[gs.op];
+    if (o.iattr[0] != 2 || o.iattr[1] != YOTA_IDX_COLON || o.iattr[4] != YOTA_IDX_VEC) continue;
+    const int x = o.in[0], t = o.out, iv = o.in[1 + (int)o.iattr[5]];
+    const TInfo &xt = P.T[x], &tt = P.T[t];
+    if (xt.d.ndim != 2 || tt.d.kind != YOTA_T_TEMP || tt.alias_of >= 0 || P.T[iv].d.dtype != YOTA_I64) continue;
+    int ri = -1;
+    bool ok = true;
+    for (int c : tt.consumers) {
+      if (!P.op_needed[c]) continue;
+      const yota_op_desc& co = P.ops[c];
+      if (!is_ew(co.opcode) || P.T[co.out].region < 0) ok = false;
+      else if (ri < 0) ri = P.T[co.out].region;
+      else if (ri != P.T[co.out].region) ok = false;
+    }
+    for (size_t q = 0; q < P.T.size(); q++)
+      if (P.T[q].alias_of == t && P.T[q].needed) ok = false;
+    if (!ok || ri < 0) continue;
+    Region& r = P.regions[ri];
+    RegionParams& rp = r.L.p;
+    if (r.step <= (int)si || P.steps[r.step].kind != STEP_REGION) continue;
+    if (r.k != 1 || rp.R != xt.d.dims[0] || rp.C != P.T[iv].numel) continue;
+    int q_in = -1;
+    for (int q = 0; q < rp.n_in; q++)
+      if (r.in_tensors[q] == t && rp.in[q].cls == CLS_FULL) q_in = q;
+    if (q_in < 0) continue;
+    rp.in[q_in].cls = CLS_GATHER;
+    r.gather_x.assign(rp.n_in, -1);
+    r.gather_idx.assign(rp.n_in, -1);
+    r.gather_x[q_in] = x;
+    r.gather_idx[q_in] = iv;
+    Step& rs = P.steps[r.step];
+    for (int& rd : rs.reads)
+      if (rd == t) rd = x;
+    rs.reads.push_back(iv);
+    P.T[root_of(P, x)].materialized = true;
+    P.T[t].materialized = false;
+    gs.kind = STEP_NOP;
+    gs.label = "(gathered inside step " + std::to_string(r.step) + ")";
+    // the operand class is part of the micro-program's signature
+    if (r.L.static_id >= 0) P.n_static--;
+    r.sig = region_signature(rp, r.L.V);
+    r.L.static_id = (P.flags & YOTA_FLAG_NO_STATIC) ? -1 : static_chain_lookup(rp, r.L.V);
+    if (r.L.static_id >= 0) P.n_static++;
+    const size_t cut = rs.label.find(" static=") != std::string::npos ? rs.label.find(" static=") : rs.label.find(" interp");
+    rs.label = rs.label.substr(0, cut) + " gather" + (r.L.static_id >= 0 ? std::string(" static=") + static_chain_name(r.L.static_id) : " interp");
+  }
+  return YOTA_OK;
+}
+
 // GEMM -> consumer-region fusion: when the only reader of a tensor-core GEMM's output is one
 // fused region whose micro-program exists as an epilogue variant (bias [+ tanh]; tanh' * delta
 // + db), the region runs inside the GEMM's epilogue and the GEMM output never touches HBM.
@@ -1220,6 +1318,7 @@ static int finish_steps(yota_program& P) {
     if (st.op < 0 || st.kind == STEP_ROWSUM_FINISH || st.kind == STEP_SCALAR_FINISH) continue;
     const yota_op_desc& o = P.ops[st.op];
     st.writes.push_back(st.out_override >= 0 ? st.out_override : o.out);
+    if (st.kind == STEP_UNGETINDEX && P.op_scale[st.op] >= 0) st.reads.push_back(P.op_scale[st.op]);
     if (st.kind == STEP_GETINDEX || st.kind == STEP_UNGETINDEX || st.kind == STEP_SLICE_ACCUM) {
       IndexSpec sp;
       long long nsel;
@@ -1298,6 +1397,7 @@ extern "C" int yota_program_build(yota_ctx* ctx, const yota_op_desc* ops, int64_
   }
   int st = validate(P);
   if (st) return fail(st);
+  rewrite_scaled_scatter(P);
   // dead-code elimination
   P.op_needed.assign(P.ops.size(), 0);
   for (int i = (int)P.ops.size() - 1; i >= 0; i--) {
@@ -1315,6 +1415,7 @@ extern "C" int yota_program_build(yota_ctx* ctx, const yota_op_desc* ops, int64_
   if ((st = plan_fusion(P))) return fail(st);
   for (size_t r = 0; r < P.regions.size(); r++)
     if ((st = codegen_region(P, (int)r))) return fail(st);
+  if ((st = plan_gather_fusion(P))) return fail(st);
   if ((st = plan_gemm_epilogues(P))) return fail(st);
   if ((st = finish_steps(P))) return fail(st);
   if ((st = plan_bf16_shadows(P))) return fail(st);
@@ -1410,9 +1511,14 @@ static int ensure_arena(yota_program& P) {
 static int bind_region(yota_program& P, Region& r, RegionLaunch& L) {
   const int n_store = L.p.n_out - (int)r.sums.size();
   for (int q = 0; q < L.p.n_in; q++) {
-    L.p.in[q].ptr = static_cast<const float*>(tensor_ptr(P, r.in_tensors[q]));
+    if (L.p.in[q].cls == CLS_GATHER) {  // x[:, idx[c]]: read from the gathered array itself
+      L.p.in[q].ptr = static_cast<const float*>(tensor_ptr(P, r.gather_x[q]));
+      L.p.in[q].idx = static_cast<const long long*>(tensor_ptr(P, r.gather_idx[q]));
+      L.p.in[q].gather_n = P.T[r.gather_x[q]].d.dims[1];
+    } else
+      L.p.in[q].ptr = static_cast<const float*>(tensor_ptr(P, r.in_tensors[q]));
     if (L.V == 4 && (reinterpret_cast<uintptr_t>(L.p.in[q].ptr) & 15) &&
-        (L.p.in[q].cls == CLS_FULL || L.p.in[q].cls == CLS_ROWVEC))
+        (L.p.in[q].cls == CLS_FULL || L.p.in[q].cls == CLS_ROWVEC || L.p.in[q].cls == CLS_GATHER))
       YOTA_FAIL(YOTA_E_ARG, "array bound to the program is not 16-byte aligned (use yota_alloc)");
   }
   for (int q = 0; q < L.p.n_out; q++) {
@@ -1553,8 +1659,10 @@ static int run_step(yota_program& P, Step& st, cudaStream_t s) {
         if (sp.kind[d] == YOTA_IDX_VEC)
           sp.vec[d] = static_cast<const int64_t*>(tensor_ptr(P, o.in[1 + (int)sp.a[d]]));
       if (st.kind == STEP_GETINDEX) return launch_getindex(sp, out, in0, ot.numel, s);
+      const float* scale =
+          P.op_scale[st.op] >= 0 ? static_cast<const float*>(tensor_ptr(P, P.op_scale[st.op])) : nullptr;
       return launch_ungetindex(sp, out, in0, st.ws_off >= 0 ? P.arena + st.ws_off : nullptr, st.ws_bytes,
-                               P.ctx->sm_count, s);
+                               P.ctx->sm_count, s, scale);
     }
     case STEP_LOGSOFTMAX: {
       const TInfo& x = P.T[o.in[0]];
