@@ -308,6 +308,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll 1
       for (int c = 0; c < TN / 32; c++) {
         uint32_t v[32];
+        // C += ...: the 32 old values are requested before the accumulator read, all in flight at
+        // once (left inside the store loop they serialise: load -> add -> store per element)
+        float old[32];
+        if (p.accumulate) {
+          const float* cp0 = crow + (long long)(c * 32) * p.ldc;
+#pragma unroll
+          for (int j = 0; j < 32; j++) old[j] = __ldcg(cp0 + j * p.ldc);
+        }
         const uint32_t taddr = tmem_base + (uint32_t)(acc * TN + c * 32) + ((uint32_t)(q * 32) << 16);
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -323,7 +331,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         float* cp = crow + (long long)(c * 32) * p.ldc;
         if (p.accumulate) {
 #pragma unroll
-          for (int j = 0; j < 32; j++) cp[j * p.ldc] = __uint_as_float(v[j]) + cp[j * p.ldc];
+          for (int j = 0; j < 32; j++) cp[j * p.ldc] = __uint_as_float(v[j]) + old[j];
         } else {
 #pragma unroll
           for (int j = 0; j < 32; j++) cp[j * p.ldc] = __uint_as_float(v[j]);
@@ -771,6 +779,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll 1
       for (int c = 0; c < TN2 / 32; c++) {
         uint32_t v[32];
+        float old[32];
+        if constexpr (EPI < 0) {
+          if (p.accumulate) {  // see gemm_tc_kernel: old values of C in flight before the accumulator read
+            const float* cp0 = crow + (long long)(c * 32) * p.ldc;
+#pragma unroll
+            for (int j = 0; j < 32; j++) old[j] = __ldcg(cp0 + j * p.ldc);
+          }
+        }
         const uint32_t taddr = tmem_base + (uint32_t)(acc * TN2 + c * 32) + ((uint32_t)(q * 32) << 16);
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -790,7 +806,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           float* cp = crow + (long long)(c * 32) * p.ldc;
           if (p.accumulate) {
 #pragma unroll
-            for (int j = 0; j < 32; j++) cp[j * p.ldc] = __uint_as_float(v[j]) + cp[j * p.ldc];
+            for (int j = 0; j < 32; j++) cp[j * p.ldc] = __uint_as_float(v[j]) + old[j];
           } else {
 #pragma unroll
             for (int j = 0; j < 32; j++) cp[j * p.ldc] = __uint_as_float(v[j]);

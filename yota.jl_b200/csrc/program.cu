@@ -50,7 +50,8 @@ struct TInfo {
   long long numel = 1;
   int producer = -1;
   std::vector<int> consumers;
-  int alias_of = -1;  // root tensor for RESHAPE outputs
+  int alias_of = -1;  // tensor whose storage this one shares: RESHAPE outputs, contiguous getindex slices
+  long long alias_elem_off = 0;  // ... starting this many elements into it
   bool needed = false;
   bool materialized = false;
   int region = -1;  // region index if produced by a fused EW op
@@ -159,6 +160,12 @@ static bool is_ew(int opcode) { return opcode >= YOTA_EW_COPY && opcode <= YOTA_
 static int root_of(const yota_program& P, int t) {
   while (P.T[t].alias_of >= 0) t = P.T[t].alias_of;
   return t;
+}
+// element offset of tensor t inside its root's storage
+static long long alias_offset(const yota_program& P, int t) {
+  long long off = 0;
+  for (; P.T[t].alias_of >= 0; t = P.T[t].alias_of) off += P.T[t].alias_elem_off;
+  return off;
 }
 
 // valid split points of an operand with canonical dims E (ne) inside iteration dims D (nd)
@@ -578,6 +585,30 @@ static int plan_fusion(yota_program& P) {
       P.T[r].materialized = true;
       out.def_step = step_of_tensor(P, o.in[0]);
       continue;
+    }
+    if (o.opcode == YOTA_OP_GETINDEX && fuse && out.d.kind == YOTA_T_TEMP && !getenv("YOTA_NO_SLICE_ALIAS")) {
+      // x[:, ..., :, t] (or a range in the last place) of a column-major array is a contiguous
+      // block: no copy, the result is a view (C4: the 128 x[:, :, t] slices of the unrolled RNN)
+      const int n = (int)o.iattr[0];
+      const TInfo& x = P.T[o.in[0]];
+      bool contiguous = n >= 2 && n == x.d.ndim && x.d.dtype == YOTA_F32;
+      for (int d = 0; d + 1 < n && contiguous; d++) contiguous = o.iattr[1 + 3 * d] == YOTA_IDX_COLON;
+      const long long kind_last = contiguous ? o.iattr[1 + 3 * (n - 1)] : -1;
+      contiguous = contiguous && (kind_last == YOTA_IDX_INT || kind_last == YOTA_IDX_RANGE);
+      if (contiguous) {
+        long long inner = 1;
+        for (int d = 0; d + 1 < n; d++) inner *= x.d.dims[d];
+        const long long a = o.iattr[2 + 3 * (n - 1)];
+        const long long cnt = kind_last == YOTA_IDX_INT ? 1 : o.iattr[3 + 3 * (n - 1)] - a + 1;
+        const long long off = (a - 1) * inner;
+        if (a >= 1 && cnt >= 1 && a - 1 + cnt <= x.d.dims[n - 1] && inner * cnt == out.numel && off % 4 == 0) {
+          out.alias_of = o.in[0];
+          out.alias_elem_off = off;
+          P.T[root_of(P, o.in[0])].materialized = true;
+          out.def_step = step_of_tensor(P, o.in[0]);
+          continue;
+        }
+      }
     }
     if (o.opcode == YOTA_EW_ADD && fuse && try_inplace_accumulate(P, F, (int)i)) continue;
     if (is_ew(o.opcode)) {
@@ -1474,8 +1505,7 @@ extern "C" int yota_program_destroy(yota_program* p) {
 // ==========================================================================================
 namespace yota {
 
-static void* tensor_ptr(yota_program& P, int t) {
-  const int r = root_of(P, t);
+static void* root_ptr(yota_program& P, int r) {
   const TInfo& ti = P.T[r];
   switch (ti.d.kind) {
     case YOTA_T_INPUT: return P.bound_in[ti.d.slot];
@@ -1486,6 +1516,12 @@ static void* tensor_ptr(yota_program& P, int t) {
       if (ti.fwd_out_slot >= 0) return P.bound_out[ti.fwd_out_slot];
       return ti.arena_off >= 0 ? P.arena + ti.arena_off : nullptr;
   }
+}
+static void* tensor_ptr(yota_program& P, int t) {
+  const int r = root_of(P, t);
+  char* p = static_cast<char*>(root_ptr(P, r));
+  const long long off = alias_offset(P, t);
+  return p && off ? p + off * (P.T[r].d.dtype == YOTA_I64 ? 8 : 4) : p;
 }
 
 static int ensure_arena(yota_program& P) {
@@ -1617,10 +1653,14 @@ static int run_step(yota_program& P, Step& st, cudaStream_t s) {
         const void* src[2] = {g.A, g.B};
         void* sh[2];
         for (int j = 0; j < 2; j++) {
-          sh[j] = P.arena + P.shadows[st.shadow[j]].arena_off;
-          if (st.cast[j])
-            YOTA_TRY(launch_cast_bf16(sh[j], static_cast<const float*>(src[j]), P.T[root_of(P, o.in[j])].numel, s));
+          char* base = P.arena + P.shadows[st.shadow[j]].arena_off;  // shadow of the whole root array
+          if (st.cast[j]) {
+            const int root = root_of(P, o.in[j]);
+            YOTA_TRY(launch_cast_bf16(base, static_cast<const float*>(root_ptr(P, root)), P.T[root].numel, s));
+          }
+          sh[j] = base + alias_offset(P, o.in[j]) * 2;
         }
+        (void)src;
         g.A = sh[0];
         g.B = sh[1];
         if (st.epi_region >= 0) return run_gemm_epilogue(P, st, g, s);
