@@ -167,11 +167,42 @@ __global__ void __launch_bounds__(256) gemm_small_kernel(long long M, long long 
   *dst = accumulate ? *dst + acc : acc;
 }
 
+// Same tiny problems when K is long (C1: K = 784, 128): one WARP per output element, lanes
+// stride K (coalesced when K is the contiguous axis), fixed xor-shuffle tree at the end --
+// deterministic, and 32x less serial latency than one thread walking K.
+__global__ void __launch_bounds__(256) gemm_small_warp_kernel(long long M, long long N, long long K,
+                                                              const float* __restrict__ A, long long sam, long long sak,
+                                                              const float* __restrict__ B, long long sbk, long long sbn,
+                                                              float* __restrict__ C, long long ldc, int accumulate) {
+  const int lane = threadIdx.x & 31;
+  const long long w = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (w >= M * N) return;
+  const long long m = w % M, n = w / M;
+  const float* a = A + m * sam;
+  const float* b = B + n * sbn;
+  float acc = 0.f;
+  for (long long k = lane; k < K; k += 32) acc = fmaf(__ldg(a + k * sak), __ldg(b + k * sbk), acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+  if (lane == 0) {
+    float* dst = C + m + n * ldc;
+    *dst = accumulate ? *dst + acc : acc;
+  }
+}
+
 int launch_gemm_ffma(const GemmArgs& g, cudaStream_t s) {
   if (g.M <= 0 || g.N <= 0) return YOTA_OK;
   // element strides: op(A)(m,k), op(B)(k,n)
   const long long sam = g.transA ? g.lda : 1, sak = g.transA ? 1 : g.lda;
   const long long sbk = g.transB ? g.ldb : 1, sbn = g.transB ? 1 : g.ldb;
+  if (g.M * g.N <= 128 * 1024 && g.M * g.N * g.K <= (64ll << 20) && g.K >= 64) {
+    const long long warps = g.M * g.N;
+    gemm_small_warp_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, s>>>(g.M, g.N, g.K, static_cast<const float*>(g.A), sam,
+                                                                       sak, static_cast<const float*>(g.B), sbk, sbn, g.C,
+                                                                       g.ldc, g.accumulate);
+    YOTA_CUDA(cudaGetLastError());
+    return YOTA_OK;
+  }
   if (g.M * g.N <= 128 * 1024 && g.M * g.N * g.K <= (64ll << 20) && (g.N + 7) / 8 <= 65535) {
     dim3 grid((unsigned)((g.M + 31) / 32), (unsigned)((g.N + 7) / 8));
     gemm_small_kernel<<<grid, 256, 0, s>>>(g.M, g.N, g.K, static_cast<const float*>(g.A), sam, sak,
