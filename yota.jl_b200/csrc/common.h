@@ -171,6 +171,9 @@ struct GemmArgs {
   float* tsh = nullptr;
   long long tsh_ld = 0;
   int tsh_out = -1;
+  // ... and BF16 copy of chain output `bsh_out` (BF16 mode: the operand shadow of later GEMMs)
+  void* bsh = nullptr;
+  int bsh_out = -1;
 };
 int launch_gemm_ffma(const GemmArgs& g, cudaStream_t s);
 int launch_gemm_tc(yota_ctx* ctx, const GemmArgs& g, cudaStream_t s);  // returns YOTA_E_UNSUPPORTED_OP if shape not eligible

@@ -143,6 +143,10 @@ struct Params {
   float* tsh;
   long long tsh_ld;
   int tsh_out;
+  // fused epilogue, BF16 mode: store output `bsh_out` a second time as BF16 (same layout): the
+  // operand shadow the next GEMMs read, written here instead of by a cast kernel
+  __nv_bfloat16* bsh;
+  int bsh_out;
 };
 
 template <int TN>
@@ -421,6 +425,8 @@ static int launch(const GemmArgs& g, const CUtensorMap& ma, const CUtensorMap& m
   p.tsh = nullptr;
   p.tsh_ld = 0;
   p.tsh_out = -1;
+  p.bsh = nullptr;
+  p.bsh_out = -1;
   p.num_m = (int)(g.M / TM);
   p.num_n = (int)(g.N / TN);
   const int tiles = p.num_m * p.num_n;
@@ -545,7 +551,8 @@ struct Epilogue {
   // the epilogue runs at one DRAM latency per element.
   __device__ __forceinline__ static void chunk32(const RegionParams& rp, const uint32_t (&z)[32], long long m,
                                                  long long n0, long long R, const float (&base)[NS], float (&accs)[NO],
-                                                 float* tsh, long long tsh_ld, int tsh_out, float4* stage) {
+                                                 float* tsh, long long tsh_ld, int tsh_out, float4* stage,
+                                                 __nv_bfloat16* bsh, int bsh_out) {
     const int lane = threadIdx.x & 31;
     float tv[4];
     constexpr int NI = N_IN > 0 ? N_IN : 1;
@@ -588,6 +595,7 @@ struct Epilogue {
         if constexpr (kind == OUT_STORE) {
           rp.out[decltype(k)::value].ptr[off] = v[src];
           if (decltype(k)::value == tsh_out) tv[j & 3] = v[src];
+          if (bsh && decltype(k)::value == bsh_out) bsh[off] = __float2bfloat16_rn(v[src]);
         } else
           accs[decltype(k)::value] = __fadd_rn(accs[decltype(k)::value], v[src]);
       });
@@ -801,7 +809,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if constexpr (EPI >= 0) {
           EP::chunk32(rp, v, m, n0 + c * 32, p.M, ebase, eaccs, p.tsh, p.tsh_ld, p.tsh_out,
-                      reinterpret_cast<float4*>(smem + S::TSH_OFF) + q * 256);
+                      reinterpret_cast<float4*>(smem + S::TSH_OFF) + q * 256, p.bsh, p.bsh_out);
         } else {
           float* cp = crow + (long long)(c * 32) * p.ldc;
           if (p.accumulate) {
@@ -851,6 +859,8 @@ static int launch2(const GemmArgs& g, const CUtensorMap& ma, const CUtensorMap& 
   p.tsh = g.tsh;
   p.tsh_ld = g.tsh_ld;
   p.tsh_out = g.tsh_out;
+  p.bsh = static_cast<__nv_bfloat16*>(g.bsh);
+  p.bsh_out = g.bsh_out;
   p.num_m = (int)(g.M / (2 * TM));
   p.num_n = (int)(g.N / TN2);
   const int tiles = p.num_m * p.num_n;

@@ -104,6 +104,8 @@ struct Step {
   int tsh_make = -1;      // fused-epilogue GEMM: transposed shadow it also writes ...
   int tsh_make_out = -1;  // ... of this store output of the chain
   int tsh_use[2] = {-1, -1};  // GEMM: operand A / B is read from this transposed shadow (K-major)
+  int bsh_make = -1;      // fused-epilogue GEMM (BF16 mode): BF16 shadow it writes itself ...
+  int bsh_make_out = -1;  // ... of this store output of the chain
 };
 
 }  // namespace yota
@@ -955,6 +957,7 @@ static void gemm_dims(const yota_program& P, const yota_op_desc& o, long long* M
 // the same tensor (H_l feeds the forward and the dW GEMM, ΔZ_l the dW and dH GEMMs, ...).
 static int plan_bf16_shadows(yota_program& P) {
   if (!(P.flags & YOTA_FLAG_GEMM_BF16)) return YOTA_OK;
+  const bool in_epilogue = !(P.flags & YOTA_FLAG_NO_FUSE) && !getenv("YOTA_NO_EPI_SHADOW");
   std::map<int, int> shadow_of;
   for (size_t s = 0; s < P.steps.size(); s++) {
     Step& st = P.steps[s];
@@ -973,9 +976,27 @@ static int plan_bf16_shadows(yota_program& P) {
         yota_program::Shadow sh;
         sh.tensor = root;
         sh.first_step = sh.last_step = (int)s;
+        st.cast[j] = true;
+        // the tensor is the stored output of a fused GEMM epilogue: that epilogue writes the BF16
+        // copy too (one more 2-byte store per element it already holds) and the cast kernel --
+        // a 4-byte read and a 2-byte write per element -- disappears
+        const TInfo& rt = P.T[root];
+        const int d = rt.def_step;
+        if (in_epilogue && rt.d.kind == YOTA_T_TEMP && rt.alias_of < 0 && d >= 0 && d < (int)s &&
+            P.steps[d].kind == STEP_GEMM && P.steps[d].epi_region >= 0 && P.steps[d].bsh_make < 0) {
+          const Region& r = P.regions[P.steps[d].epi_region];
+          const int n_store = r.L.p.n_out - (int)r.sums.size();
+          for (int q = 0; q < n_store; q++)
+            if (r.out_tensors[q] == root) {
+              P.steps[d].bsh_make = (int)P.shadows.size();
+              P.steps[d].bsh_make_out = q;
+              P.steps[d].label += " +bf16";
+              sh.first_step = d;
+              st.cast[j] = false;
+            }
+        }
         P.shadows.push_back(sh);
         it = shadow_of.insert({root, (int)P.shadows.size() - 1}).first;
-        st.cast[j] = true;
       }
       st.shadow[j] = it->second;
       P.shadows[it->second].last_step = (int)s;
@@ -1575,6 +1596,10 @@ static int run_gemm_epilogue(yota_program& P, Step& st, const GemmArgs& g_in, cu
     g.tsh = reinterpret_cast<float*>(P.arena + sh.arena_off);
     g.tsh_ld = P.T[sh.tensor].dims[1];
     g.tsh_out = st.tsh_make_out;
+  }
+  if (st.bsh_make >= 0) {
+    g.bsh = P.arena + P.shadows[st.bsh_make].arena_off;
+    g.bsh_out = st.bsh_make_out;
   }
   Region& r = P.regions[st.epi_region];
   RegionLaunch L = r.L;

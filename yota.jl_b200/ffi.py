@@ -9,7 +9,8 @@ import os
 from . import ir
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libyota_cuda.so")
+# YOTA_LIB: load another build of the same ABI (A/B of kernel changes inside one GPU job)
+LIB_PATH = os.environ.get("YOTA_LIB") or os.path.join(_HERE, "lib", "libyota_cuda.so")
 
 
 class YotaError(RuntimeError):
