@@ -22,7 +22,8 @@ F32 = np.float32
 @pytest.mark.parametrize("tA,tB", [(0, 0), (0, 1), (1, 0), (1, 1)])
 def test_tf32_exact_on_small_integers(tA, tB):
     r = cases.rng(20)
-    for m, n, k in [(128, 128, 32), (128, 256, 64), (384, 640, 160), (1024, 1024, 512)]:
+    # (128 x 32 / 128 x 64 tiles for the skinny outputs, 128 x 128 and wider for the others)
+    for m, n, k in [(128, 128, 32), (128, 256, 64), (384, 640, 160), (1024, 1024, 512), (1024, 128, 1024)]:
         A = r.integers(-3, 4, size=(k, m) if tA else (m, k)).astype(F32)
         B = r.integers(-3, 4, size=(n, k) if tB else (k, n)).astype(F32)
         ref = (A.T if tA else A).astype(np.float64) @ (B.T if tB else B).astype(np.float64)

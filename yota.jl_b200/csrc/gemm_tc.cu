@@ -151,10 +151,13 @@ struct Params {
 
 template <int TN>
 struct Smem {
+  // narrow tiles (skinny outputs: a 1024 x 128 result is 8 CTAs at TN = 128, 32 at TN = 32) are
+  // latency-bound streams of A: twice the stages keep the same bytes in flight
+  static constexpr int NSTAGE = TN <= 64 ? 2 * STAGES : STAGES;
   static constexpr int A_BYTES = TM * 128;  // TM rows (or TM*EB/128 chunks of TK rows) of 128 bytes
   static constexpr int B_BYTES = TN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int BAR_OFF = NSTAGE * STAGE_BYTES;
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;  // + barriers + slack for 1 KiB alignment
 };
 
@@ -167,8 +170,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
-  uint64_t* empty = full + STAGES;
-  uint64_t* tfull = empty + STAGES;
+  uint64_t* empty = full + S::NSTAGE;
+  uint64_t* tfull = empty + S::NSTAGE;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
@@ -177,7 +180,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int nkb = (int)(p.K / (128 / EB));
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; s++) {
+    for (int s = 0; s < S::NSTAGE; s++) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
@@ -248,7 +251,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           else
             tma_load_2d(sb, &map_b, &full[stage], k0, n0);
         }
-        if (++stage == STAGES) {
+        if (++stage == S::NSTAGE) {
           stage = 0;
           phase ^= 1;
         }
@@ -286,7 +289,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               umma_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
-          if (++stage == STAGES) {
+          if (++stage == S::NSTAGE) {
             stage = 0;
             phase ^= 1;
           }
@@ -977,23 +980,38 @@ int launch_gemm_tc(yota_ctx* ctx, const GemmArgs& g, cudaStream_t s) {
     GO2(false, false);
 #undef GO2
   }
-  const int TN = (g.N % 256 == 0 && (g.M / tc::TM) * (g.N / 256) >= ctx->sm_count / 2) ? 256 : 128;
+  // widest tile that still gives half the SMs a CTA; skinny outputs go down to 128 x 32 (64 for
+  // BF16 operands, whose MN-major boxes are 64 elements wide)
+  const int widths[4] = {256, 128, 64, 32};
+  int TN = eb == 4 ? 32 : 64;
+  for (int w : widths)
+    if (w >= (eb == 4 ? 32 : 64) && g.N % w == 0 && (g.M / tc::TM) * (g.N / w) >= ctx->sm_count / 2) {
+      TN = w;
+      break;
+    }
   YOTA_TRY(tc::make_map(&ma, g.A, g.M, g.K, g.lda, A_MN, tc::TM, eb));
   YOTA_TRY(tc::make_map(&mb, g.B, g.N, g.K, g.ldb, B_MN, TN, eb));
 #define GO(TNv, a, b)                                                          \
   return eb == 4 ? tc::launch<TNv, a, b, 4>(g, ma, mb, grid_sms(ctx), s)       \
                  : tc::launch<TNv, a, b, 2>(g, ma, mb, grid_sms(ctx), s)
-  if (TN == 256) {
-    if (A_MN && B_MN) GO(256, true, true);
-    if (A_MN && !B_MN) GO(256, true, false);
-    if (!A_MN && B_MN) GO(256, false, true);
-    GO(256, false, false);
-  } else {
-    if (A_MN && B_MN) GO(128, true, true);
-    if (A_MN && !B_MN) GO(128, true, false);
-    if (!A_MN && B_MN) GO(128, false, true);
-    GO(128, false, false);
+#define GOALL(TNv)                          \
+  do {                                      \
+    if (A_MN && B_MN) GO(TNv, true, true);  \
+    if (A_MN && !B_MN) GO(TNv, true, false); \
+    if (!A_MN && B_MN) GO(TNv, false, true); \
+    GO(TNv, false, false);                  \
+  } while (0)
+  if (TN == 256) GOALL(256);
+  if (TN == 128) GOALL(128);
+  if (TN == 64) GOALL(64);
+  if (eb == 4) {
+    if (A_MN && B_MN) return tc::launch<32, true, true, 4>(g, ma, mb, grid_sms(ctx), s);
+    if (A_MN && !B_MN) return tc::launch<32, true, false, 4>(g, ma, mb, grid_sms(ctx), s);
+    if (!A_MN && B_MN) return tc::launch<32, false, true, 4>(g, ma, mb, grid_sms(ctx), s);
+    return tc::launch<32, false, false, 4>(g, ma, mb, grid_sms(ctx), s);
   }
+  YOTA_FAIL(YOTA_E_ARG, "internal: no tile width for this GEMM");
+#undef GOALL
 #undef GO
 }
 
