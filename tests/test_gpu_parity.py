@@ -207,3 +207,30 @@ def test_deterministic_run_to_run():
     assert r1[0] == r2[0]
     for x, y in zip(r1[1][1:], r2[1][1:]):
         assert np.array_equal(U.bits(x.to_host()), U.bits(y.to_host()))
+
+
+def test_c5_fused_plans_bit_exact_with_seed():
+    """getindex fused into the region as a gather operand, the fold reading V scaled by the seed:
+    every plan (fused / static chains off / unfused) gives the bits of the oracle, seed != 1 too."""
+    E, idx, V = cases.c5_args(64, 300, 2000)
+    for seed in (1, 0.5, -3.0):
+        oval, og = O.grad(cases.c5_embed, E, idx, V, seed=seed, dtype=np.float32)
+        for flags in (0, ffi.FLAG_NO_STATIC, ffi.FLAG_NO_FUSE):
+            val, g = Y.grad(cases.c5_embed, Y.cu(E), Y.cu(idx), Y.cu(V), seed=seed, flags=flags)
+            assert np.array_equal(U.bits(g[1].to_host()), U.bits(og[1])), (seed, flags)
+            assert np.array_equal(U.bits(g[3].to_host()), U.bits(og[3])), (seed, flags)
+            assert abs(val - float(oval)) <= 1e-5 * abs(float(oval)) + 1e-3
+
+
+def test_c4_rnn_tensor_core_modes():
+    """Tile-aligned RNN in TF32 and BF16 modes: the x[:, :, t] views (element offsets into x and
+    into its BF16 shadow), in-place C += A*B with batched loads, narrow-tile GEMMs."""
+    args = cases.c4_args(128, 128, 6)
+    f = cases.make_c4(6)
+    v64, g64 = O.grad(f, *U.to_f64(list(args)), dtype=np.float64)
+    for flags, tol in ((ffi.FLAG_GEMM_TF32, 5e-3), (ffi.FLAG_GEMM_BF16, 4e-2)):
+        val, g = Y.grad(f, *map(Y.cu, args), flags=flags)
+        assert abs(val - v64) <= tol * abs(v64), (flags, val, v64)
+        for a, b in zip(g[1:], g64[1:]):
+            a = a.to_host()
+            assert np.max(np.abs(a - b)) <= tol * np.max(np.abs(b)), (flags, np.max(np.abs(a - b)) / np.max(np.abs(b)))
