@@ -142,6 +142,41 @@ def test_planner_never_materialises_pullback_temporaries(built):
     assert "region[exp,mul,sub]+sum" in desc, desc  # exp.(logp) is recomputed inside the dz pass, not stored
 
 
+def test_planner_c3_epilogues_and_k_major_shadows(built):
+    """C3 in TF32 mode: bias+tanh and tanh'*delta+db run as GEMM epilogues (their region steps are
+    absorbed), and those epilogues write the transposed copies the dW GEMMs read K-major; in BF16
+    mode they write the BF16 operand shadows."""
+    av = [A((4096, 4096))] * 8 + [A((4096,))] * 8 + [A((4096, 8192))] * 2
+    desc, (steps, launches, ws, regions, _) = _plan(cases.make_c3(8, 8192), *av, flags=ffi.FLAG_GEMM_TF32)
+    assert desc.count("matmul + epilogue{region[add,tanh]}") == 7 and desc.count("+sum} ->") == 7, desc
+    assert desc.count("(absorbed into step") == 15
+    assert desc.count("[K-major AB]") == 6 and desc.count("[K-major B]") == 1 and desc.count("[K-major A]") == 1, desc
+    assert launches == steps - 15  # absorbed regions launch nothing
+    desc16, _ = _plan(cases.make_c3(8, 8192), *av, flags=ffi.FLAG_GEMM_BF16)
+    assert desc16.count("+bf16") == 14 and "K-major" not in desc16, desc16
+    plain, (steps_p, *_r) = _plan(cases.make_c3(8, 8192), *av, flags=0)  # strict FP32: no tensor-core fusions
+    assert "epilogue" not in plain and steps_p == steps
+
+
+def test_planner_c5_gathers_in_the_region_and_scales_in_the_fold(built):
+    """C5: E[:, idx] is never materialised (the region gathers), nor is seed .* V (the fold scales
+    on load): one fused pass + the scatter-add, and an arena of partials only."""
+    av = [A((256, 1 << 20)), A((1 << 22,), "i64"), A((256, 1 << 22))]
+    desc, (steps, launches, ws, regions, _) = _plan(cases.c5_embed, *av)
+    assert "(gathered inside step" in desc and " gather " in desc and regions == 1, desc
+    assert "region[mul,copy,mul]+sum" in desc  # dG = seed .* V is gone from the region
+    assert ws < 128 << 20, ws  # was 2 x 4 GiB of temporaries
+    unf, (_s, _l, ws_u, *_r) = _plan(cases.c5_embed, *av, flags=ffi.FLAG_NO_FUSE)
+    assert ": getindex ->" in unf and ws_u > 8 << 30
+
+
+def test_planner_c4_slices_are_views_and_accumulation_is_in_place(built):
+    av = [A((1024, 1024)), A((1024, 1024)), A((1024,)), A((1024, 128, 16))]
+    desc, _ = _plan(cases.make_c4(16), *av)
+    assert ": getindex ->" not in desc, "x[:, :, t] must be a view, not a copy"
+    assert desc.count("(+= in place)") >= 3 * 15 - 2 and "slice += in place" in desc, desc
+
+
 def test_build_rejects_unsupported_and_bad_programs(built):
     lib = ffi.lib()
     ctx = C.c_void_p()

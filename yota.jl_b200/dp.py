@@ -91,7 +91,15 @@ def symmetric_outputs(compiled, slots, ctx=None):
         offs[s] = total
         total += (nbytes + 255) & ~255
     base = C.c_void_p()
-    ffi.check(ffi.lib().yota_comm_symm_alloc(ctx.h, total, C.byref(base)))
+    try:
+        ffi.check(ffi.lib().yota_comm_symm_alloc(ctx.h, total, C.byref(base)))
+    except ffi.YotaError as e:
+        # no symmetric windows on this communicator (the call is collective, so every rank lands
+        # here): the outputs stay ordinary allocations and are reduced by ncclAllReduce
+        import sys
+        if rank == 0:
+            print(f"yota_b200.dp: symmetric memory unavailable ({e}); using ncclAllReduce", file=sys.stderr)
+        return {}, None
     ffi.check(ffi.lib().yota_memset(ctx.h, base, 0, total))
     return {s: B200Array(compiled._out_dims[s], "f32", ctx, ptr=base.value + offs[s], owner=False) for s in slots}, base
 

@@ -83,6 +83,8 @@ mutable struct B200Array{T,N} <: AbstractArray{T,N}
         finalizer(x -> ccall((:yota_free, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), context().h, x.ptr), a)
         return a
     end
+    # non-owning view of memory allocated elsewhere (symmetric memory: symmetric_array)
+    B200Array{T,N}(ptr::Ptr{Cvoid}, dims::NTuple{N,Int}) where {T,N} = new{T,N}(ptr, dims)
 end
 Base.size(a::B200Array) = a.dims
 Base.getindex(::B200Array, i...) = error("scalar indexing of a B200Array is disabled; use Array(x)")
@@ -399,5 +401,39 @@ function Yota.update!(x::B200Array{Float32}, gx::B200Array{Float32}, lr::Real=1)
                 context().h, x.ptr, gx.ptr, length(x), Float32(lr)))
     return x
 end
+
+# ---- multi-GPU: one Julia process per GPU (INTEGRATION.md) ---------------------------------
+"Create the communicator of this process' context from a 128-byte id made on rank 0 (`comm_unique_id`)."
+function comm_unique_id()
+    id = zeros(UInt8, 128)
+    check(ccall((:yota_comm_unique_id, LIB), Cint, (Ptr{UInt8},), id))
+    return id
+end
+comm_init(rank::Integer, nranks::Integer, id::Vector{UInt8}) =
+    check(ccall((:yota_comm_init, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), context().h, rank, nranks, id))
+
+"""
+    symmetric_array(T, dims...)
+
+Collective: an output array in symmetric memory (same call, same sizes, same order on every
+rank).  Arrays allocated this way and marked with `set_allreduce!` are reduced by the library's
+own NVSwitch kernel instead of `ncclAllReduce`.  Falls back to an ordinary `B200Array` when
+symmetric memory is unavailable.
+"""
+function symmetric_array(::Type{Float32}, dims::Integer...)
+    ctx = context()
+    if ccall((:yota_comm_symm_available, LIB), Cint, (Ptr{Cvoid},), ctx.h) == 0
+        return B200Array{Float32,length(dims)}(Tuple(Int.(dims)))
+    end
+    p = Ref{Ptr{Cvoid}}()
+    check(ccall((:yota_comm_symm_alloc, LIB), Cint, (Ptr{Cvoid}, Csize_t, Ptr{Ptr{Cvoid}}), ctx.h, 4 * prod(dims), p))
+    a = B200Array{Float32,length(dims)}(p[], Tuple(Int.(dims)))   # non-owning constructor: freed with yota_comm_symm_free
+    finalizer(x -> ccall((:yota_comm_symm_free, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), ctx.h, x.ptr), a)
+    return a
+end
+
+"Mark program outputs (0-based out slots) whose buffers are summed over ranks inside every run."
+set_allreduce!(prog::Ptr{Cvoid}, slots::Vector{Int32}) =
+    check(ccall((:yota_program_set_allreduce, LIB), Cint, (Ptr{Cvoid}, Ptr{Int32}, Int64), prog, slots, length(slots)))
 
 end # module
