@@ -74,12 +74,6 @@ static int nccl_load() {
     if (_r != 0) YOTA_FAIL(YOTA_E_NCCL, "NCCL error at %s:%d: %s", __FILE__, __LINE__, g_nccl.GetErrorString(_r)); \
   } while (0)
 
-int comm_allreduce(yota_ctx* ctx, float* buf, long long n, cudaStream_t s) {
-  if (!ctx->nccl_comm) YOTA_FAIL(YOTA_E_NCCL, "yota_comm_init has not been called");
-  if (n == 0) return YOTA_OK;
-  YOTA_NCCL(g_nccl.AllReduce(buf, buf, (size_t)n, ncclFloat32, ncclSum, (ncclComm_t)ctx->nccl_comm, s));
-  return YOTA_OK;
-}
 static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v && *v ? atoi(v) : dflt;
@@ -116,18 +110,6 @@ int comm_allreduce_bucket(yota_ctx* ctx, float* const* bufs, const long long* nu
       YOTA_NCCL(g_nccl.AllReduce(nb[i], nb[i], (size_t)nn[i], ncclFloat32, ncclSum, (ncclComm_t)ctx->nccl_comm, s));
     YOTA_NCCL(g_nccl.GroupEnd());
   }
-  return YOTA_OK;
-}
-
-int comm_group_start(yota_ctx* ctx) {
-  (void)ctx;
-  YOTA_TRY(nccl_load());
-  YOTA_NCCL(g_nccl.GroupStart());
-  return YOTA_OK;
-}
-int comm_group_end(yota_ctx* ctx) {
-  (void)ctx;
-  YOTA_NCCL(g_nccl.GroupEnd());
   return YOTA_OK;
 }
 

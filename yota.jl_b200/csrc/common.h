@@ -217,9 +217,6 @@ int launch_copy_strided(float* dst, const float* src, int nd, const long long* d
 int launch_axpy(float* x, const float* g, long long n, float lr, cudaStream_t s);
 
 // ---- NCCL (comm.cu) ---------------------------------------------------------------------
-int comm_allreduce(yota_ctx* ctx, float* buf, long long n, cudaStream_t s);
-int comm_group_start(yota_ctx* ctx);
-int comm_group_end(yota_ctx* ctx);
 int comm_reserved_sms(yota_ctx* ctx);
 // all-reduce (sum) of a bucket of buffers: the NVSwitch multimem kernel for buffers in symmetric
 // memory, one grouped ncclAllReduce launch for the others

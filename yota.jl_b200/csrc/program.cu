@@ -1811,6 +1811,10 @@ struct Timeline {
 static int run_all_steps(yota_program& P, cudaStream_t s, bool with_comm, Timeline* tl = nullptr) {
   // which step last writes each all-reduced output
   std::vector<std::vector<int>> ar_at(P.steps.size());
+  struct ReserveGuard {  // the SM reservation never outlives this sweep, error paths included
+    yota_ctx* c;
+    ~ReserveGuard() { c->sm_reserved = 0; }
+  } guard{P.ctx};
   P.ctx->sm_reserved = 0;
   if (with_comm) {
     for (int slot : P.allreduce_slots) {
