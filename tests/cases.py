@@ -173,3 +173,24 @@ def c5_args(rows=256, n_table=1 << 20, n_idx=1 << 22, seed=5, zipf=False):
         idx = r.integers(1, n_table + 1, size=n_idx).astype(np.int64)
     V = r.standard_normal((rows, n_idx), dtype=f)
     return (np.asfortranarray(E), idx, np.asfortranarray(V))
+
+
+# ---- the reference's end-to-end fixtures (test/test_examples.jl) ------------------------
+def linear2_loss(W, b, X, y):  # test/test_examples.jl:44, the Linear2 struct flattened to (W, b)
+    return jl.mean((W @ X + b - y) ** 2.0)
+
+
+def linreg_data(n=1000, d=10, seed=1):  # test/test_examples.jl:14-24
+    r = rng(seed)
+    X = r.standard_normal((n, d))
+    b = r.standard_normal(d)
+    Yv = X @ b + 0.1 * r.standard_normal(n)
+    return Yv, X, r.standard_normal(d)
+
+
+def linreg2_data(n_vars=10, n_out=2, n_obs=1000, seed=2):  # test/test_examples.jl:48-56
+    r = rng(seed)
+    X = r.standard_normal((n_vars, n_obs))
+    W_true, b_true = r.random((n_out, n_vars)), r.random(n_out)
+    Yv = W_true @ X + b_true[:, None] + 0.1 * r.standard_normal((n_out, n_obs))
+    return X, Yv, W_true, b_true, r.random((n_out, n_vars)), r.random(n_out)

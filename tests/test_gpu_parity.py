@@ -234,3 +234,23 @@ def test_c4_rnn_tensor_core_modes():
         for a, b in zip(g[1:], g64[1:]):
             a = a.to_host()
             assert np.max(np.abs(a - b)) <= tol * np.max(np.abs(b)), (flags, np.max(np.abs(a - b)) / np.max(np.abs(b)))
+
+
+def test_examples_converge_on_device():
+    """The reference's end-to-end fixtures through the device path (test/test_examples.jl:12-36,
+    46-70): 100 warm grad() calls from GRAD_CACHE + update! on device arrays."""
+    Yv, X, theta = (a.astype(F32) for a in cases.linreg_data())
+    dY, dX, dth = Y.cu(Yv), Y.cu(X), Y.cu(theta)
+    first, _ = Y.grad(cases.linreg_obj, dY, dX, dth)
+    last = first
+    for _ in range(100):
+        last, g = Y.grad(cases.linreg_obj, dY, dX, dth)
+        Y.update(dth, g[3], 0.01)
+    assert last < first / 10
+    X, Yv, W_true, b_true, W, b = (a.astype(F32) for a in cases.linreg2_data())
+    dW, db, dX, dYv = Y.cu(W), Y.cu(b), Y.cu(X), Y.cu(Yv)
+    for _ in range(100):
+        _, g = Y.grad(cases.linear2_loss, dW, db, dX, dYv)
+        Y.update(dW, g[1], 0.1)
+        Y.update(db, g[2], 0.1)
+    assert np.allclose(dW.to_host(), W_true, atol=0.1) and np.allclose(db.to_host(), b_true, atol=0.1)

@@ -131,3 +131,20 @@ def test_c_scatter_matches_numpy_fold():
     # -0.0 contributions: 0.0f + (-0.0f) = +0.0f
     z = c_oracle.scatter_add_cols(np.full((1, 1), -0.0, np.float32), [1], 1)
     assert not np.signbit(z[0, 0])
+
+
+def test_examples_converge():
+    """test/test_examples.jl:12-36 (loss drops >= 10x in 100 gradient steps) and :46-70 (W, b
+    recovered to atol 0.1 with the update! rule x - 0.1 gx), on the oracle."""
+    Yv, X, theta = cases.linreg_data()
+    first, _ = O.grad(cases.linreg_obj, Yv, X, theta)
+    last = first
+    for _ in range(100):
+        last, g = O.grad(cases.linreg_obj, Yv, X, theta)
+        theta = theta - 0.01 * g[3]
+    assert last < first / 10
+    X, Yv, W_true, b_true, W, b = cases.linreg2_data()
+    for _ in range(100):
+        _, g = O.grad(cases.linear2_loss, W, b, X, Yv)
+        W, b = W - 0.1 * g[1], b - 0.1 * g[2]
+    assert np.allclose(W, W_true, atol=0.1) and np.allclose(b, b_true, atol=0.1)
