@@ -120,6 +120,12 @@ def run_reference(a):
     from oracle import yota_oracle as O
 
     cores = os.cpu_count() or 1
+    blas = None
+    try:  # BLAS library and thread count actually in use (north_star: state both)
+        from threadpoolctl import threadpool_info
+        blas = [{"lib": i.get("internal_api"), "threads": i.get("num_threads")} for i in threadpool_info() if i.get("user_api") == "blas"]
+    except Exception:
+        pass
     wl = workload(a.workload, 0, 1, a.small)
     scale = 1.0
     sample = "full workload"
@@ -148,7 +154,7 @@ def run_reference(a):
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["label"], "note": "restated reference CPU path (NumPy/OpenBLAS oracle), not Julia"},
-            "cpu_baseline": {"value": val, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "evals/s", "cores": cores, "blas": blas, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
