@@ -161,6 +161,10 @@ int yota_host_free(yota_ctx* ctx, void* hptr);
 /* Asynchronous upload on the context's COPY stream (overlaps yota_program_run on the compute
  * stream).  Order the two streams with yota_stream_fence. */
 int yota_h2d_async(yota_ctx* ctx, void* dst_dev, const void* src_pinned, size_t bytes);
+/* Device -> pinned host copy on the compute stream, ordered after the runs issued before it; the
+ * value is valid after yota_sync (or any later synchronous call).  Reads a step's loss without
+ * stalling the host before it has enqueued the next step. */
+int yota_d2h_async(yota_ctx* ctx, void* dst_pinned, const void* src_dev, size_t bytes);
 /* Make stream `to` wait for everything enqueued so far on stream `from`
  * (0 = compute stream, 1 = copy stream). */
 int yota_stream_fence(yota_ctx* ctx, int from, int to);

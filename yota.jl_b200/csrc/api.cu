@@ -159,6 +159,13 @@ int yota_d2h(yota_ctx* ctx, void* dst, const void* src, size_t bytes) {
   return YOTA_OK;
 }
 
+int yota_d2h_async(yota_ctx* ctx, void* dst_pinned, const void* src, size_t bytes) {
+  if (!ctx) YOTA_FAIL(YOTA_E_ARG, "null ctx");
+  YOTA_TRY(ctx_ensure_device(ctx));
+  YOTA_CUDA(cudaMemcpyAsync(dst_pinned, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return YOTA_OK;
+}
+
 int yota_host_alloc(yota_ctx* ctx, size_t bytes, void** hptr) {
   if (!ctx || !hptr) YOTA_FAIL(YOTA_E_ARG, "yota_host_alloc: bad arguments");
   YOTA_TRY(ctx_ensure_device(ctx));

@@ -46,6 +46,7 @@ SYMBOLS = {
     "yota_host_alloc": (_i, [_vp, _sz, _pp]),
     "yota_host_free": (_i, [_vp, _vp]),
     "yota_h2d_async": (_i, [_vp, _vp, _vp, _sz]),
+    "yota_d2h_async": (_i, [_vp, _vp, _vp, _sz]),
     "yota_stream_fence": (_i, [_vp, _i, _i]),
     "yota_memset": (_i, [_vp, _vp, _i, _sz]),
     "yota_sync": (_i, [_vp]),
