@@ -237,6 +237,12 @@ int yota_comm_destroy(yota_ctx* ctx);
  * last writes it has been issued (overlaps the rest of the pullback sweep). */
 int yota_program_set_allreduce(yota_program* p, const int32_t* out_slots, int64_t n);
 int yota_allreduce_f32(yota_ctx* ctx, float* buf, int64_t n);
+/* update! folded into the run (src/update.jl:42-49, fn = (x, gx) -> x .- lr .* gx): after the
+ * sweep -- and after the all-reduce of the gradient, if it is marked -- the array bound to input
+ * slot in_slots[i] is updated in place from the gradient in output slot out_slots[i].  One eval
+ * then is one training step; n = 0 clears the marks. */
+int yota_program_set_update(yota_program* p, const int32_t* in_slots, const int32_t* out_slots,
+                            int64_t n, float lr);
 /* Symmetric memory for buffers that are all-reduced: collective (every rank calls it with the
  * same size, in the same order, after yota_comm_init).  Buffers carved from it are reduced by
  * the library's own NVSwitch kernel (multimem.ld_reduce / multimem.st over NCCL symmetric

@@ -254,3 +254,24 @@ def test_examples_converge_on_device():
         Y.update(dW, g[1], 0.1)
         Y.update(db, g[2], 0.1)
     assert np.allclose(dW.to_host(), W_true, atol=0.1) and np.allclose(db.to_host(), b_true, atol=0.1)
+
+
+def test_update_folded_into_the_run():
+    """yota_program_set_update: update!(x, gx, (x, g) -> x .- lr .* g) (src/update.jl:42-49) applied
+    inside the program run -- one eval is one training step; bitwise the host formula."""
+    r = cases.rng(12)
+    W, b, x = r.random((4, 3)).astype(F32), r.random(4).astype(F32), r.random((3, 5)).astype(F32)
+    dW, db, dx = Y.cu(W), Y.cu(b), Y.cu(x)
+    gf = Y.CompiledGrad(Y.gradtape(cases.loss_tanh, dW, db, dx))
+    gf.set_update([0, 1], lr=0.25)
+    lr = F32(0.25)
+    for _ in range(3):  # eager run, captured run, graph replay
+        val, g = gf.run([dW, db, dx])
+        gW, gb = g[0].to_host(), g[1].to_host()
+        _, og = O.grad(cases.loss_tanh, W, b, x, dtype=np.float32)
+        assert np.allclose(gW, og[1], rtol=1e-5, atol=1e-6) and np.allclose(gb, og[2], rtol=1e-5, atol=1e-6)
+        W, b = W - lr * gW, b - lr * gb
+        assert np.array_equal(U.bits(dW.to_host()), U.bits(W)) and np.array_equal(U.bits(db.to_host()), U.bits(b))
+    gf.set_update([], lr=1.0)
+    gf.run([dW, db, dx])
+    assert np.array_equal(U.bits(dW.to_host()), U.bits(W))  # marks cleared: parameters untouched

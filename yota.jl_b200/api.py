@@ -160,6 +160,20 @@ class CompiledGrad:
         labels = names.value.decode().split("\n")
         return [(labels[i] if i < len(labels) else "?", rec[3 * i], rec[3 * i + 1], rec[3 * i + 2]) for i in range(n)]
 
+    def set_update(self, arg_indices, lr=1.0):
+        """Fold update!(arg, grad) into every run for these argument positions (0-based):
+        arg .= arg .- lr .* grad after the sweep (and after the all-reduce, if marked)."""
+        ins = [self.low.arg_slots[i] for i in arg_indices]
+        outs = []
+        for i in arg_indices:
+            g = self.low.grads[i]
+            if not (isinstance(g, tuple) and g[0] == "out"):
+                raise ValueError(f"argument {i} has no array gradient")
+            outs.append(g[1])
+        a = (C.c_int32 * max(1, len(ins)))(*ins)
+        b = (C.c_int32 * max(1, len(outs)))(*outs)
+        ffi.check(ffi.lib().yota_program_set_update(self.h, a, b, len(ins), float(lr)))
+
     def set_allreduce(self, out_slots):
         arr = (C.c_int32 * max(1, len(out_slots)))(*out_slots)
         ffi.check(ffi.lib().yota_program_set_allreduce(self.h, arr, len(out_slots)))

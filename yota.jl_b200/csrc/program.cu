@@ -147,6 +147,9 @@ struct yota_program {
   std::vector<Shadow> tshadows;  // transposed Float32 copies written by GEMM epilogues (TF32 mode)
   std::vector<int> allreduce_slots;
   std::vector<cudaEvent_t> ar_events;
+  // update!(x, gx) folded into the run (yota_program_set_update): param input slot, grad output slot
+  std::vector<std::pair<int, int>> updates;
+  float update_lr = 1.f;
 };
 
 namespace yota {
@@ -1884,6 +1887,17 @@ static int run_all_steps(yota_program& P, cudaStream_t s, bool with_comm, Timeli
     YOTA_CUDA(cudaEventRecord(P.ar_events[ev], P.ctx->comm_stream));
     YOTA_CUDA(cudaStreamWaitEvent(s, P.ar_events[ev], 0));
   }
+  // update!(param, grad) for the marked pairs: after every reader of the parameter in this sweep
+  // and after its gradient has been summed over ranks (src/update.jl:42-49, x .= x .- lr .* gx)
+  for (auto& u : P.updates) {
+    long long n = 0;
+    for (auto& t : P.T)
+      if (t.d.kind == YOTA_T_OUTPUT && t.d.slot == u.second) n = t.numel;
+    if (tl) YOTA_TRY(tl->open("update! input " + std::to_string(u.first), s));
+    YOTA_TRY(launch_axpy(static_cast<float*>(P.bound_in[u.first]), static_cast<const float*>(P.bound_out[u.second]), n,
+                         P.update_lr, s));
+    if (tl) YOTA_TRY(tl->close(s));
+  }
   return YOTA_OK;
 }
 
@@ -1929,7 +1943,18 @@ extern "C" int yota_program_run(yota_program* p, void* const* in_ptrs, int64_t n
   YOTA_TRY(set_seed(P, seed));
   cudaStream_t s = P.ctx->stream;
   const bool with_comm = !P.allreduce_slots.empty() && P.ctx->nccl_comm;
-  const bool use_graph = !(P.flags & YOTA_FLAG_NO_GRAPH) && !with_comm;
+  // With reductions in the sweep the run is issued eagerly.  Experimental (YOTA_GRAPH_COMM=1, not
+  // yet validated on hardware): when every reduced output lives in symmetric memory the
+  // reductions are the library's own kernels and the two-stream sweep can be captured as well.
+  bool graph_comm = with_comm && getenv("YOTA_GRAPH_COMM") != nullptr;
+  if (graph_comm)
+    for (int slot : P.allreduce_slots) {
+      long long n = 0;
+      for (auto& t : P.T)
+        if (t.d.kind == YOTA_T_OUTPUT && t.d.slot == slot) n = t.numel;
+      graph_comm = graph_comm && symm_contains(P.ctx, P.bound_out[slot], (size_t)n * 4);
+    }
+  const bool use_graph = !(P.flags & YOTA_FLAG_NO_GRAPH) && (!with_comm || graph_comm);
   (void)changed;
   if (!use_graph) return run_all_steps(P, s, with_comm);
   // one graph per pointer binding: eager on the first run with a binding (also the warm-up
@@ -1951,11 +1976,11 @@ extern "C" int yota_program_run(yota_program* p, void* const* in_ptrs, int64_t n
     ge->out = P.bound_out;
   }
   ge->last_use = ++P.run_counter;
-  if (++ge->runs == 1) return run_all_steps(P, s, false);
+  if (++ge->runs == 1) return run_all_steps(P, s, with_comm);
   if (!ge->exec) {
     cudaGraph_t g = nullptr;
     YOTA_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-    const int st = run_all_steps(P, s, false);
+    const int st = run_all_steps(P, s, with_comm);
     cudaError_t e = cudaStreamEndCapture(s, &g);
     if (st != YOTA_OK) {
       if (g) cudaGraphDestroy(g);
@@ -2068,6 +2093,30 @@ extern "C" int yota_program_timeline(yota_program* p, void* const* in_ptrs, int6
   }
   if (st != YOTA_OK) return st;
   return (int)std::min<int64_t>(n, cap_recs);
+}
+
+extern "C" int yota_program_set_update(yota_program* p, const int32_t* in_slots, const int32_t* out_slots, int64_t n,
+                                       float lr) {
+  if (!p || n < 0 || (n > 0 && (!in_slots || !out_slots))) YOTA_FAIL(YOTA_E_ARG, "yota_program_set_update: bad arguments");
+  std::vector<std::pair<int, int>> ups;
+  for (int64_t i = 0; i < n; i++) {
+    const int a = in_slots[i], b = out_slots[i];
+    if (a < 0 || a >= p->n_in || b < 0 || b >= p->n_out) YOTA_FAIL(YOTA_E_ARG, "yota_program_set_update: bad slot");
+    long long na = -1, nb = -2;
+    for (auto& t : p->T) {
+      if (t.d.kind == YOTA_T_INPUT && t.d.slot == a && t.d.dtype == YOTA_F32) na = t.numel;
+      if (t.d.kind == YOTA_T_OUTPUT && t.d.slot == b) nb = t.numel;
+    }
+    if (na != nb)
+      YOTA_FAIL(YOTA_E_SHAPE, "yota_program_set_update: input %d and output %d are not Float32 arrays of one size", a, b);
+    ups.push_back({a, b});
+  }
+  p->updates = ups;
+  p->update_lr = lr;
+  for (auto& g : p->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  p->graphs.clear();
+  return YOTA_OK;
 }
 
 extern "C" int yota_program_set_allreduce(yota_program* p, const int32_t* out_slots, int64_t n) {

@@ -70,6 +70,7 @@ SYMBOLS = {
     "yota_comm_destroy": (_i, [_vp]),
     "yota_program_set_allreduce": (_i, [_vp, C.POINTER(C.c_int32), _i64]),
     "yota_allreduce_f32": (_i, [_vp, _vp, _i64]),
+    "yota_program_set_update": (_i, [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _i64, _f]),
     "yota_comm_symm_available": (_i, [_vp]),
     "yota_comm_symm_alloc": (_i, [_vp, _sz, _pp]),
     "yota_comm_symm_free": (_i, [_vp, _vp]),
