@@ -275,3 +275,15 @@ def test_update_folded_into_the_run():
     gf.set_update([], lr=1.0)
     gf.run([dW, db, dx])
     assert np.array_equal(U.bits(dW.to_host()), U.bits(W))  # marks cleared: parameters untouched
+
+
+@pytest.mark.parametrize("seed", range(0, 60, 2))
+def test_random_programs_on_device(seed):
+    """The random loss functions of tests/test_fuzz_host.py through the device path against the
+    oracle (Float32 and Float64, the SURVEY §8(d) gate): exercises the region interpreter on
+    chains that have no ahead-of-time kernel, gather operands, slice views, small GEMMs,
+    in-place accumulation and the unbroadcast sinks in combinations no hand-written case has."""
+    import test_fuzz_host as Fz
+
+    args = [a.astype(F32) if a.dtype.kind == "f" else a for a in Fz._args(seed)]
+    U.check_parity(Fz.make_loss(seed), args, rtol=2e-5)
