@@ -81,3 +81,66 @@ def test_random_programs_plan_under_every_configuration(seed):
         assert st[1].value <= st[0].value * 8 and st[2].value >= 0
         lib.yota_program_destroy(h)
     lib.yota_shutdown(ctx)
+
+
+# ---- a wider vocabulary (CPU only: lowering + planner) ---------------------------------------
+def make_loss_wide(seed):
+    plan = np.random.default_rng(7000 + seed)
+    steps = [(int(plan.integers(0, 12)), int(plan.integers(0, 1 << 30))) for _ in range(int(plan.integers(3, 9)))]
+    tail = int(plan.integers(0, 5))
+
+    def loss(W, x, b, idx):
+        vals = [x]
+        for kind, salt in steps:
+            v = vals[salt % len(vals)]
+            u = vals[(salt >> 8) % len(vals)]
+            if kind == 0:
+                vals.append(UNARY[salt % len(UNARY)](v))
+            elif kind == 1 and v.shape[0] == W.shape[1]:
+                vals.append(W @ v)
+            elif kind == 2 and v.shape[0] == b.shape[0]:
+                vals.append(v + b if salt & 1 else v * b)
+            elif kind == 3 and v.shape == u.shape:
+                vals.append(v * u if salt & 1 else v + u)
+            elif kind == 4:
+                vals.append(v[jl.colon, idx])
+            elif kind == 5 and v.shape[1] >= 2:
+                vals.append(v[jl.colon, jl.range_(1, 2)])
+            elif kind == 6 and v.shape[0] == u.shape[0]:
+                vals.append(jl.hcat(v, u))
+            elif kind == 7 and v.shape[1] == u.shape[1] and v.shape[0] + u.shape[0] <= 12:
+                vals.append(jl.vcat(v, u))
+            elif kind == 8:
+                vals.append(jl.logsoftmax(v))
+            elif kind == 9 and v.shape[0] == v.shape[1]:
+                vals.append(jl.transpose(v) + v)
+            elif kind == 10:
+                vals.append(v / (u * u + 1.5) if v.shape == u.shape else v / 2.0)
+            else:
+                vals.append(jl.sqrt(v * v + 1.0))
+        out = vals[-1]
+        if tail == 0:
+            return jl.sum(out)
+        if tail == 1:
+            return jl.mean(out ** 2.0)
+        if tail == 2:
+            return jl.sum(jl.mean(out, dims=1))
+        if tail == 3:
+            return jl.sum(out[1, jl.colon]) + jl.sum(out[jl.colon, 1] ** 2)
+        return jl.sum(out * out) + jl.sum(vals[len(vals) // 2])
+
+    return loss
+
+
+@pytest.mark.parametrize("seed", range(80))
+def test_random_programs_wide_vocabulary(seed):
+    L = _lowered_vs_oracle(make_loss_wide(seed), _args(seed), rtol=1e-9)
+    lib = ffi.lib()
+    ctx = C.c_void_p()
+    ffi.check(lib.yota_init(0, C.byref(ctx)))
+    ops, tens = ffi.pack_program(L.prog)
+    for flags in (0, ffi.FLAG_NO_FUSE, ffi.FLAG_GEMM_TF32):
+        h = C.c_void_p()
+        ffi.check(lib.yota_program_build(ctx, ops, len(L.prog.ops), tens, len(L.prog.tensors), flags, C.byref(h)))
+        lib.yota_program_destroy(h)
+    lib.yota_shutdown(ctx)
