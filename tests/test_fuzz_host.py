@@ -144,3 +144,33 @@ def test_random_programs_wide_vocabulary(seed):
         ffi.check(lib.yota_program_build(ctx, ops, len(L.prog.ops), tens, len(L.prog.tensors), flags, C.byref(h)))
         lib.yota_program_destroy(h)
     lib.yota_shutdown(ctx)
+
+
+@pytest.mark.parametrize("seed", range(120))
+def test_random_programs_plan_at_tile_aligned_shapes(seed):
+    """Plan-only (abstract arrays, no data): the same random programs at shapes where the
+    tensor-core GEMMs, their fused epilogues, the K-major / BF16 shadows and the vectorised
+    regions are all eligible -- the planner must produce a program under every flag."""
+    R, Cc = 256, 512
+    av = [Y.AVal((R, R)), Y.AVal((R, Cc)), Y.AVal((R,)), Y.AVal((640,), "i64")]
+    f = make_loss(seed) if seed % 2 else make_loss_wide(seed)
+    try:
+        L = lower(Y.gradtape(f, *av))
+    except Exception as e:  # shape-dependent branches of the generator (vcat limits) may not apply
+        pytest.skip(f"generator: {e}")
+    lib = ffi.lib()
+    ctx = C.c_void_p()
+    ffi.check(lib.yota_init(0, C.byref(ctx)))
+    ops, tens = ffi.pack_program(L.prog)
+    descs = {}
+    for flags in (0, ffi.FLAG_NO_FUSE, ffi.FLAG_NO_STATIC, ffi.FLAG_GEMM_TF32, ffi.FLAG_GEMM_BF16,
+                  ffi.FLAG_GEMM_TF32 | ffi.FLAG_NO_FUSE):
+        h = C.c_void_p()
+        ffi.check(lib.yota_program_build(ctx, ops, len(L.prog.ops), tens, len(L.prog.tensors), flags, C.byref(h)))
+        n = lib.yota_program_describe(h, None, 0)
+        buf = C.create_string_buffer(n + 1)
+        lib.yota_program_describe(h, buf, n + 1)
+        descs[flags] = buf.value.decode()
+        lib.yota_program_destroy(h)
+    lib.yota_shutdown(ctx)
+    assert descs[0].count("step ") <= descs[ffi.FLAG_NO_FUSE].count("step "), "fusion never adds steps"

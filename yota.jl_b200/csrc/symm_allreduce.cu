@@ -7,9 +7,9 @@
 //   4. meets the others again so that nobody leaves while stores to it are in flight.
 // Per GPU and direction that is ~1.125 x the bucket over NVLink -- the floor for an all-reduce
 // through an NVLS switch -- with a fixed, small CTA count that the persistent GEMM grids leave
-// free (yota_ctx::sm_reserved), so the reductions run beside the pullback sweep.  Without
-// multicast support (or on 2 ranks where NCCL creates no multicast team) the same kernel reads
-// the n copies through peer pointers in rank order and stores to every peer.
+// free (yota_ctx::sm_reserved), so the reductions run beside the pullback sweep.  Without a
+// multicast team on the communicator the same kernel reads the n copies through peer pointers
+// in rank order and stores to every peer (on this pool 2, 4 and 8 ranks all get multicast).
 //
 // The buffers must live in symmetric memory (yota_comm_symm_alloc: ncclMemAlloc +
 // ncclCommWindowRegister(NCCL_WIN_COLL_SYMMETRIC)); NCCL 2.28's device API supplies the
