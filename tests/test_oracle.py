@@ -148,3 +148,14 @@ def test_examples_converge():
         _, g = O.grad(cases.linear2_loss, W, b, X, Yv)
         W, b = W - 0.1 * g[1], b - 0.1 * g[2]
     assert np.allclose(W, W_true, atol=0.1) and np.allclose(b, b_true, atol=0.1)
+
+
+def test_broadcast_pullback_equals_elementwise_pullbacks():
+    """test/test_rulesets.jl:21-36: the pullback of the broadcast rule applied to ones equals the
+    per-element scalar pullbacks applied to 1.0 (sin: cos(x_i)), exactly."""
+    xs = cases.rng(3).random(2)
+    _, g = O.grad(lambda x: jl.sum(jl.sin(x)), xs, dtype=np.float64)
+    assert np.array_equal(g[1], np.cos(xs))
+    inc = lambda x: jl.sum(jl.sin(x) + 1.0)  # noqa: E731  (sin_inc, :13)
+    _, g = O.grad(inc, xs, dtype=np.float64)
+    assert np.array_equal(g[1], np.cos(xs))
