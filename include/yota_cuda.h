@@ -138,6 +138,9 @@ typedef struct yota_op_desc {
 #define YOTA_FLAG_GEMM_TF32 0x10u /* tcgen05 kind::tf32 tensor-core contractions, FP32 accum    */
 #define YOTA_FLAG_GEMM_BF16 0x20u /* tcgen05 kind::f16 (BF16 operands), FP32 accum              */
 #define YOTA_FLAG_NO_STATIC 0x40u /* never pick a precompiled chain kernel (interpreter only)   */
+#define YOTA_FLAG_GEMM_TF32X3 0x80u /* compensated tensor-core contractions: operands split into
+                                     tf32 hi + lo, three tcgen05 MMAs per k-step (hi*hi + hi*lo +
+                                     lo*hi) into one FP32 accumulator; meets the rtol 1e-5 gate   */
 
 typedef struct yota_ctx yota_ctx;
 typedef struct yota_program yota_program;
@@ -213,7 +216,7 @@ int yota_program_timeline(yota_program* p, void* const* in_ptrs, int64_t n_in,
 
 /* ---- standalone operators (same kernels the program uses; unit-test / glue entry) ------ */
 /* C[m x n] = op(A) op(B) (+ C if accumulate), column-major, lda/ldb/ldc in elements.
- * mode: 0 = strict FP32 FFMA, 1 = tcgen05 TF32, 2 = tcgen05 BF16. */
+ * mode: 0 = strict FP32 FFMA, 1 = tcgen05 TF32, 2 = tcgen05 BF16, 3 = tcgen05 3xTF32 (compensated). */
 int yota_gemm(yota_ctx* ctx, int mode, int transA, int transB, int64_t m, int64_t n, int64_t k,
               const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
               int accumulate);

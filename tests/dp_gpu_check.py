@@ -53,8 +53,12 @@ for mode, flags, tol in (("fp32", 0, 2e-5), ("tf32", ffi.FLAG_GEMM_TF32, 5e-3)):
             ctx.sync()
         check(variant, val, g)
         first = [x.to_host() for x in g[:2 * L]]
-        val, g = gf.run(dsh, out=outs)
-        ctx.sync()
+        # back to back without a sync in between: the last reductions of one eval overlap the
+        # forward sweep of the next (the run no longer joins the communication stream); the
+        # results read afterwards must be those of a fully reduced eval
+        for it in range(4):
+            val, g = gf.run(dsh, out=outs)
+        check(variant + "/back-to-back", val, g)
         for a, b in zip(first, g[:2 * L]):  # run to run, and rank to rank below: bit-identical sums
             assert variant == "nccl" or np.array_equal(a.view(np.uint32), b.to_host().view(np.uint32)), (mode, "run-to-run")
         if variant == "symmetric":

@@ -76,6 +76,68 @@ def test_c4_full_size_vs_oracle():
     U.check_parity(f, list(args), flags=0, o64=O.grad(f, *U.to_f64(list(args)), dtype=np.float64))
 
 
+@pytest.fixture(scope="module")
+def c3_oracle():
+    """The restated reference path on the FULL C3 config (8 x 4096-wide, batch 8192), once per
+    session, in Float32 (the reference's own arithmetic) and Float64 (ground truth): ~1-3 min of
+    host BLAS.  Only (val, grads) are kept."""
+    L, W, B = 8, 4096, 8192
+    args = cases.c3_args(L, W, B)
+    f = cases.make_c3(L, B)
+    v32, g32 = O.grad(f, *args, dtype=np.float32)
+    g32 = [np.asarray(g, dtype=np.float32) for g in g32[1:]]
+    v64, g64 = O.grad(f, *U.to_f64(list(args)), dtype=np.float64)
+    g64 = [np.asarray(g, dtype=np.float64) for g in g64[1:]]
+    return args, f, (float(v32), g32), (float(v64), g64)
+
+
+# mode -> (flags, how it is gated).  "gate": the reference's rtol 1e-5 (SURVEY §8(d): against the
+# Float64 truth with the Float32 oracle's own error as the floor); numbers: tolerance relative to
+# max|g| per tensor, the stated looser tolerance of the tensor-core modes.
+C3_MODES = {
+    "fp32_ffma": (0, "gate"),
+    "tf32x3": (ffi.FLAG_GEMM_TF32X3, "gate"),
+    "tf32": (ffi.FLAG_GEMM_TF32, 5e-3),
+    "bf16": (ffi.FLAG_GEMM_BF16, 3e-2),
+}
+
+
+@pytest.mark.parametrize("mode", list(C3_MODES))
+def test_c3_full_size_vs_oracle(mode, c3_oracle):
+    """THE benchmarked plan (bench.py default: 2-CTA tcgen05 GEMMs, fused bias+tanh / tanh'+db
+    epilogues, K-major shadows, CUDA graph) at the benchmarked size against the oracle: the loss
+    and all 18 gradients (8 W, 8 b, x, Y).  Three calls: eager, captured, replayed -- the replay
+    is what bench.py times."""
+    args, f, (v32, g32), (v64, g64) = c3_oracle
+    flags, how = C3_MODES[mode]
+    d = [Y.cu(a) for a in args]
+    gf = Y.CompiledGrad(Y.gradtape(f, *d), flags=flags)
+    if mode in ("tf32", "bf16", "tf32x3"):
+        desc = gf.describe()
+        assert desc.count("+ epilogue{") == 15 and "ffma" not in desc, desc
+    outs = None
+    for _ in range(3):
+        val, g = gf.run(d)
+        outs = g
+    val = float(val.to_host())
+    report = {}
+    if how == "gate":
+        report["val"] = U.gate(val, v32, v64, f"{mode}: val")
+    else:
+        assert abs(val - v64) <= how * abs(v64), (mode, val, v64)
+    for i, (a, b32, b64) in enumerate(zip(outs, g32, g64)):
+        a = a.to_host()
+        assert a.shape == b64.shape, (i, a.shape, b64.shape)
+        if how == "gate":
+            report[i] = U.gate(a, b32, b64, f"{mode}: grad[{i}]")
+        else:
+            scale = float(np.abs(b64).max())
+            err = float(np.abs(a - b64).max())
+            report[i] = err / scale
+            assert err <= how * scale, (mode, i, err / scale)
+    print(f"C3 full size, {mode}: worst err / max|g| = {max(report.values()):.3e}")
+
+
 def _c3(flags, B=8192, L=8, W=4096):
     args = cases.c3_args(L, W, B)
     return args, cases.make_c3(L, B), [Y.cu(a) for a in args]

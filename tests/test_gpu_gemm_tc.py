@@ -109,7 +109,7 @@ def force_2cta(monkeypatch):
     Y.reset()
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2, 3])
 @pytest.mark.parametrize("tA,tB", [(0, 0), (0, 1), (1, 0), (1, 1)])
 def test_2cta_exact_on_small_integers(force_2cta, mode, tA, tB):
     r = cases.rng(24)
@@ -146,3 +146,51 @@ def test_fused_epilogues_match_unfused(force_2cta, monkeypatch, flags, tol):
     v64, g64 = O.grad(f, *U.to_f64(args), dtype=np.float64)
     for a, b in zip(g1, g64[1:]):
         assert np.max(np.abs(a - b)) <= tol * np.max(np.abs(b))
+
+
+# ---- compensated 3xTF32 mode (mode 3): tensor cores at the reference's own tolerance --------
+def test_tensor_core_truncates_float32_to_tf32():
+    """The split of the compensated mode assumes the tensor core reads a Float32 as TF32 by
+    DROPPING the 13 low mantissa bits (hi = x & 0xFFFFE000, lo = x - hi is then exact).  Probe:
+    1 + 2^-11 + 2^-12 is above the rounding midpoint, so truncation gives 1, rounding 1 + 2^-10."""
+    m = n = 128
+    k = 32
+    A = np.zeros((m, k), F32, order="F")
+    A[:, 0] = F32(1.0) + F32(2.0 ** -11) + F32(2.0 ** -12)
+    B = np.zeros((k, n), F32, order="F")
+    B[0, :] = 1
+    got = U.gemm(1, 0, 0, A, B)
+    assert np.all(got == F32(1.0)), got[0, 0]
+    got3 = U.gemm(3, 0, 0, A, B)  # hi + lo restores the value exactly
+    assert np.all(got3 == A[0, 0]), (got3[0, 0], A[0, 0])
+
+
+@pytest.mark.parametrize("tA,tB", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_tf32x3_meets_the_fp32_tolerance(tA, tB):
+    """Random data at every tile width (1-CTA 128 x 32 ... 256, and the 2-CTA kernel at the last
+    shape): the error against Float64 is that of an FP32 dot product, not of TF32 -- gated at
+    4e-6 * (|A| |B|) (TF32 alone: ~1e-3), next to the strict-FP32 FFMA kernel on the same data."""
+    r = cases.rng(25)
+    for m, n, k in [(128, 128, 32), (1024, 128, 1024), (384, 640, 160), (512, 768, 1024), (2048, 2560, 512)]:
+        A = r.standard_normal((k, m) if tA else (m, k)).astype(F32)
+        B = r.standard_normal((n, k) if tB else (k, n)).astype(F32)
+        a, b = (A.T if tA else A).astype(np.float64), (B.T if tB else B).astype(np.float64)
+        ref = a @ b
+        bound = np.abs(a) @ np.abs(b)
+        got = U.gemm(3, tA, tB, np.asfortranarray(A), np.asfortranarray(B))
+        e3 = float(np.max(np.abs(got - ref) / bound))
+        ffma = U.gemm(0, tA, tB, np.asfortranarray(A), np.asfortranarray(B))
+        e0 = float(np.max(np.abs(ffma - ref) / bound))
+        assert e3 <= 4e-6, (m, n, k, e3, e0)
+        C0 = np.asfortranarray(r.standard_normal((m, n)).astype(F32))
+        got = U.gemm(3, tA, tB, np.asfortranarray(A), np.asfortranarray(B), C0)
+        assert float(np.max(np.abs(got - (ref + C0)) / (bound + np.abs(C0)))) <= 4e-6
+
+
+def test_mlp_gradients_in_tf32x3_mode(force_2cta):
+    """C3 at a tile-aligned scale through the compensated mode with fused epilogues: the FP32 gate
+    of the reference (rtol 1e-5 against Float64 with the Float32 oracle's error as floor)."""
+    f, args = cases.make_c3(4, 512), cases.c3_args(4, 256, 512)
+    gf = Y.CompiledGrad(Y.gradtape(f, *[Y.cu(a) for a in args]), flags=ffi.FLAG_GEMM_TF32X3)
+    assert "epilogue{region[add,tanh]}" in gf.describe()
+    U.check_parity(f, list(args), flags=ffi.FLAG_GEMM_TF32X3)

@@ -17,6 +17,9 @@ from yota_b200 import ffi, jl
 
 pytestmark = pytest.mark.gpu
 F32 = np.float32
+# random programs whose gate is looser than the reference's 1e-5, with the reason (filled from a
+# device run that printed every seed's worst error: see the test)
+FUZZ_RTOL = {}
 
 
 def f32(args):
@@ -286,4 +289,48 @@ def test_random_programs_on_device(seed):
     import test_fuzz_host as Fz
 
     args = [a.astype(F32) if a.dtype.kind == "f" else a for a in Fz._args(seed)]
-    U.check_parity(Fz.make_loss(seed), args, rtol=2e-5)
+    U.check_parity(Fz.make_loss(seed), args, rtol=FUZZ_RTOL.get(seed, 1e-5))
+
+
+def test_runtime_index_out_of_range_is_a_bounds_error():
+    """A run-time index vector with an entry outside 1..n: the reference throws BoundsError from
+    getindex / NNlib.scatter! (src/helpers.jl:7-11).  The device path reports it from the kernel
+    that reads the index (stand-alone gather, the fused gather operand, the scatter-add's key
+    pass) and the next synchronising call fails with YOTA_E_SHAPE -- forward and pullback alike."""
+    r = cases.rng(21)
+    E, V = r.random((8, 16)).astype(F32), r.random((8, 12)).astype(F32)
+    good = r.integers(1, 17, size=12).astype(np.int64)
+    for bad_value in (0, 17, -3, 1 << 40):
+        idx = good.copy()
+        idx[5] = bad_value
+        for f in (cases.c5_embed,  # gather fused into the region + scaled scatter-add
+                  lambda E, idx, V: jl.sum(jl.tanh(E[jl.colon, idx]) @ jl.transpose(V))):  # stand-alone gather + scatter
+            with pytest.raises(Y.YotaError, match="BoundsError") as ei:
+                _, g = Y.grad(f, Y.cu(E), Y.cu(idx), Y.cu(V))
+                g[1].to_host()
+            assert ei.value.code == -3
+    # the flag is cleared by the failing call: the next, valid call is clean
+    val, g = Y.grad(cases.c5_embed, Y.cu(E), Y.cu(good), Y.cu(V))
+    _, og = O.grad(cases.c5_embed, E, good, V)
+    assert np.array_equal(U.bits(g[1].to_host()), U.bits(og[1]))
+    # stand-alone operators of the C ABI
+    lib, ctx = ffi.lib(), Y.context()
+    dx, dy, di = Y.B200Array((8, 16)), Y.cu(V), Y.cu(np.array([1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 99], np.int64))
+    ffi.check(lib.yota_scatter_add_cols(ctx.h, dx.ptr, 8, 16, dy.ptr, di.ptr, 12))
+    with pytest.raises(Y.YotaError, match="BoundsError"):
+        ctx.sync()
+    ctx.sync()
+
+
+def test_accumulation_never_lands_in_a_view_of_a_shared_array():
+    """a matmul thunk added to x[:, :, t] of a saved activation must not be accumulated
+    in place (the view's parent is read again by the tanh pullback)."""
+    import test_host
+
+    r = cases.rng(31)
+    args = [r.random((8, 4, 3)).astype(F32), r.random((8, 8)).astype(F32), r.random((8, 4)).astype(F32)]
+    U.check_parity(test_host.alias_hazard_loss, args)
+    big = [r.random((256, 128, 3)).astype(F32) - F32(0.5), (r.random((256, 256)).astype(F32) - F32(0.5)) / 16,
+           r.random((256, 128)).astype(F32)]
+    for flags in (0, ffi.FLAG_GEMM_TF32):
+        U.check_parity(test_host.alias_hazard_loss, big, flags=flags, rtol=1e-5 if flags == 0 else 5e-3)

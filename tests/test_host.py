@@ -177,6 +177,23 @@ def test_planner_c4_slices_are_views_and_accumulation_is_in_place(built):
     assert desc.count("(+= in place)") >= 3 * 15 - 2 and "slice += in place" in desc, desc
 
 
+def alias_hazard_loss(X3, W, h):
+    """A matmul thunk added to a VIEW of a saved activation: accumulating in place would overwrite
+    H[:, :, 2], which the tanh pullback (1 - H^2) and sum(H) read later."""
+    H = jl.tanh(X3)
+    s = jl.sum(H)
+    z = (W @ h) + H[jl.colon, jl.colon, 2]
+    return jl.sum(z * z) + s
+
+
+def test_planner_never_accumulates_into_a_view_of_a_shared_array(built):
+    av = [A((8, 4, 3)), A((8, 8)), A((8, 4))]
+    desc, _ = _plan(alias_hazard_loss, *av)
+    assert "(+= in place)" not in desc, desc
+    r = cases.rng(3)
+    _lowered_vs_oracle(alias_hazard_loss, (r.random((8, 4, 3)), r.random((8, 8)), r.random((8, 4))))
+
+
 def test_build_rejects_unsupported_and_bad_programs(built):
     lib = ffi.lib()
     ctx = C.c_void_p()

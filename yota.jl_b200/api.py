@@ -24,7 +24,7 @@ from .tape import AVal, Call, Constant, Input, NoTangent, ZeroTangent
 
 GRAD_CACHE = {}
 
-_MODE_FLAGS = {"fp32": 0, "tf32": ffi.FLAG_GEMM_TF32, "bf16": ffi.FLAG_GEMM_BF16}
+_MODE_FLAGS = {"fp32": 0, "tf32": ffi.FLAG_GEMM_TF32, "bf16": ffi.FLAG_GEMM_BF16, "tf32x3": ffi.FLAG_GEMM_TF32X3}
 
 
 def default_flags():

@@ -1,6 +1,9 @@
 // C ABI: context, caller-owned device buffers, events, stand-alone operators.
 #include <stdarg.h>
 
+#include <algorithm>
+#include <string.h>
+
 #include "common.h"
 
 namespace yota {
@@ -40,8 +43,73 @@ int ctx_ensure_device(yota_ctx* ctx) {
   YOTA_CUDA(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
   YOTA_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   YOTA_CUDA(cudaEventCreateWithFlags(&ctx->fence_event, cudaEventDisableTiming));
+  YOTA_CUDA(cudaEventCreateWithFlags(&ctx->free_event, cudaEventDisableTiming));
+  YOTA_CUDA(cudaHostAlloc((void**)&ctx->err_host, 4 * sizeof(long long), cudaHostAllocMapped));
+  memset(ctx->err_host, 0, 4 * sizeof(long long));
+  YOTA_CUDA(cudaHostGetDevicePointer((void**)&ctx->err_dev, ctx->err_host, 0));
   ctx->device_ready = true;
   return YOTA_OK;
+}
+
+static bool overlaps(const yota_ctx::PendingAr& e, const char* lo, const char* hi) {
+  for (auto& r : e.ranges)
+    if (r.first < hi && lo < r.second) return true;
+  return false;
+}
+
+int ctx_wait_pending(yota_ctx* ctx, const void* ptr, size_t bytes, cudaStream_t s) {
+  if (ctx->pending_ar.empty() || !ptr) return YOTA_OK;
+  const char* lo = static_cast<const char*>(ptr);
+  for (auto& e : ctx->pending_ar)
+    if (overlaps(e, lo, lo + (bytes ? bytes : 1))) YOTA_CUDA(cudaStreamWaitEvent(s, e.ev, 0));
+  return YOTA_OK;
+}
+
+int ctx_join_comm(yota_ctx* ctx, cudaStream_t s) {
+  // the communication stream is in order: the newest event implies all older ones
+  if (!ctx->pending_ar.empty()) YOTA_CUDA(cudaStreamWaitEvent(s, ctx->pending_ar.back().ev, 0));
+  for (auto& e : ctx->pending_ar) ctx->event_pool.push_back(e.ev);
+  ctx->pending_ar.clear();
+  return YOTA_OK;
+}
+
+int ctx_add_pending(yota_ctx* ctx, const std::vector<std::pair<const char*, const char*>>& ranges) {
+  yota_ctx::PendingAr n;
+  n.ranges = ranges;
+  // an older entry over the same bytes is superseded (same stream, later event); bytes it covered
+  // beyond the new ranges ride along with the new, later event (waits longer, never too short)
+  for (size_t i = 0; i < ctx->pending_ar.size();) {
+    bool hit = false;
+    for (auto& r : ranges) hit = hit || overlaps(ctx->pending_ar[i], r.first, r.second);
+    if (!hit) {
+      i++;
+      continue;
+    }
+    for (auto& r : ctx->pending_ar[i].ranges)
+      if (std::find(n.ranges.begin(), n.ranges.end(), r) == n.ranges.end()) n.ranges.push_back(r);
+    ctx->event_pool.push_back(ctx->pending_ar[i].ev);
+    ctx->pending_ar.erase(ctx->pending_ar.begin() + i);
+  }
+  if (ctx->event_pool.empty()) {
+    cudaEvent_t e;
+    YOTA_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->event_pool.push_back(e);
+  }
+  n.ev = ctx->event_pool.back();
+  ctx->event_pool.pop_back();
+  YOTA_CUDA(cudaEventRecord(n.ev, ctx->comm_stream));
+  ctx->pending_ar.push_back(n);
+  return YOTA_OK;
+}
+
+int ctx_check_index_errors(yota_ctx* ctx) {
+  if (!ctx->err_host || !*(volatile long long*)ctx->err_host) return YOTA_OK;
+  const long long j = ctx->err_host[1], n = ctx->err_host[2];
+  memset(ctx->err_host, 0, 4 * sizeof(long long));
+  YOTA_FAIL(YOTA_E_SHAPE,
+            "BoundsError: attempt to access a dimension of extent %lld at index [%lld] (run-time index vector of a "
+            "getindex / scatter-add; the results of that run are invalid)",
+            n, j);
 }
 
 int ctx_scratch(yota_ctx* ctx, size_t bytes, void** out) {
@@ -92,6 +160,10 @@ int yota_shutdown(yota_ctx* ctx) {
     cudaStreamDestroy(ctx->comm_stream);
     cudaStreamDestroy(ctx->copy_stream);
     cudaEventDestroy(ctx->fence_event);
+    if (ctx->free_event) cudaEventDestroy(ctx->free_event);
+    for (auto& e : ctx->pending_ar) cudaEventDestroy(e.ev);
+    for (auto e : ctx->event_pool) cudaEventDestroy(e);
+    if (ctx->err_host) cudaFreeHost(ctx->err_host);
   }
   delete ctx;
   return YOTA_OK;
@@ -136,8 +208,12 @@ int yota_free(yota_ctx* ctx, void* dptr) {
   if (!ctx || !dptr) return YOTA_OK;
   auto it = ctx->live_blocks.find(dptr);
   if (it == ctx->live_blocks.end()) YOTA_FAIL(YOTA_E_ARG, "yota_free: pointer was not allocated by yota_alloc");
-  // stream-ordered reuse: every consumer runs on ctx->stream, so a recycled block is only
-  // touched after the work already queued on it
+  // stream-ordered reuse: consumers on ctx->stream touch a recycled block only after the work
+  // already queued on it; the COPY stream is ordered behind that work the next time it is used
+  // (yota_h2d_async), the communication stream always waits for the compute stream before a
+  // reduction (program.cu)
+  ctx->free_pending = true;
+  YOTA_TRY(ctx_wait_pending(ctx, dptr, it->second, ctx->stream));  // a reduction may still be writing it
   ctx->free_blocks.insert({it->second, dptr});
   ctx->live_blocks.erase(it);
   return YOTA_OK;
@@ -146,6 +222,7 @@ int yota_free(yota_ctx* ctx, void* dptr) {
 int yota_h2d(yota_ctx* ctx, void* dst, const void* src, size_t bytes) {
   if (!ctx) YOTA_FAIL(YOTA_E_ARG, "null ctx");
   YOTA_TRY(ctx_ensure_device(ctx));
+  YOTA_TRY(ctx_wait_pending(ctx, dst, bytes, ctx->stream));
   YOTA_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
   YOTA_CUDA(cudaStreamSynchronize(ctx->stream));
   return YOTA_OK;
@@ -154,14 +231,16 @@ int yota_h2d(yota_ctx* ctx, void* dst, const void* src, size_t bytes) {
 int yota_d2h(yota_ctx* ctx, void* dst, const void* src, size_t bytes) {
   if (!ctx) YOTA_FAIL(YOTA_E_ARG, "null ctx");
   YOTA_TRY(ctx_ensure_device(ctx));
+  YOTA_TRY(ctx_wait_pending(ctx, src, bytes, ctx->stream));  // the value of a reduced buffer is the reduced one
   YOTA_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   YOTA_CUDA(cudaStreamSynchronize(ctx->stream));
-  return YOTA_OK;
+  return ctx_check_index_errors(ctx);
 }
 
 int yota_d2h_async(yota_ctx* ctx, void* dst_pinned, const void* src, size_t bytes) {
   if (!ctx) YOTA_FAIL(YOTA_E_ARG, "null ctx");
   YOTA_TRY(ctx_ensure_device(ctx));
+  YOTA_TRY(ctx_wait_pending(ctx, src, bytes, ctx->stream));
   YOTA_CUDA(cudaMemcpyAsync(dst_pinned, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   return YOTA_OK;
 }
@@ -182,6 +261,12 @@ int yota_host_free(yota_ctx* ctx, void* hptr) {
 int yota_h2d_async(yota_ctx* ctx, void* dst, const void* src, size_t bytes) {
   if (!ctx) YOTA_FAIL(YOTA_E_ARG, "null ctx");
   YOTA_TRY(ctx_ensure_device(ctx));
+  if (ctx->free_pending) {  // dst may be a block recycled from kernels still queued on the compute stream
+    YOTA_CUDA(cudaEventRecord(ctx->free_event, ctx->stream));
+    YOTA_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->free_event, 0));
+    ctx->free_pending = false;
+  }
+  YOTA_TRY(ctx_wait_pending(ctx, dst, bytes, ctx->copy_stream));
   YOTA_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
   return YOTA_OK;
 }
@@ -198,6 +283,7 @@ int yota_stream_fence(yota_ctx* ctx, int from, int to) {
 int yota_memset(yota_ctx* ctx, void* dptr, int byte, size_t bytes) {
   if (!ctx) YOTA_FAIL(YOTA_E_ARG, "null ctx");
   YOTA_TRY(ctx_ensure_device(ctx));
+  YOTA_TRY(ctx_wait_pending(ctx, dptr, bytes, ctx->stream));
   YOTA_CUDA(cudaMemsetAsync(dptr, byte, bytes, ctx->stream));
   return YOTA_OK;
 }
@@ -208,7 +294,9 @@ int yota_sync(yota_ctx* ctx) {
   YOTA_CUDA(cudaStreamSynchronize(ctx->stream));
   YOTA_CUDA(cudaStreamSynchronize(ctx->comm_stream));
   YOTA_CUDA(cudaStreamSynchronize(ctx->copy_stream));
-  return YOTA_OK;
+  for (auto& e : ctx->pending_ar) ctx->event_pool.push_back(e.ev);
+  ctx->pending_ar.clear();
+  return ctx_check_index_errors(ctx);
 }
 
 int yota_event_create(yota_ctx* ctx, void** ev) {
@@ -220,6 +308,9 @@ int yota_event_create(yota_ctx* ctx, void** ev) {
   return YOTA_OK;
 }
 int yota_event_record(yota_ctx* ctx, void* ev) {
+  if (!ctx) YOTA_FAIL(YOTA_E_ARG, "null ctx");
+  // a timing event covers the reductions of the runs issued before it
+  YOTA_TRY(ctx_join_comm(ctx, ctx->stream));
   YOTA_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ev), ctx->stream));
   return YOTA_OK;
 }
@@ -239,6 +330,7 @@ int yota_gemm(yota_ctx* ctx, int mode, int transA, int transB, int64_t m, int64_
               int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int accumulate) {
   if (!ctx) YOTA_FAIL(YOTA_E_ARG, "null ctx");
   YOTA_TRY(ctx_ensure_device(ctx));
+  YOTA_TRY(ctx_join_comm(ctx, ctx->stream));
   GemmArgs g{mode, transA, transB, m, n, k, A, lda, B, ldb, C, ldc, accumulate};
   if (mode != 0) {
     if (!gemm_tc_eligible(g))
@@ -254,6 +346,16 @@ int yota_gemm(yota_ctx* ctx, int mode, int transA, int transB, int64_t m, int64_
       g.A = w;
       g.B = static_cast<char*>(w) + offb;
     }
+    if (mode == 3) {  // compensated: lo parts of A and B into scratch, hi is read from the arrays themselves
+      const long long na = lda * (transA ? m : k), nb = ldb * (transB ? k : n);
+      const size_t offb = ((size_t)na * 4 + 255) & ~(size_t)255;
+      void* w = nullptr;
+      YOTA_TRY(ctx_scratch(ctx, offb + (size_t)nb * 4 + 256, &w));
+      YOTA_TRY(launch_split_tf32(static_cast<float*>(w), A, na, ctx->stream));
+      YOTA_TRY(launch_split_tf32(reinterpret_cast<float*>(static_cast<char*>(w) + offb), B, nb, ctx->stream));
+      g.A_lo = w;
+      g.B_lo = static_cast<char*>(w) + offb;
+    }
     return launch_gemm_tc(ctx, g, ctx->stream);
   }
   return launch_gemm_ffma(g, ctx->stream);
@@ -263,22 +365,25 @@ int yota_scatter_add_cols(yota_ctx* ctx, float* dx, int64_t rows, int64_t n_dst,
                           int64_t n_src) {
   if (!ctx) YOTA_FAIL(YOTA_E_ARG, "null ctx");
   YOTA_TRY(ctx_ensure_device(ctx));
+  YOTA_TRY(ctx_join_comm(ctx, ctx->stream));
   const size_t ws = scatter_cols_workspace_bytes(n_dst, n_src);
   void* w = nullptr;
   YOTA_TRY(ctx_scratch(ctx, ws, &w));
-  return launch_scatter_add_cols(dx, rows, n_dst, dy, idx, n_src, w, ws, ctx->stream);
+  return launch_scatter_add_cols(dx, rows, n_dst, dy, idx, n_src, w, ws, ctx->stream, nullptr, ctx->err_dev);
 }
 
 int yota_gather_cols(yota_ctx* ctx, float* y, const float* x, int64_t rows, int64_t n_dst, const int64_t* idx,
                      int64_t n_src) {
   if (!ctx) YOTA_FAIL(YOTA_E_ARG, "null ctx");
   YOTA_TRY(ctx_ensure_device(ctx));
-  return launch_gather_cols(y, x, rows, n_dst, idx, n_src, ctx->stream);
+  YOTA_TRY(ctx_join_comm(ctx, ctx->stream));
+  return launch_gather_cols(y, x, rows, n_dst, idx, n_src, ctx->stream, ctx->err_dev);
 }
 
 int yota_update_sgd(yota_ctx* ctx, float* x, const float* gx, int64_t n, float lr) {
   if (!ctx) YOTA_FAIL(YOTA_E_ARG, "null ctx");
   YOTA_TRY(ctx_ensure_device(ctx));
+  YOTA_TRY(ctx_join_comm(ctx, ctx->stream));
   return launch_axpy(x, gx, n, lr, ctx->stream);
 }
 

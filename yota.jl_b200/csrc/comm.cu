@@ -172,8 +172,15 @@ int yota_comm_destroy(yota_ctx* ctx) {
 int yota_allreduce_f32(yota_ctx* ctx, float* buf, int64_t n) {
   if (!ctx) YOTA_FAIL(YOTA_E_ARG, "null ctx");
   YOTA_TRY(ctx_ensure_device(ctx));
+  // On the communication stream like the reductions of a run (they share the kernel's barrier
+  // slots, so two of them must never be in flight at once), ordered after the compute stream's
+  // work so far; the compute stream then waits for it.
   const long long nn = n;
-  return comm_allreduce_bucket(ctx, &buf, &nn, 1, ctx->stream);
+  YOTA_CUDA(cudaEventRecord(ctx->fence_event, ctx->stream));
+  YOTA_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->fence_event, 0));
+  YOTA_TRY(comm_allreduce_bucket(ctx, &buf, &nn, 1, ctx->comm_stream));
+  YOTA_TRY(ctx_add_pending(ctx, {{reinterpret_cast<const char*>(buf), reinterpret_cast<const char*>(buf + n)}}));
+  return ctx_join_comm(ctx, ctx->stream);
 }
 
 }  // extern "C"

@@ -66,12 +66,53 @@ struct yota_ctx {
   // scratch for standalone ops
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
+  // Run-time index errors (Julia: BoundsError thrown by getindex / NNlib.scatter!,
+  // src/helpers.jl:7-11): kernels that read index VECTORS report an out-of-range entry here
+  // (pinned, device-mapped: {flag, offending 1-based index, extent}); checked at the next
+  // synchronising entry point (yota_sync / yota_d2h), which then fails with YOTA_E_SHAPE.
+  long long* err_host = nullptr;
+  long long* err_dev = nullptr;
+  // caller-owned blocks recycled by yota_free while work on another stream may still touch them
+  cudaEvent_t free_event = nullptr;
+  bool free_pending = false;
+  // Reductions still in flight on the communication stream when yota_program_run returned:
+  // the run does NOT join the two streams, so the tail buckets of eval i overlap the forward
+  // sweep of eval i+1.  Every later operation that touches one of these byte ranges first
+  // makes its stream wait for the bucket's event (ctx_wait_pending); yota_sync,
+  // yota_event_record and the stand-alone operators join everything (ctx_join_comm).
+  struct PendingAr {
+    std::vector<std::pair<const char*, const char*>> ranges;
+    cudaEvent_t ev;
+  };
+  std::vector<PendingAr> pending_ar;
+  std::vector<cudaEvent_t> event_pool;
 };
 
 namespace yota {
 
 int ctx_ensure_device(yota_ctx* ctx);
+// fails with YOTA_E_SHAPE ("BoundsError ...") if a kernel reported an out-of-range run-time index
+// since the last check; call after the stream has been synchronised
+int ctx_check_index_errors(yota_ctx* ctx);
+#ifdef __CUDACC__
+// Out-of-range entry `j1` (1-based, as the caller wrote it) of an index vector into an extent of n.
+// Plain stores: every reporter writes the same flag; which offender's value survives is immaterial.
+__device__ __forceinline__ void report_index_error(long long* err, long long j1, long long n) {
+  if (err) {
+    volatile long long* e = err;
+    e[1] = j1;
+    e[2] = n;
+    e[0] = 1;
+  }
+}
+#endif
 int ctx_scratch(yota_ctx* ctx, size_t bytes, void** out);
+// stream `s` waits for every in-flight reduction that overlaps [ptr, ptr + bytes)
+int ctx_wait_pending(yota_ctx* ctx, const void* ptr, size_t bytes, cudaStream_t s);
+// stream `s` waits for all in-flight reductions; the list is cleared
+int ctx_join_comm(yota_ctx* ctx, cudaStream_t s);
+// records a new in-flight reduction on the communication stream (event taken from the pool)
+int ctx_add_pending(yota_ctx* ctx, const std::vector<std::pair<const char*, const char*>>& ranges);
 
 // ---- elementwise region (ew_kernels.cu) ------------------------------------------------
 // CLS_GATHER: a FULL operand read through a column index, element (r, c) = x[r, idx[c]]
@@ -90,8 +131,9 @@ struct RegionIn {
   const float* ptr;
   int cls;
   int slot;
-  const long long* idx;  // CLS_GATHER: 1-based Int64 column indices (clamped like the stand-alone gather)
+  const long long* idx;  // CLS_GATHER: 1-based Int64 column indices (out of range: reported, then clamped)
   long long gather_n;    // CLS_GATHER: number of columns of the gathered array
+  long long* err;        // CLS_GATHER: where an out-of-range index is reported (yota_ctx::err_dev)
 };
 struct RegionOut {
   float* ptr;  // STORE: destination; ROWSUM / SCALARSUM: partials workspace
@@ -157,7 +199,7 @@ std::string region_signature(const RegionParams& p, int V);
 
 // ---- GEMM (gemm_ffma.cu / gemm_tc.cu) ---------------------------------------------------
 struct GemmArgs {
-  int mode;  // 0 fp32 ffma, 1 tf32 tcgen05, 2 bf16 tcgen05
+  int mode;  // 0 fp32 ffma, 1 tf32 tcgen05, 2 bf16 tcgen05, 3 compensated 3xTF32 tcgen05
   int transA, transB;
   long long M, N, K;
   const void* A;  // Float32 (modes 0, 1) or BF16 shadow (mode 2)
@@ -174,6 +216,9 @@ struct GemmArgs {
   // ... and BF16 copy of chain output `bsh_out` (BF16 mode: the operand shadow of later GEMMs)
   void* bsh = nullptr;
   int bsh_out = -1;
+  // mode 3: Float32 shadows  x - tf32(x)  of both operands (same dims / leading dimensions)
+  const void* A_lo = nullptr;
+  const void* B_lo = nullptr;
 };
 int launch_gemm_ffma(const GemmArgs& g, cudaStream_t s);
 int launch_gemm_tc(yota_ctx* ctx, const GemmArgs& g, cudaStream_t s);  // returns YOTA_E_UNSUPPORTED_OP if shape not eligible
@@ -183,6 +228,7 @@ bool gemm_epilogue_chain_ok(int static_id, int transA, int transB, int z_in);
 int launch_gemm_tc_epilogue(yota_ctx* ctx, const GemmArgs& g, int static_id, const RegionParams& rp, int z_in,
                             cudaStream_t s);
 int launch_cast_bf16(void* dst, const float* src, long long n, cudaStream_t s);
+int launch_split_tf32(float* lo, const float* src, long long n, cudaStream_t s);
 
 // ---- indexing (index_kernels.cu) --------------------------------------------------------
 struct IndexSpec {
@@ -194,10 +240,11 @@ struct IndexSpec {
   int nd_x;
   long long xdims[4];     // dims of x as indexed (flattened when n == 1)
 };
-int launch_getindex(const IndexSpec& sp, float* y, const float* x, long long n_out, cudaStream_t s);
+int launch_getindex(const IndexSpec& sp, float* y, const float* x, long long n_out, cudaStream_t s,
+                    long long* err = nullptr);
 size_t ungetindex_workspace_bytes(const IndexSpec& sp);
 int launch_ungetindex(const IndexSpec& sp, float* dx, const float* dy, void* workspace, size_t ws_bytes,
-                      int sm_count, cudaStream_t s, const float* scale = nullptr);
+                      int sm_count, cudaStream_t s, const float* scale = nullptr, long long* err = nullptr);
 // acc[I...] = acc[I...] + (0.0f + dy) over the selection (no index vectors); other elements untouched
 int launch_slice_accum(const IndexSpec& sp, float* acc, const float* dy, bool scalar_dy, cudaStream_t s);
 size_t scatter_cols_workspace_bytes(long long n_dst, long long n_src);
@@ -205,9 +252,9 @@ size_t scatter_cols_workspace_bytes(long long n_dst, long long n_src);
 // been materialised first): the seed-scaled source of a scatter-add pullback read in place
 int launch_scatter_add_cols(float* dx, long long rows, long long n_dst, const float* dy, const int64_t* idx,
                             long long n_src, void* workspace, size_t ws_bytes, cudaStream_t s,
-                            const float* scale = nullptr);
+                            const float* scale = nullptr, long long* err = nullptr);
 int launch_gather_cols(float* y, const float* x, long long rows, long long n_dst, const int64_t* idx,
-                       long long n_src, cudaStream_t s);
+                       long long n_src, cudaStream_t s, long long* err = nullptr);
 
 // ---- misc kernels (misc_kernels.cu) -----------------------------------------------------
 int launch_logsoftmax(float* y, const float* x, long long R, long long C, cudaStream_t s);

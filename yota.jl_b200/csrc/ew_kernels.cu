@@ -61,10 +61,16 @@ __device__ __forceinline__ float block_sum_fixed(float t, float* red /* >= 8 flo
   return s;
 }
 
-// column base of a gathered operand: x[:, idx[c]] with the index clamped into range
+// column base of a gathered operand: x[:, idx[c]]; an out-of-range index (BoundsError in the
+// reference) is reported through in.err and clamped so the load stays in bounds
 __device__ __forceinline__ long long gather_col(const RegionIn& in, long long c) {
-  long long j = __ldg(in.idx + c) - 1;
-  return j < 0 ? 0 : (j >= in.gather_n ? in.gather_n - 1 : j);
+  const long long j1 = __ldg(in.idx + c);
+  long long j = j1 - 1;
+  if (j < 0 || j >= in.gather_n) {
+    report_index_error(in.err, j1, in.gather_n);
+    j = j < 0 ? 0 : in.gather_n - 1;
+  }
+  return j;
 }
 
 template <int V>

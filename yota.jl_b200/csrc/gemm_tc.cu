@@ -149,22 +149,31 @@ struct Params {
   int bsh_out;
 };
 
-template <int TN>
+// X3 (3xTF32, the compensated mode): a stage also holds the LOW parts of both tiles,
+// lo = x - tf32(x) (planner-made Float32 shadows, see launch_split_tf32), and every k-step
+// issues three MMAs into the same TMEM accumulator: hi*hi + hi*lo + lo*hi.  What is dropped is
+// lo*lo and the truncation of lo itself, ~2^-21 relative per product -- the error level of an
+// FP32 FMA chain, so this mode is gated at the reference's rtol 1e-5 (tests/gpu_util.py::gate)
+// while running on the tensor cores at ~1/3 of the TF32 rate.
+template <int TN, bool X3 = false>
 struct Smem {
-  // narrow tiles (skinny outputs: a 1024 x 128 result is 8 CTAs at TN = 128, 32 at TN = 32) are
-  // latency-bound streams of A: twice the stages keep the same bytes in flight
-  static constexpr int NSTAGE = TN <= 64 ? 2 * STAGES : STAGES;
   static constexpr int A_BYTES = TM * 128;  // TM rows (or TM*EB/128 chunks of TK rows) of 128 bytes
   static constexpr int B_BYTES = TN * 128;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int HALF = A_BYTES + B_BYTES;  // the hi tiles; X3: the lo tiles follow
+  static constexpr int STAGE_BYTES = X3 ? 2 * HALF : HALF;
+  // narrow tiles (skinny outputs: a 1024 x 128 result is 8 CTAs at TN = 128, 32 at TN = 32) are
+  // latency-bound streams of A: twice the stages keep the same bytes in flight
+  static constexpr int NSTAGE = X3 ? (TN == 256 ? 2 : TN == 128 ? 3 : 4) : (TN <= 64 ? 2 * STAGES : STAGES);
   static constexpr int BAR_OFF = NSTAGE * STAGE_BYTES;
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;  // + barriers + slack for 1 KiB alignment
 };
 
-template <int TN, bool A_MN, bool B_MN, int EB>
+template <int TN, bool A_MN, bool B_MN, int EB, bool X3>
 __global__ void __launch_bounds__(THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
-  using S = Smem<TN>;
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ CUtensorMap map_al, const __grid_constant__ CUtensorMap map_bl, const Params p) {
+  static_assert(!X3 || EB == 4, "the compensated mode splits Float32 operands");
+  using S = Smem<TN, X3>;
   using E = El<EB>;
   constexpr int TK = E::TK;
   extern __shared__ unsigned char smem_raw[];
@@ -212,7 +221,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // issues box c: the whole stage is in flight after one issue slot.
     constexpr int NA = A_MN ? TM / E::CHUNK : 1;
     constexpr int NB = B_MN ? TN / E::CHUNK : 1;
-    static_assert(NA + NB <= 32, "one lane per TMA box");
+    static_assert((X3 ? 2 : 1) * (NA + NB) <= 32, "one lane per TMA box");
     int stage = 0;
     uint32_t phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -223,33 +232,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           mbar_expect_tx(&full[stage], S::STAGE_BYTES);
         }
         __syncwarp();
-        unsigned char* sa = smem + stage * S::STAGE_BYTES;
-        unsigned char* sb = sa + S::A_BYTES;
         const int k0 = kb * TK;
-        if (!p.spread) {
-          if (lane == 0) {
-            if (A_MN) {
 #pragma unroll
-              for (int c = 0; c < NA; c++) tma_load_2d(sa + c * E::CHUNK_BYTES, &map_a, &full[stage], m0 + E::CHUNK * c, k0);
-            } else
-              tma_load_2d(sa, &map_a, &full[stage], k0, m0);
-            if (B_MN) {
+        for (int part = 0; part < (X3 ? 2 : 1); part++) {  // part 1: the lo tiles of the compensated mode
+          unsigned char* sa = smem + stage * S::STAGE_BYTES + part * S::HALF;
+          unsigned char* sb = sa + S::A_BYTES;
+          const CUtensorMap* ma = part ? &map_al : &map_a;
+          const CUtensorMap* mb = part ? &map_bl : &map_b;
+          const int l0 = part * (NA + NB);
+          if (!p.spread) {
+            if (lane == 0) {
+              if (A_MN) {
 #pragma unroll
-              for (int c = 0; c < NB; c++) tma_load_2d(sb + c * E::CHUNK_BYTES, &map_b, &full[stage], n0 + E::CHUNK * c, k0);
-            } else
-              tma_load_2d(sb, &map_b, &full[stage], k0, n0);
+                for (int c = 0; c < NA; c++) tma_load_2d(sa + c * E::CHUNK_BYTES, ma, &full[stage], m0 + E::CHUNK * c, k0);
+              } else
+                tma_load_2d(sa, ma, &full[stage], k0, m0);
+              if (B_MN) {
+#pragma unroll
+                for (int c = 0; c < NB; c++) tma_load_2d(sb + c * E::CHUNK_BYTES, mb, &full[stage], n0 + E::CHUNK * c, k0);
+              } else
+                tma_load_2d(sb, mb, &full[stage], k0, n0);
+            }
+          } else if (lane >= l0 && lane < l0 + NA) {
+            if (A_MN)
+              tma_load_2d(sa + (lane - l0) * E::CHUNK_BYTES, ma, &full[stage], m0 + E::CHUNK * (lane - l0), k0);
+            else
+              tma_load_2d(sa, ma, &full[stage], k0, m0);
+          } else if (lane >= l0 + NA && lane < l0 + NA + NB) {
+            const int c = lane - l0 - NA;
+            if (B_MN)
+              tma_load_2d(sb + c * E::CHUNK_BYTES, mb, &full[stage], n0 + E::CHUNK * c, k0);
+            else
+              tma_load_2d(sb, mb, &full[stage], k0, n0);
           }
-        } else if (lane < NA) {
-          if (A_MN)
-            tma_load_2d(sa + lane * E::CHUNK_BYTES, &map_a, &full[stage], m0 + E::CHUNK * lane, k0);
-          else
-            tma_load_2d(sa, &map_a, &full[stage], k0, m0);
-        } else if (lane < NA + NB) {
-          const int c = lane - NA;
-          if (B_MN)
-            tma_load_2d(sb + c * E::CHUNK_BYTES, &map_b, &full[stage], n0 + E::CHUNK * c, k0);
-          else
-            tma_load_2d(sb, &map_b, &full[stage], k0, n0);
         }
         if (++stage == S::NSTAGE) {
           stage = 0;
@@ -287,6 +302,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               umma_tf32(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
             else
               umma_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (X3) {
+              const uint32_t sal = sa + S::HALF, sbl = sal + S::A_BYTES;
+              const uint64_t dal = A_MN ? make_desc(sal + k * E::MN_KSTEP, E::CHUNK_BYTES, E::MN_SBO, E::MN_LAYOUT)
+                                        : make_desc(sal + k * 32, 16, 1024, 2);
+              const uint64_t dbl = B_MN ? make_desc(sbl + k * E::MN_KSTEP, E::CHUNK_BYTES, E::MN_SBO, E::MN_LAYOUT)
+                                        : make_desc(sbl + k * 32, 16, 1024, 2);
+              umma_tf32(d_tmem, da, dbl, idesc, 1u);
+              umma_tf32(d_tmem, dal, db, idesc, 1u);
+            }
           }
           umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
           if (++stage == S::NSTAGE) {
@@ -409,12 +433,16 @@ static int make_map(CUtensorMap* map, const void* ptr, long long mn, long long k
   return YOTA_OK;
 }
 
-template <int TN, bool A_MN, bool B_MN, int EB>
-static int launch(const GemmArgs& g, const CUtensorMap& ma, const CUtensorMap& mb, int sm_count, cudaStream_t s) {
+struct Maps {
+  CUtensorMap a, b, al, bl;  // al / bl: the lo shadows of the compensated mode (copies of a / b otherwise)
+};
+
+template <int TN, bool A_MN, bool B_MN, int EB, bool X3 = false>
+static int launch(const GemmArgs& g, const Maps& mp, int sm_count, cudaStream_t s) {
   static bool attr = false;
-  auto kern = gemm_tc_kernel<TN, A_MN, B_MN, EB>;
+  auto kern = gemm_tc_kernel<TN, A_MN, B_MN, EB, X3>;
   if (!attr) {
-    YOTA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<TN>::TOTAL));
+    YOTA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<TN, X3>::TOTAL));
     attr = true;
   }
   Params p;
@@ -434,7 +462,7 @@ static int launch(const GemmArgs& g, const CUtensorMap& ma, const CUtensorMap& m
   p.num_n = (int)(g.N / TN);
   const int tiles = p.num_m * p.num_n;
   const int grid = tiles < sm_count ? tiles : sm_count;
-  kern<<<grid, THREADS, Smem<TN>::TOTAL, s>>>(ma, mb, p);
+  kern<<<grid, THREADS, Smem<TN, X3>::TOTAL, s>>>(mp.a, mp.b, mp.al, mp.bl, p);
   YOTA_CUDA(cudaGetLastError());
   return YOTA_OK;
 }
@@ -455,11 +483,14 @@ static int launch(const GemmArgs& g, const CUtensorMap& ma, const CUtensorMap& m
 constexpr int STAGES2 = 6;
 constexpr int TN2 = 256;
 
-struct Smem2 {
+template <bool X3>
+struct Smem2T {
+  static constexpr int NST = X3 ? 3 : STAGES2;
   static constexpr int A_BYTES = TM * 128;
   static constexpr int B_BYTES = (TN2 / 2) * 128;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFF = STAGES2 * STAGE_BYTES;
+  static constexpr int HALF = A_BYTES + B_BYTES;
+  static constexpr int STAGE_BYTES = X3 ? 2 * HALF : HALF;
+  static constexpr int BAR_OFF = NST * STAGE_BYTES;
   static constexpr int TSH_OFF = BAR_OFF + 256;           // 4 epilogue warps x (32 x 32 floats): transpose staging
   static constexpr int TOTAL = TSH_OFF + 4 * 4096 + 1024;  // + slack for 1 KiB alignment
 };
@@ -629,11 +660,14 @@ struct Epilogue {
 };
 #undef YCE
 
-template <bool A_MN, bool B_MN, int EB, int EPI, int ZIN>
+template <bool A_MN, bool B_MN, int EB, int EPI, int ZIN, bool X3>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
-gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p,
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                const __grid_constant__ CUtensorMap map_al, const __grid_constant__ CUtensorMap map_bl, const Params p,
                 const __grid_constant__ RegionParams rp) {
-  using S = Smem2;
+  static_assert(!X3 || EB == 4, "the compensated mode splits Float32 operands");
+  using S = Smem2T<X3>;
+  constexpr int STAGES2 = S::NST;  // shadows the namespace constant: 3 deep with the lo tiles aboard
   using E = El<EB>;
   constexpr int TK = E::TK;
   constexpr int TNH = TN2 / 2;  // B columns held by one CTA
@@ -697,35 +731,41 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             mbar_arrive_remote(&full[stage], 0);
         }
         __syncwarp();
-        unsigned char* sa = smem + stage * S::STAGE_BYTES;
-        unsigned char* sb = sa + S::A_BYTES;
         const int k0 = kb * TK;
-        if (!p.spread) {
-          if (lane == 0) {
-            if (A_MN) {
 #pragma unroll
-              for (int c = 0; c < NA; c++)
-                tma_load_2d_2sm(sa + c * E::CHUNK_BYTES, &map_a, &full[stage], m0 + E::CHUNK * c, k0);
-            } else
-              tma_load_2d_2sm(sa, &map_a, &full[stage], k0, m0);
-            if (B_MN) {
+        for (int part = 0; part < (X3 ? 2 : 1); part++) {  // part 1: the lo tiles of the compensated mode
+          unsigned char* sa = smem + stage * S::STAGE_BYTES + part * S::HALF;
+          unsigned char* sb = sa + S::A_BYTES;
+          const CUtensorMap* ma = part ? &map_al : &map_a;
+          const CUtensorMap* mb = part ? &map_bl : &map_b;
+          const int l0 = part * (NA + NB);
+          if (!p.spread) {
+            if (lane == 0) {
+              if (A_MN) {
 #pragma unroll
-              for (int c = 0; c < NB; c++)
-                tma_load_2d_2sm(sb + c * E::CHUNK_BYTES, &map_b, &full[stage], n0 + E::CHUNK * c, k0);
-            } else
-              tma_load_2d_2sm(sb, &map_b, &full[stage], k0, n0);
+                for (int c = 0; c < NA; c++)
+                  tma_load_2d_2sm(sa + c * E::CHUNK_BYTES, ma, &full[stage], m0 + E::CHUNK * c, k0);
+              } else
+                tma_load_2d_2sm(sa, ma, &full[stage], k0, m0);
+              if (B_MN) {
+#pragma unroll
+                for (int c = 0; c < NB; c++)
+                  tma_load_2d_2sm(sb + c * E::CHUNK_BYTES, mb, &full[stage], n0 + E::CHUNK * c, k0);
+              } else
+                tma_load_2d_2sm(sb, mb, &full[stage], k0, n0);
+            }
+          } else if (lane >= l0 && lane < l0 + NA) {
+            if (A_MN)
+              tma_load_2d_2sm(sa + (lane - l0) * E::CHUNK_BYTES, ma, &full[stage], m0 + E::CHUNK * (lane - l0), k0);
+            else
+              tma_load_2d_2sm(sa, ma, &full[stage], k0, m0);
+          } else if (lane >= l0 + NA && lane < l0 + NA + NB) {
+            const int c = lane - l0 - NA;
+            if (B_MN)
+              tma_load_2d_2sm(sb + c * E::CHUNK_BYTES, mb, &full[stage], n0 + E::CHUNK * c, k0);
+            else
+              tma_load_2d_2sm(sb, mb, &full[stage], k0, n0);
           }
-        } else if (lane < NA) {
-          if (A_MN)
-            tma_load_2d_2sm(sa + lane * E::CHUNK_BYTES, &map_a, &full[stage], m0 + E::CHUNK * lane, k0);
-          else
-            tma_load_2d_2sm(sa, &map_a, &full[stage], k0, m0);
-        } else if (lane < NA + NB) {
-          const int c = lane - NA;
-          if (B_MN)
-            tma_load_2d_2sm(sb + c * E::CHUNK_BYTES, &map_b, &full[stage], n0 + E::CHUNK * c, k0);
-          else
-            tma_load_2d_2sm(sb, &map_b, &full[stage], k0, n0);
         }
         if (++stage == STAGES2) {
           stage = 0;
@@ -759,6 +799,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const uint64_t db = B_MN ? make_desc(sb + k * E::MN_KSTEP, E::CHUNK_BYTES, E::MN_SBO, E::MN_LAYOUT)
                                      : make_desc(sb + k * 32, 16, 1024, 2);
             umma_2sm<EB>(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (X3) {
+              const uint32_t sal = sa + S::HALF, sbl = sal + S::A_BYTES;
+              const uint64_t dal = A_MN ? make_desc(sal + k * E::MN_KSTEP, E::CHUNK_BYTES, E::MN_SBO, E::MN_LAYOUT)
+                                        : make_desc(sal + k * 32, 16, 1024, 2);
+              const uint64_t dbl = B_MN ? make_desc(sbl + k * E::MN_KSTEP, E::CHUNK_BYTES, E::MN_SBO, E::MN_LAYOUT)
+                                        : make_desc(sbl + k * 32, 16, 1024, 2);
+              umma_2sm<EB>(d_tmem, da, dbl, idesc, 1u);
+              umma_2sm<EB>(d_tmem, dal, db, idesc, 1u);
+            }
           }
           umma_commit_2sm(&empty[stage]);
           if (++stage == STAGES2) {
@@ -842,13 +891,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   }
 }
 
-template <bool A_MN, bool B_MN, int EB, int EPI = -1, int ZIN = 0>
-static int launch2(const GemmArgs& g, const CUtensorMap& ma, const CUtensorMap& mb, int sm_count, cudaStream_t s,
-                   const RegionParams* rp = nullptr) {
+template <bool A_MN, bool B_MN, int EB, int EPI = -1, int ZIN = 0, bool X3 = false>
+static int launch2(const GemmArgs& g, const Maps& mp, int sm_count, cudaStream_t s, const RegionParams* rp = nullptr) {
   static bool attr = false;
-  auto kern = gemm_tc2_kernel<A_MN, B_MN, EB, EPI, ZIN>;
+  auto kern = gemm_tc2_kernel<A_MN, B_MN, EB, EPI, ZIN, X3>;
   if (!attr) {
-    YOTA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem2::TOTAL));
+    YOTA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem2T<X3>::TOTAL));
     attr = true;
   }
   Params p;
@@ -870,7 +918,7 @@ static int launch2(const GemmArgs& g, const CUtensorMap& ma, const CUtensorMap& 
   int pairs = sm_count / 2;
   if (tiles < pairs) pairs = tiles;
   static const RegionParams no_rp{};
-  kern<<<2 * pairs, THREADS, Smem2::TOTAL, s>>>(ma, mb, p, rp ? *rp : no_rp);
+  kern<<<2 * pairs, THREADS, Smem2T<X3>::TOTAL, s>>>(mp.a, mp.b, mp.al, mp.bl, p, rp ? *rp : no_rp);
   YOTA_CUDA(cudaGetLastError());
   return YOTA_OK;
 }
@@ -885,8 +933,8 @@ static inline int grid_sms(const yota_ctx* ctx) {
 }
 
 bool gemm_tc_eligible(const GemmArgs& g) {
-  if (g.mode != 1 && g.mode != 2) return false;
-  const int tk = g.mode == 1 ? 32 : 64;
+  if (g.mode < 1 || g.mode > 3) return false;
+  const int tk = g.mode == 2 ? 64 : 32;
   if (g.M < tc::TM || g.N < 128 || g.K < tk) return false;
   if (g.M % tc::TM || g.N % 128 || g.K % tk) return false;
   if ((g.lda | g.ldb) % 8) return false;
@@ -921,15 +969,33 @@ bool gemm_epilogue_chain_ok(int static_id, int transA, int transB, int z_in) {
 }
 
 namespace tc {
+// tensor maps of both operands (mode 3: also of their lo shadows, same dims and strides)
+static int make_maps(Maps* mp, const GemmArgs& g, bool A_MN, bool B_MN, int tile_n) {
+  const int eb = g.mode == 2 ? 2 : 4;
+  YOTA_TRY(make_map(&mp->a, g.A, g.M, g.K, g.lda, A_MN, TM, eb));
+  YOTA_TRY(make_map(&mp->b, g.B, g.N, g.K, g.ldb, B_MN, tile_n, eb));
+  if (g.mode == 3) {
+    if (!g.A_lo || !g.B_lo) YOTA_FAIL(YOTA_E_ARG, "internal: compensated GEMM without lo shadows");
+    YOTA_TRY(make_map(&mp->al, g.A_lo, g.M, g.K, g.lda, A_MN, TM, eb));
+    YOTA_TRY(make_map(&mp->bl, g.B_lo, g.N, g.K, g.ldb, B_MN, tile_n, eb));
+  } else {
+    mp->al = mp->a;
+    mp->bl = mp->b;
+  }
+  return YOTA_OK;
+}
+
 template <int ID, int ZIN>
-static int launch_epi(const GemmArgs& g, const CUtensorMap& ma, const CUtensorMap& mb, int sm_count, cudaStream_t s,
-                      const RegionParams& rp, bool A_MN, int eb) {
+static int launch_epi(const GemmArgs& g, const Maps& mp, int sm_count, cudaStream_t s, const RegionParams& rp,
+                      bool A_MN) {
   if constexpr (epi_z_ok<ID>(ZIN)) {
-    if (A_MN)
-      return eb == 4 ? launch2<true, false, 4, ID, ZIN>(g, ma, mb, sm_count, s, &rp)
-                     : launch2<true, false, 2, ID, ZIN>(g, ma, mb, sm_count, s, &rp);
-    return eb == 4 ? launch2<false, false, 4, ID, ZIN>(g, ma, mb, sm_count, s, &rp)
-                   : launch2<false, false, 2, ID, ZIN>(g, ma, mb, sm_count, s, &rp);
+#define GOE(a)                                                                           \
+  return g.mode == 3   ? launch2<a, false, 4, ID, ZIN, true>(g, mp, sm_count, s, &rp)    \
+         : g.mode == 1 ? launch2<a, false, 4, ID, ZIN>(g, mp, sm_count, s, &rp)          \
+                       : launch2<a, false, 2, ID, ZIN>(g, mp, sm_count, s, &rp)
+    if (A_MN) GOE(true);
+    GOE(false);
+#undef GOE
   } else {
     YOTA_FAIL(YOTA_E_ARG, "internal: chain %d has no FULL operand %d", ID, ZIN);
   }
@@ -943,15 +1009,13 @@ int launch_gemm_tc_epilogue(yota_ctx* ctx, const GemmArgs& g, int static_id, con
       !gemm_epilogue_chain_ok(static_id, g.transA, g.transB, z_in))
     YOTA_FAIL(YOTA_E_ARG, "internal: GEMM epilogue fusion planned for an ineligible GEMM");
   const bool A_MN = !g.transA;
-  const int eb = g.mode == 1 ? 4 : 2;
-  CUtensorMap ma, mb;
-  YOTA_TRY(tc::make_map(&ma, g.A, g.M, g.K, g.lda, A_MN, tc::TM, eb));
-  YOTA_TRY(tc::make_map(&mb, g.B, g.N, g.K, g.ldb, false, tc::TN2 / 2, eb));
+  tc::Maps mp;
+  YOTA_TRY(tc::make_maps(&mp, g, A_MN, false, tc::TN2 / 2));
   switch (static_id) {
-#define X(ID)                                                                                 \
-  case ID:                                                                                    \
-    return z_in == 0 ? tc::launch_epi<ID, 0>(g, ma, mb, grid_sms(ctx), s, rp, A_MN, eb)      \
-                     : tc::launch_epi<ID, 1>(g, ma, mb, grid_sms(ctx), s, rp, A_MN, eb); 
+#define X(ID)                                                                       \
+  case ID:                                                                          \
+    return z_in == 0 ? tc::launch_epi<ID, 0>(g, mp, grid_sms(ctx), s, rp, A_MN)    \
+                     : tc::launch_epi<ID, 1>(g, mp, grid_sms(ctx), s, rp, A_MN);
     YOTA_EPI_CHAIN_LIST(X)
 #undef X
   }
@@ -960,20 +1024,21 @@ int launch_gemm_tc_epilogue(yota_ctx* ctx, const GemmArgs& g, int static_id, con
 
 // mode 1: A/B are the Float32 arrays (read as TF32).  mode 2: A/B point at BF16 shadows with the
 // same dims / leading dimensions (see launch_cast_bf16 and the planner's shadow tensors).
+// mode 3: A/B as in mode 1 plus A_lo/B_lo, the Float32 shadows x - tf32(x) (launch_split_tf32).
 int launch_gemm_tc(yota_ctx* ctx, const GemmArgs& g, cudaStream_t s) {
   if (!gemm_tc_eligible(g)) YOTA_FAIL(YOTA_E_UNSUPPORTED_OP, "gemm: shape not eligible for the tensor-core kernel");
   const bool A_MN = !g.transA;      // A stored M x K column-major: M contiguous
   const bool B_MN = g.transB != 0;  // B stored N x K column-major: N contiguous
-  const int eb = g.mode == 1 ? 4 : 2;
-  CUtensorMap ma, mb;
+  const int eb = g.mode == 2 ? 2 : 4;
+  tc::Maps mp;
   const bool two_cta = gemm_tc2_eligible(g, ctx->sm_count);
   if (two_cta) {
     // each CTA of a pair loads a 128-row box of A and a 128-column box of B
-    YOTA_TRY(tc::make_map(&ma, g.A, g.M, g.K, g.lda, A_MN, tc::TM, eb));
-    YOTA_TRY(tc::make_map(&mb, g.B, g.N, g.K, g.ldb, B_MN, tc::TN2 / 2, eb));
-#define GO2(a, b)                                                        \
-  return eb == 4 ? tc::launch2<a, b, 4>(g, ma, mb, grid_sms(ctx), s)     \
-                 : tc::launch2<a, b, 2>(g, ma, mb, grid_sms(ctx), s)
+    YOTA_TRY(tc::make_maps(&mp, g, A_MN, B_MN, tc::TN2 / 2));
+#define GO2(a, b)                                                                         \
+  return g.mode == 3   ? tc::launch2<a, b, 4, -1, 0, true>(g, mp, grid_sms(ctx), s)       \
+         : g.mode == 1 ? tc::launch2<a, b, 4>(g, mp, grid_sms(ctx), s)                    \
+                       : tc::launch2<a, b, 2>(g, mp, grid_sms(ctx), s)
     if (A_MN && B_MN) GO2(true, true);
     if (A_MN && !B_MN) GO2(true, false);
     if (!A_MN && B_MN) GO2(false, true);
@@ -989,11 +1054,11 @@ int launch_gemm_tc(yota_ctx* ctx, const GemmArgs& g, cudaStream_t s) {
       TN = w;
       break;
     }
-  YOTA_TRY(tc::make_map(&ma, g.A, g.M, g.K, g.lda, A_MN, tc::TM, eb));
-  YOTA_TRY(tc::make_map(&mb, g.B, g.N, g.K, g.ldb, B_MN, TN, eb));
-#define GO(TNv, a, b)                                                          \
-  return eb == 4 ? tc::launch<TNv, a, b, 4>(g, ma, mb, grid_sms(ctx), s)       \
-                 : tc::launch<TNv, a, b, 2>(g, ma, mb, grid_sms(ctx), s)
+  YOTA_TRY(tc::make_maps(&mp, g, A_MN, B_MN, TN));
+#define GO(TNv, a, b)                                                                          \
+  return g.mode == 3   ? tc::launch<TNv, a, b, 4, true>(g, mp, grid_sms(ctx), s)               \
+         : g.mode == 1 ? tc::launch<TNv, a, b, 4>(g, mp, grid_sms(ctx), s)                     \
+                       : tc::launch<TNv, a, b, 2>(g, mp, grid_sms(ctx), s)
 #define GOALL(TNv)                          \
   do {                                      \
     if (A_MN && B_MN) GO(TNv, true, true);  \
@@ -1005,14 +1070,43 @@ int launch_gemm_tc(yota_ctx* ctx, const GemmArgs& g, cudaStream_t s) {
   if (TN == 128) GOALL(128);
   if (TN == 64) GOALL(64);
   if (eb == 4) {
-    if (A_MN && B_MN) return tc::launch<32, true, true, 4>(g, ma, mb, grid_sms(ctx), s);
-    if (A_MN && !B_MN) return tc::launch<32, true, false, 4>(g, ma, mb, grid_sms(ctx), s);
-    if (!A_MN && B_MN) return tc::launch<32, false, true, 4>(g, ma, mb, grid_sms(ctx), s);
-    return tc::launch<32, false, false, 4>(g, ma, mb, grid_sms(ctx), s);
+#define GO32(a, b)                                                                      \
+  return g.mode == 3 ? tc::launch<32, a, b, 4, true>(g, mp, grid_sms(ctx), s)           \
+                     : tc::launch<32, a, b, 4>(g, mp, grid_sms(ctx), s)
+    if (A_MN && B_MN) GO32(true, true);
+    if (A_MN && !B_MN) GO32(true, false);
+    if (!A_MN && B_MN) GO32(false, true);
+    GO32(false, false);
+#undef GO32
   }
   YOTA_FAIL(YOTA_E_ARG, "internal: no tile width for this GEMM");
 #undef GOALL
 #undef GO
+}
+
+// lo = x - tf32(x): the low part of a Float32 operand for the compensated (3xTF32) mode.  tf32(x)
+// is x with the 13 low mantissa bits cleared -- what the tensor core makes of a Float32 it reads
+// as TF32 -- so hi needs no array of its own (the GEMM reads x itself) and x = hi + lo exactly.
+__global__ void split_tf32_kernel(float4* __restrict__ lo, const float4* __restrict__ src, long long n4) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(src + i);
+    float4 r;
+    r.x = __fsub_rn(v.x, __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u));
+    r.y = __fsub_rn(v.y, __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u));
+    r.z = __fsub_rn(v.z, __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u));
+    r.w = __fsub_rn(v.w, __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
+    lo[i] = r;
+  }
+}
+int launch_split_tf32(float* lo, const float* src, long long n, cudaStream_t s) {
+  if (n == 0) return YOTA_OK;
+  if ((n & 3) || ((reinterpret_cast<uintptr_t>(lo) | reinterpret_cast<uintptr_t>(src)) & 15))
+    YOTA_FAIL(YOTA_E_SHAPE, "split_tf32: element count and pointers must be multiples of 4 / 16 bytes");
+  long long blocks = (n / 4 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  split_tf32_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<float4*>(lo), reinterpret_cast<const float4*>(src), n / 4);
+  YOTA_CUDA(cudaGetLastError());
+  return YOTA_OK;
 }
 
 // Float32 -> BF16 (round to nearest even) shadow of a GEMM operand

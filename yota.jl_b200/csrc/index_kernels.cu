@@ -19,27 +19,36 @@ namespace yota {
 // ------------------------------------------------------------------------------------------
 // gather
 // ------------------------------------------------------------------------------------------
+// An out-of-range index is a BoundsError in the reference; here it is REPORTED (the next
+// synchronising call fails with YOTA_E_SHAPE) and clamped so the kernel itself stays in bounds.
+__device__ __forceinline__ long long checked_index(long long j1, long long n, long long* err) {
+  long long j = j1 - 1;
+  if (j < 0 || j >= n) {
+    report_index_error(err, j1, n);
+    j = j < 0 ? 0 : n - 1;
+  }
+  return j;
+}
+
 __global__ void gather_cols_v4_kernel(float4* __restrict__ y, const float4* __restrict__ x, int R4, long long n_dst,
-                                      const int64_t* __restrict__ idx, long long n_src) {
+                                      const int64_t* __restrict__ idx, long long n_src, long long* err) {
   const long long total = n_src * R4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const long long k = i / R4;
     const int r = (int)(i - k * R4);
-    long long j = __ldg(idx + k) - 1;
-    j = j < 0 ? 0 : (j >= n_dst ? n_dst - 1 : j);
+    const long long j = checked_index(__ldg(idx + k), n_dst, err);
     y[i] = __ldg(x + j * R4 + r);
   }
 }
 __global__ void gather_cols_v1_kernel(float* __restrict__ y, const float* __restrict__ x, long long R, long long n_dst,
-                                      const int64_t* __restrict__ idx, long long n_src) {
+                                      const int64_t* __restrict__ idx, long long n_src, long long* err) {
   const long long total = n_src * R;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const long long k = i / R;
     const long long r = i - k * R;
-    long long j = __ldg(idx + k) - 1;
-    j = j < 0 ? 0 : (j >= n_dst ? n_dst - 1 : j);
+    const long long j = checked_index(__ldg(idx + k), n_dst, err);
     y[i] = __ldg(x + j * R + r);
   }
 }
@@ -52,14 +61,14 @@ static unsigned grid_for(long long total, int threads, int cap_blocks = 148 * 16
 }
 
 int launch_gather_cols(float* y, const float* x, long long rows, long long n_dst, const int64_t* idx, long long n_src,
-                       cudaStream_t s) {
+                       cudaStream_t s, long long* err) {
   if (rows * n_src == 0) return YOTA_OK;
   const bool v4 = (rows % 4 == 0) && ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(x)) % 16 == 0);
   if (v4)
     gather_cols_v4_kernel<<<grid_for(n_src * (rows / 4), 256), 256, 0, s>>>(
-        reinterpret_cast<float4*>(y), reinterpret_cast<const float4*>(x), (int)(rows / 4), n_dst, idx, n_src);
+        reinterpret_cast<float4*>(y), reinterpret_cast<const float4*>(x), (int)(rows / 4), n_dst, idx, n_src, err);
   else
-    gather_cols_v1_kernel<<<grid_for(n_src * rows, 256), 256, 0, s>>>(y, x, rows, n_dst, idx, n_src);
+    gather_cols_v1_kernel<<<grid_for(n_src * rows, 256), 256, 0, s>>>(y, x, rows, n_dst, idx, n_src, err);
   YOTA_CUDA(cudaGetLastError());
   return YOTA_OK;
 }
@@ -72,6 +81,7 @@ struct GetIdxParams {
   long long xdim[4];     // extent of x along index d
   long long xstride[4];  // element stride of x along index d
   long long odim[4];     // extent of the (unsqueezed) output along index d (1 for INT)
+  long long* err;        // out-of-range entries of an index vector are reported here
 };
 
 __global__ void getindex_generic_kernel(GetIdxParams p, float* __restrict__ y, const float* __restrict__ x,
@@ -88,8 +98,7 @@ __global__ void getindex_generic_kernel(GetIdxParams p, float* __restrict__ y, c
         if (p.kind[d] == YOTA_IDX_COLON)
           xi = c;
         else if (p.kind[d] == YOTA_IDX_VEC) {
-          xi = __ldg(p.vec[d] + c) - 1;
-          xi = xi < 0 ? 0 : (xi >= p.xdim[d] ? p.xdim[d] - 1 : xi);
+          xi = checked_index(__ldg(p.vec[d] + c), p.xdim[d], p.err);
         } else
           xi = p.a[d] - 1 + c;  // INT (c == 0) or RANGE
         off += xi * p.xstride[d];
@@ -101,6 +110,7 @@ __global__ void getindex_generic_kernel(GetIdxParams p, float* __restrict__ y, c
 
 static void fill_getidx(const IndexSpec& sp, GetIdxParams& p) {
   p.n = sp.n;
+  p.err = nullptr;
   long long st = 1;
   for (int d = 0; d < 4; d++) {
     p.kind[d] = 0;
@@ -125,13 +135,14 @@ static void fill_getidx(const IndexSpec& sp, GetIdxParams& p) {
   }
 }
 
-int launch_getindex(const IndexSpec& sp, float* y, const float* x, long long n_out, cudaStream_t s) {
+int launch_getindex(const IndexSpec& sp, float* y, const float* x, long long n_out, cudaStream_t s, long long* err) {
   if (n_out == 0) return YOTA_OK;
   // fast path: x[:, idx] on a matrix
   if (sp.n == 2 && sp.kind[0] == YOTA_IDX_COLON && sp.kind[1] == YOTA_IDX_VEC)
-    return launch_gather_cols(y, x, sp.xdims[0], sp.xdims[1], sp.vec[1], sp.vlen[1], s);
+    return launch_gather_cols(y, x, sp.xdims[0], sp.xdims[1], sp.vec[1], sp.vlen[1], s, err);
   GetIdxParams p;
   fill_getidx(sp, p);
+  p.err = err;
   getindex_generic_kernel<<<grid_for(n_out, 256), 256, 0, s>>>(p, y, x, n_out);
   YOTA_CUDA(cudaGetLastError());
   return YOTA_OK;
@@ -254,10 +265,17 @@ static int exclusive_scan_u32(unsigned* data, long long n, unsigned* ws, cudaStr
 // ------------------------------------------------------------------------------------------
 constexpr int RS_T = 256, RS_WARPS = 8, RS_ROUNDS = 16, RS_TILE = RS_T * RS_ROUNDS;  // 4096 keys per CTA
 
-__device__ __forceinline__ unsigned key_of_idx(const int64_t* __restrict__ idx, long long i, long long n_dst) {
+__device__ __forceinline__ unsigned key_of_idx(const int64_t* __restrict__ idx, long long i, long long n_dst,
+                                               long long* err = nullptr) {
   const long long j = __ldg(idx + i) - 1;
-  // out-of-range indices (a BoundsError in Julia) go to an overflow bucket that is never read
-  return (j < 0 || j >= n_dst) ? (unsigned)n_dst : (unsigned)j;
+  // out-of-range indices (a BoundsError in Julia, src/helpers.jl:7-11 -> NNlib.scatter!) are
+  // reported by the first histogram pass (err != nullptr there) and go to an overflow bucket
+  // that is never read, so the fold itself stays in bounds
+  if (j < 0 || j >= n_dst) {
+    report_index_error(err, j + 1, n_dst);
+    return (unsigned)n_dst;
+  }
+  return (unsigned)j;
 }
 
 // FROM_IDX: first pass -- keys are derived from the Int64 index vector on the fly and the value
@@ -266,7 +284,7 @@ template <int BITS, bool FROM_IDX>
 __global__ void __launch_bounds__(RS_T) radix_hist_kernel(const unsigned* __restrict__ keys,
                                                           const int64_t* __restrict__ idx, long long n_dst,
                                                           long long n, int shift, unsigned* __restrict__ hist,
-                                                          int nblocks) {
+                                                          int nblocks, long long* err) {
   constexpr int ND = 1 << BITS;
   __shared__ unsigned sh[ND];
   for (int i = threadIdx.x; i < ND; i += RS_T) sh[i] = 0;
@@ -276,7 +294,7 @@ __global__ void __launch_bounds__(RS_T) radix_hist_kernel(const unsigned* __rest
   for (int r = 0; r < RS_ROUNDS; r++) {
     const long long i = base + r * RS_T + threadIdx.x;
     if (i < n) {
-      const unsigned k = FROM_IDX ? key_of_idx(idx, i, n_dst) : keys[i];
+      const unsigned k = FROM_IDX ? key_of_idx(idx, i, n_dst, err) : keys[i];
       atomicAdd(&sh[(k >> shift) & (ND - 1)], 1u);  // integer counts: order-independent
     }
   }
@@ -408,9 +426,9 @@ static SortPlan sort_plan(long long n_dst, long long n_src) {
 template <int BITS, bool FROM_IDX>
 static int radix_pass(const unsigned* kin, const unsigned* vin, const int64_t* idx, long long n_dst, unsigned* kout,
                       unsigned* vout, long long n, int shift, unsigned* hist, int nblocks, unsigned* scan_ws,
-                      cudaStream_t s) {
+                      cudaStream_t s, long long* err) {
   constexpr int ND = 1 << BITS;
-  radix_hist_kernel<BITS, FROM_IDX><<<nblocks, RS_T, 0, s>>>(kin, idx, n_dst, n, shift, hist, nblocks);
+  radix_hist_kernel<BITS, FROM_IDX><<<nblocks, RS_T, 0, s>>>(kin, idx, n_dst, n, shift, hist, nblocks, err);
   YOTA_CUDA(cudaGetLastError());
   YOTA_TRY(exclusive_scan_u32(hist, (long long)ND * nblocks, scan_ws, s));
   radix_scatter_kernel<BITS, FROM_IDX><<<nblocks, RS_T, 0, s>>>(kin, vin, idx, n_dst, kout, vout, n, shift, hist, nblocks);
@@ -421,7 +439,7 @@ static int radix_pass(const unsigned* kin, const unsigned* vin, const int64_t* i
 // Sort (idx -> dest key, position) and build segment starts.  Results: *perm (source
 // positions grouped by destination, ascending inside a group), *seg (n_dst + 1 starts).
 static int sort_by_destination(const int64_t* idx, long long n_src, long long n_dst, void* ws, const unsigned** perm,
-                               const unsigned** seg, cudaStream_t s) {
+                               const unsigned** seg, cudaStream_t s, long long* err) {
   const SortPlan sp = sort_plan(n_dst, n_src);
   char* base = static_cast<char*>(ws);
   unsigned* keys[2] = {reinterpret_cast<unsigned*>(base + sp.off_keys[0]),
@@ -439,9 +457,9 @@ static int sort_by_destination(const int64_t* idx, long long n_src, long long n_
 #define RP(B)                                                                                                     \
   case B:                                                                                                         \
     st = pass == 0 ? radix_pass<B, true>(nullptr, nullptr, idx, n_dst, keys[0], vals[0], n_src, shift, hist,      \
-                                         (int)sp.nblocks, scan_ws, s)                                             \
+                                         (int)sp.nblocks, scan_ws, s, err)                                        \
                    : radix_pass<B, false>(keys[cur], vals[cur], idx, n_dst, keys[cur ^ 1], vals[cur ^ 1], n_src,  \
-                                          shift, hist, (int)sp.nblocks, scan_ws, s);                              \
+                                          shift, hist, (int)sp.nblocks, scan_ws, s, nullptr);                     \
     break;
       RP(4) RP(5) RP(6) RP(7) RP(8)
 #undef RP
@@ -521,13 +539,14 @@ __global__ void __launch_bounds__(256) scatter_fold_cols_kernel(typename FV<V>::
 }
 
 int launch_scatter_add_cols(float* dx, long long rows, long long n_dst, const float* dy, const int64_t* idx,
-                            long long n_src, void* workspace, size_t ws_bytes, cudaStream_t s, const float* scale) {
+                            long long n_src, void* workspace, size_t ws_bytes, cudaStream_t s, const float* scale,
+                            long long* err) {
   if (rows * n_dst == 0) return YOTA_OK;
   if (n_src >= (1ll << 32) - 1 || n_dst >= (1ll << 32) - 2)
     YOTA_FAIL(YOTA_E_SHAPE, "scatter-add: more than 2^32 sources/destinations are not supported");
   if (ws_bytes < scatter_cols_workspace_bytes(n_dst, n_src)) YOTA_FAIL(YOTA_E_ARG, "scatter-add: workspace too small");
   const unsigned *perm, *seg;
-  YOTA_TRY(sort_by_destination(idx, n_src, n_dst, workspace, &perm, &seg, s));
+  YOTA_TRY(sort_by_destination(idx, n_src, n_dst, workspace, &perm, &seg, s, err));
   const bool v4 = (rows % 4 == 0) && ((reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(dy)) % 16 == 0);
   if (v4) {
     const int RV = (int)(rows / 4);
@@ -609,7 +628,7 @@ size_t ungetindex_workspace_bytes(const IndexSpec& sp) {
 }
 
 int launch_ungetindex(const IndexSpec& sp, float* dx, const float* dy, void* workspace, size_t ws_bytes, int sm_count,
-                      cudaStream_t s, const float* scale) {
+                      cudaStream_t s, const float* scale, long long* err) {
   (void)sm_count;
   long long n_x = 1;
   for (int d = 0; d < sp.n; d++) n_x *= sp.xdims[d];
@@ -624,7 +643,7 @@ int launch_ungetindex(const IndexSpec& sp, float* dx, const float* dy, void* wor
   // fast path: dx[:, idx] += dy on a matrix
   if (sp.n == 2 && sp.kind[0] == YOTA_IDX_COLON && vec_dim == 1)
     return launch_scatter_add_cols(dx, sp.xdims[0], sp.xdims[1], dy, sp.vec[1], sp.vlen[1], workspace, ws_bytes, s,
-                                   scale);
+                                   scale, err);
   if (scale) YOTA_FAIL(YOTA_E_ARG, "internal: scaled source planned for a general ungetindex");
   UngetParams p{};
   p.nd = sp.n;
@@ -653,7 +672,8 @@ int launch_ungetindex(const IndexSpec& sp, float* dx, const float* dy, void* wor
   }
   if (vec_dim >= 0) {
     if (ws_bytes < ungetindex_workspace_bytes(sp)) YOTA_FAIL(YOTA_E_ARG, "ungetindex: workspace too small");
-    YOTA_TRY(sort_by_destination(sp.vec[vec_dim], sp.vlen[vec_dim], sp.xdims[vec_dim], workspace, &p.perm, &p.seg, s));
+    YOTA_TRY(sort_by_destination(sp.vec[vec_dim], sp.vlen[vec_dim], sp.xdims[vec_dim], workspace, &p.perm, &p.seg, s,
+                                 err));
   }
   ungetindex_generic_kernel<<<grid_for(n_x, 256), 256, 0, s>>>(p, dx, dy, n_x);
   YOTA_CUDA(cudaGetLastError());

@@ -52,6 +52,7 @@ struct TInfo {
   std::vector<int> consumers;
   int alias_of = -1;  // tensor whose storage this one shares: RESHAPE outputs, contiguous getindex slices
   long long alias_elem_off = 0;  // ... starting this many elements into it
+  bool inplace_alias = false;    // alias made by an in-place accumulation: the whole buffer, rewritten
   bool needed = false;
   bool materialized = false;
   int region = -1;  // region index if produced by a fused EW op
@@ -144,9 +145,19 @@ struct yota_program {
     int first_step = -1, last_step = -1;
   };
   std::vector<Shadow> shadows;
+  int shadow_elem_bytes = 2;  // BF16 operand shadows (2) or the Float32 lo shadows of the 3xTF32 mode (4)
   std::vector<Shadow> tshadows;  // transposed Float32 copies written by GEMM epilogues (TF32 mode)
   std::vector<int> allreduce_slots;
   std::vector<cudaEvent_t> ar_events;
+  // where the caller-owned output buffers are touched, and which reductions follow which step
+  // (plan_comm; rebuilt after yota_program_set_allreduce)
+  struct CommPlan {
+    bool valid = false;
+    std::vector<long long> out_bytes, in_bytes;      // per out / in slot
+    std::vector<std::vector<int>> first_touch_at;    // per step: out slots first touched there
+    std::vector<std::vector<int>> ar_at;             // per step: all-reduced slots complete after it
+    size_t last_ar_step = 0;
+  } comm;
   // update!(x, gx) folded into the run (yota_program_set_update): param input slot, grad output slot
   std::vector<std::pair<int, int>> updates;
   float update_lr = 1.f;
@@ -161,6 +172,11 @@ static long long prod(const long long* d, int a, int b) {
 }
 
 static bool is_ew(int opcode) { return opcode >= YOTA_EW_COPY && opcode <= YOTA_EW__LAST; }
+
+// contraction mode of a program: 0 strict-FP32 FFMA, 1 TF32, 2 BF16, 3 compensated 3xTF32
+static int gemm_mode_of(uint32_t flags) {
+  return (flags & YOTA_FLAG_GEMM_TF32X3) ? 3 : (flags & YOTA_FLAG_GEMM_TF32) ? 1 : (flags & YOTA_FLAG_GEMM_BF16) ? 2 : 0;
+}
 
 static int root_of(const yota_program& P, int t) {
   while (P.T[t].alias_of >= 0) t = P.T[t].alias_of;
@@ -542,7 +558,14 @@ static bool try_inplace_accumulate(yota_program& P, Fuser& F, int add_op) {
     if (ta.alias_of >= 0) continue;
     if (!same_dims(ta, out.dims, out.nd) || !same_dims(tb, out.dims, out.nd)) continue;
     if (count_needed_consumers(P, a) != 1 || count_needed_consumers(P, b) != 1) continue;
-    // b's buffer must not be visible through another alias that is still read elsewhere
+    // b's buffer must not be visible through another alias that is still read elsewhere: b is
+    // its own root, or the end of a chain of earlier in-place accumulations (each link the whole
+    // buffer, its only reader the add that replaced it).  A view of a larger or shared array
+    // (x[:, :, t] of a saved activation, a reshape) is never accumulated into: the array's other
+    // readers -- a later pullback region recomputing 1 - H^2 -- would see the sums.
+    bool chain_ok = true;
+    for (int t = b; P.T[t].alias_of >= 0; t = P.T[t].alias_of) chain_ok = chain_ok && P.T[t].inplace_alias;
+    if (!chain_ok) continue;
     const int rb = root_of(P, b);
     if (P.T[rb].d.kind != YOTA_T_TEMP) continue;
     const yota_op_desc& pa = P.ops[ta.producer];
@@ -568,6 +591,7 @@ static bool try_inplace_accumulate(yota_program& P, Fuser& F, int add_op) {
     P.T[rb].materialized = true;
     P.T[a].materialized = false;
     out.alias_of = b;
+    out.inplace_alias = true;
     out.def_step = st;
     out.materialized = true;
     return true;
@@ -958,22 +982,27 @@ static void gemm_dims(const yota_program& P, const yota_op_desc& o, long long* M
 // BF16 mode: every tensor-core-eligible GEMM reads BF16 shadows of its Float32 operands.  A
 // shadow is cast once (by the first GEMM step that needs it) and shared by all later GEMMs of
 // the same tensor (H_l feeds the forward and the dW GEMM, ΔZ_l the dW and dH GEMMs, ...).
+// 3xTF32 mode: the same machinery plans the Float32 lo shadows  x - tf32(x)  (4 bytes per element,
+// made by launch_split_tf32 before the first GEMM that reads the tensor).
 static int plan_bf16_shadows(yota_program& P) {
-  if (!(P.flags & YOTA_FLAG_GEMM_BF16)) return YOTA_OK;
-  const bool in_epilogue = !(P.flags & YOTA_FLAG_NO_FUSE) && !getenv("YOTA_NO_EPI_SHADOW");
+  const int mode = gemm_mode_of(P.flags);
+  if (mode != 2 && mode != 3) return YOTA_OK;
+  P.shadow_elem_bytes = mode == 2 ? 2 : 4;
+  const bool in_epilogue = mode == 2 && !(P.flags & YOTA_FLAG_NO_FUSE) && !getenv("YOTA_NO_EPI_SHADOW");
   std::map<int, int> shadow_of;
   for (size_t s = 0; s < P.steps.size(); s++) {
     Step& st = P.steps[s];
     if (st.kind != STEP_GEMM) continue;
     const yota_op_desc& o = P.ops[st.op];
     GemmArgs g{};
-    g.mode = 2;
+    g.mode = mode;
     g.transA = (int)o.iattr[0];
     g.transB = (int)o.iattr[1];
     gemm_dims(P, o, &g.M, &g.N, &g.K, &g.lda, &g.ldb);
     if (!gemm_tc_eligible(g)) continue;
     for (int j = 0; j < 2; j++) {
       const int root = root_of(P, o.in[j]);
+      if (mode == 3 && (P.T[root].numel & 3)) continue;  // (never: eligible dims are multiples of 8)
       auto it = shadow_of.find(root);
       if (it == shadow_of.end()) {
         yota_program::Shadow sh;
@@ -1111,7 +1140,7 @@ static int plan_memory(yota_program& P) {
   for (int s = 0; s < ns; s++) {
     Step& st = P.steps[s];
     for (auto& sh : P.shadows)
-      if (sh.first_step == s) sh.arena_off = (long long)fl.alloc((size_t)P.T[sh.tensor].numel * 2);
+      if (sh.first_step == s) sh.arena_off = (long long)fl.alloc((size_t)P.T[sh.tensor].numel * P.shadow_elem_bytes);
     for (auto& sh : P.tshadows)
       if (sh.first_step == s) sh.arena_off = (long long)fl.alloc((size_t)P.T[sh.tensor].numel * 4);
     for (int t : defs[s]) P.T[t].arena_off = (long long)fl.alloc((size_t)P.T[t].numel * elem_size(P.T[t]));
@@ -1131,7 +1160,7 @@ static int plan_memory(yota_program& P) {
     for (int t : frees[s]) fl.release((size_t)P.T[t].arena_off, (size_t)P.T[t].numel * elem_size(P.T[t]));
     for (auto& w : ws_frees[s]) fl.release(w.first, w.second);
     for (auto& sh : P.shadows)
-      if (sh.last_step == s) fl.release((size_t)sh.arena_off, (size_t)P.T[sh.tensor].numel * 2);
+      if (sh.last_step == s) fl.release((size_t)sh.arena_off, (size_t)P.T[sh.tensor].numel * P.shadow_elem_bytes);
     for (auto& sh : P.tshadows)
       if (sh.last_step == s) fl.release((size_t)sh.arena_off, (size_t)P.T[sh.tensor].numel * 4);
   }
@@ -1293,7 +1322,7 @@ static int plan_gather_fusion(yota_program& P) {
 // + db), the region runs inside the GEMM's epilogue and the GEMM output never touches HBM.
 static int plan_gemm_epilogues(yota_program& P) {
   if (P.flags & YOTA_FLAG_NO_FUSE) return YOTA_OK;
-  const int mode = (P.flags & YOTA_FLAG_GEMM_TF32) ? 1 : (P.flags & YOTA_FLAG_GEMM_BF16) ? 2 : 0;
+  const int mode = gemm_mode_of(P.flags);
   if (mode == 0 || getenv("YOTA_NO_EPILOGUE")) return YOTA_OK;
   for (size_t si = 0; si < P.steps.size(); si++) {
     Step& gs = P.steps[si];
@@ -1575,6 +1604,7 @@ static int bind_region(yota_program& P, Region& r, RegionLaunch& L) {
       L.p.in[q].ptr = static_cast<const float*>(tensor_ptr(P, r.gather_x[q]));
       L.p.in[q].idx = static_cast<const long long*>(tensor_ptr(P, r.gather_idx[q]));
       L.p.in[q].gather_n = P.T[r.gather_x[q]].d.dims[1];
+      L.p.in[q].err = P.ctx->err_dev;
     } else
       L.p.in[q].ptr = static_cast<const float*>(tensor_ptr(P, r.in_tensors[q]));
     if (L.V == 4 && (reinterpret_cast<uintptr_t>(L.p.in[q].ptr) & 15) &&
@@ -1676,24 +1706,32 @@ static int run_step(yota_program& P, Step& st, cudaStream_t s) {
       g.C = out;
       g.ldc = g.M;
       g.accumulate = st.acc_tensor >= 0 ? 1 : 0;
-      g.mode = (P.flags & YOTA_FLAG_GEMM_TF32) ? 1 : (P.flags & YOTA_FLAG_GEMM_BF16) ? 2 : 0;
-      if (g.mode == 2 && st.shadow[0] >= 0) {
-        const void* src[2] = {g.A, g.B};
+      g.mode = gemm_mode_of(P.flags);
+      if ((g.mode == 2 || g.mode == 3) && st.shadow[0] >= 0) {
         void* sh[2];
         for (int j = 0; j < 2; j++) {
           char* base = P.arena + P.shadows[st.shadow[j]].arena_off;  // shadow of the whole root array
           if (st.cast[j]) {
             const int root = root_of(P, o.in[j]);
-            YOTA_TRY(launch_cast_bf16(base, static_cast<const float*>(root_ptr(P, root)), P.T[root].numel, s));
+            const float* src = static_cast<const float*>(root_ptr(P, root));
+            if (g.mode == 2)
+              YOTA_TRY(launch_cast_bf16(base, src, P.T[root].numel, s));
+            else
+              YOTA_TRY(launch_split_tf32(reinterpret_cast<float*>(base), src, P.T[root].numel, s));
           }
-          sh[j] = base + alias_offset(P, o.in[j]) * 2;
+          sh[j] = base + alias_offset(P, o.in[j]) * P.shadow_elem_bytes;
         }
-        (void)src;
-        g.A = sh[0];
-        g.B = sh[1];
+        if (g.mode == 2) {
+          g.A = sh[0];
+          g.B = sh[1];
+        } else {
+          g.A_lo = sh[0];
+          g.B_lo = sh[1];
+        }
         if (st.epi_region >= 0) return run_gemm_epilogue(P, st, g, s);
         return launch_gemm_tc(P.ctx, g, s);
       }
+      if (g.mode == 2 || g.mode == 3) g.mode = 0;  // not tile-aligned: no shadows were planned, strict-FP32 kernel
       if (st.epi_region >= 0) return run_gemm_epilogue(P, st, g, s);
       if (g.mode == 1) {  // operands with a transposed copy are read K-major from it
         if (st.tsh_use[0] >= 0) {
@@ -1726,11 +1764,11 @@ static int run_step(yota_program& P, Step& st, cudaStream_t s) {
       for (int d = 0; d < sp.n; d++)
         if (sp.kind[d] == YOTA_IDX_VEC)
           sp.vec[d] = static_cast<const int64_t*>(tensor_ptr(P, o.in[1 + (int)sp.a[d]]));
-      if (st.kind == STEP_GETINDEX) return launch_getindex(sp, out, in0, ot.numel, s);
+      if (st.kind == STEP_GETINDEX) return launch_getindex(sp, out, in0, ot.numel, s, P.ctx->err_dev);
       const float* scale =
           P.op_scale[st.op] >= 0 ? static_cast<const float*>(tensor_ptr(P, P.op_scale[st.op])) : nullptr;
       return launch_ungetindex(sp, out, in0, st.ws_off >= 0 ? P.arena + st.ws_off : nullptr, st.ws_bytes,
-                               P.ctx->sm_count, s, scale);
+                               P.ctx->sm_count, s, scale, P.ctx->err_dev);
     }
     case STEP_LOGSOFTMAX: {
       const TInfo& x = P.T[o.in[0]];
@@ -1811,23 +1849,84 @@ struct Timeline {
   }
 };
 
+// out slot whose caller-owned buffer tensor t lives in (-1: program-owned or an input)
+static int out_slot_of(const yota_program& P, int t) {
+  const TInfo& r = P.T[root_of(P, t)];
+  return r.d.kind == YOTA_T_OUTPUT ? r.d.slot : r.fwd_out_slot;
+}
+
+// Which step first / last touches every output buffer.  A reduction is issued after the LAST
+// step that reads or writes the buffer (a later step may still read an output: two parameters
+// sharing one tangent, an output consumed by later ops); the first touch is where a run must
+// wait for a reduction of the same buffer left in flight by the previous run.
+static int plan_comm(yota_program& P) {
+  yota_program::CommPlan& C = P.comm;
+  if (C.valid) return YOTA_OK;
+  const size_t ns = P.steps.size();
+  C.out_bytes.assign(P.n_out, 0);
+  C.in_bytes.assign(P.n_in, 0);
+  for (auto& t : P.T) {
+    const long long b = t.numel * (t.d.dtype == YOTA_I64 ? 8 : 4);
+    if (t.d.kind == YOTA_T_OUTPUT && t.d.slot >= 0 && t.d.slot < P.n_out) C.out_bytes[t.d.slot] = std::max(C.out_bytes[t.d.slot], b);
+    if (t.d.kind == YOTA_T_INPUT && t.d.slot >= 0 && t.d.slot < P.n_in) C.in_bytes[t.d.slot] = std::max(C.in_bytes[t.d.slot], b);
+  }
+  std::vector<int> first(P.n_out, -1), last(P.n_out, -1);
+  auto touch = [&](size_t q, int t) {
+    const int slot = out_slot_of(P, t);
+    if (slot < 0 || slot >= P.n_out) return;
+    if (first[slot] < 0) first[slot] = (int)q;
+    last[slot] = (int)q;
+  };
+  for (size_t q = 0; q < ns; q++) {
+    const Step& st = P.steps[q];
+    if (st.kind == STEP_NOP) continue;
+    for (int t : st.reads) touch(q, t);
+    for (int t : st.writes) touch(q, t);
+    if (st.out_tensor >= 0) touch(q, st.out_tensor);
+    if (st.op >= 0 && st.kind != STEP_ROWSUM_FINISH && st.kind != STEP_SCALAR_FINISH) {
+      const yota_op_desc& o = P.ops[st.op];
+      for (int j = 0; j < o.n_in; j++) touch(q, o.in[j]);
+      touch(q, st.out_override >= 0 ? st.out_override : o.out);
+    }
+  }
+  C.first_touch_at.assign(ns, {});
+  C.ar_at.assign(ns, {});
+  for (int slot = 0; slot < P.n_out; slot++)
+    if (first[slot] >= 0) C.first_touch_at[first[slot]].push_back(slot);
+  C.last_ar_step = 0;
+  for (int slot : P.allreduce_slots) {
+    if (last[slot] < 0)
+      YOTA_FAIL(YOTA_E_ARG, "all-reduce marked for output slot %d, which no step of the program writes", slot);
+    C.ar_at[last[slot]].push_back(slot);
+    C.last_ar_step = std::max(C.last_ar_step, (size_t)last[slot]);
+  }
+  C.valid = true;
+  return YOTA_OK;
+}
+
+static int env_int_p(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
 static int run_all_steps(yota_program& P, cudaStream_t s, bool with_comm, Timeline* tl = nullptr) {
-  // which step last writes each all-reduced output
-  std::vector<std::vector<int>> ar_at(P.steps.size());
+  yota_ctx* ctx = P.ctx;
   struct ReserveGuard {  // the SM reservation never outlives this sweep, error paths included
     yota_ctx* c;
     ~ReserveGuard() { c->sm_reserved = 0; }
-  } guard{P.ctx};
-  P.ctx->sm_reserved = 0;
-  if (with_comm) {
-    for (int slot : P.allreduce_slots) {
-      int last = -1;
-      for (size_t q = 0; q < P.steps.size(); q++)
-        for (int t : P.steps[q].writes)
-          if (P.T[t].d.kind == YOTA_T_OUTPUT && P.T[t].d.slot == slot) last = (int)q;
-      if (last >= 0) ar_at[last].push_back(slot);
-    }
-  }
+  } guard{ctx};
+  ctx->sm_reserved = 0;
+  YOTA_TRY(plan_comm(P));
+  const yota_program::CommPlan& C = P.comm;
+  // Reductions of an earlier run may still be in flight (the previous eval's tail buckets overlap
+  // this forward sweep): order this run behind the ones that touch its buffers, and leave their
+  // CTAs some SMs during the first GEMMs.
+  const bool inherited = !ctx->pending_ar.empty();
+  if (inherited)
+    for (int i = 0; i < P.n_in; i++) YOTA_TRY(ctx_wait_pending(ctx, P.bound_in[i], (size_t)C.in_bytes[i], s));
+  int head_gemms = inherited && with_comm ? env_int_p("YOTA_AR_HEAD_RESERVE", 3) : 0;
+  const int reserve = with_comm ? comm_reserved_sms(ctx) : 0;
+  bool in_flight = false;
   size_t ev = 0;
   // Buckets: outputs finished by a step wait until at least kBucketBytes are pending (a
   // layer's 16 KiB bias gradient rides with the next weight gradient instead of paying a
@@ -1836,63 +1935,58 @@ static int run_all_steps(yota_program& P, cudaStream_t s, bool with_comm, Timeli
   std::vector<float*> pend_buf;
   std::vector<long long> pend_n;
   long long pend_bytes = 0;
-  size_t last_ar_step = 0;
-  for (size_t q = 0; q < P.steps.size(); q++)
-    if (!ar_at[q].empty()) last_ar_step = q;
   for (size_t q = 0; q < P.steps.size(); q++) {
-    if (tl && P.steps[q].kind != STEP_NOP) YOTA_TRY(tl->open(P.steps[q].label, s));
-    YOTA_TRY(run_step(P, P.steps[q], s));
-    if (tl && P.steps[q].kind != STEP_NOP) YOTA_TRY(tl->close(s));
-    if (with_comm && !ar_at[q].empty()) {
-      for (int slot : ar_at[q]) {
-        long long n = 0;
-        for (auto& t : P.T)
-          if (t.d.kind == YOTA_T_OUTPUT && t.d.slot == slot) n = t.numel;
+    Step& st = P.steps[q];
+    if (!ctx->pending_ar.empty())
+      for (int slot : C.first_touch_at[q])
+        YOTA_TRY(ctx_wait_pending(ctx, P.bound_out[slot], (size_t)C.out_bytes[slot], s));
+    if (st.kind == STEP_GEMM) {
+      ctx->sm_reserved = (in_flight || head_gemms > 0) ? reserve : 0;
+      if (head_gemms > 0) head_gemms--;
+    }
+    if (tl && st.kind != STEP_NOP) YOTA_TRY(tl->open(st.label, s));
+    YOTA_TRY(run_step(P, st, s));
+    if (tl && st.kind != STEP_NOP) YOTA_TRY(tl->close(s));
+    if (with_comm && !C.ar_at[q].empty()) {
+      for (int slot : C.ar_at[q]) {
         pend_buf.push_back(static_cast<float*>(P.bound_out[slot]));
-        pend_n.push_back(n);
-        pend_bytes += n * 4;
+        pend_n.push_back(C.out_bytes[slot] / 4);
+        pend_bytes += C.out_bytes[slot];
       }
-      if (pend_bytes < kBucketBytes && q != last_ar_step) continue;
+      if (pend_bytes < kBucketBytes && q != C.last_ar_step) continue;
       // all-reduce the bucket on the comm stream while the compute stream continues with the
-      // rest of the pullback sweep
+      // rest of the pullback sweep -- and, for the last buckets, with the next eval
       if (ev >= P.ar_events.size()) {
         cudaEvent_t e;
         YOTA_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         P.ar_events.push_back(e);
       }
       YOTA_CUDA(cudaEventRecord(P.ar_events[ev], s));
-      YOTA_CUDA(cudaStreamWaitEvent(P.ctx->comm_stream, P.ar_events[ev], 0));
+      YOTA_CUDA(cudaStreamWaitEvent(ctx->comm_stream, P.ar_events[ev], 0));
       ev++;
       if (tl)
         YOTA_TRY(tl->open("allreduce " + std::to_string(pend_bytes) + " B (" + std::to_string(pend_buf.size()) +
                               " buffers) after step " + std::to_string(q),
-                          P.ctx->comm_stream));
-      YOTA_TRY(comm_allreduce_bucket(P.ctx, pend_buf.data(), pend_n.data(), (int)pend_buf.size(), P.ctx->comm_stream));
-      if (tl) YOTA_TRY(tl->close(P.ctx->comm_stream));
+                          ctx->comm_stream));
+      YOTA_TRY(comm_allreduce_bucket(ctx, pend_buf.data(), pend_n.data(), (int)pend_buf.size(), ctx->comm_stream));
+      if (tl) YOTA_TRY(tl->close(ctx->comm_stream));
+      std::vector<std::pair<const char*, const char*>> ranges;
+      for (size_t b = 0; b < pend_buf.size(); b++)
+        ranges.push_back({reinterpret_cast<const char*>(pend_buf[b]), reinterpret_cast<const char*>(pend_buf[b] + pend_n[b])});
+      YOTA_TRY(ctx_add_pending(ctx, ranges));
       pend_buf.clear();
       pend_n.clear();
       pend_bytes = 0;
-      // from here on reductions are in flight beside the sweep: leave their CTAs some SMs
-      P.ctx->sm_reserved = comm_reserved_sms(P.ctx);
+      in_flight = true;  // from here on reductions run beside the sweep: leave their CTAs some SMs
     }
   }
-  P.ctx->sm_reserved = 0;
-  if (with_comm && ev > 0) {
-    // the compute stream (and therefore yota_d2h / yota_sync) waits for the reductions
-    if (ev >= P.ar_events.size()) {
-      cudaEvent_t e;
-      YOTA_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-      P.ar_events.push_back(e);
-    }
-    YOTA_CUDA(cudaEventRecord(P.ar_events[ev], P.ctx->comm_stream));
-    YOTA_CUDA(cudaStreamWaitEvent(s, P.ar_events[ev], 0));
-  }
+  ctx->sm_reserved = 0;
+  if (with_comm && getenv("YOTA_AR_JOIN")) YOTA_TRY(ctx_join_comm(ctx, s));  // A/B: the round-1 behaviour
   // update!(param, grad) for the marked pairs: after every reader of the parameter in this sweep
   // and after its gradient has been summed over ranks (src/update.jl:42-49, x .= x .- lr .* gx)
   for (auto& u : P.updates) {
-    long long n = 0;
-    for (auto& t : P.T)
-      if (t.d.kind == YOTA_T_OUTPUT && t.d.slot == u.second) n = t.numel;
+    const long long n = C.out_bytes[u.second] / 4;
+    YOTA_TRY(ctx_wait_pending(ctx, P.bound_out[u.second], (size_t)n * 4, s));
     if (tl) YOTA_TRY(tl->open("update! input " + std::to_string(u.first), s));
     YOTA_TRY(launch_axpy(static_cast<float*>(P.bound_in[u.first]), static_cast<const float*>(P.bound_out[u.second]), n,
                          P.update_lr, s));
@@ -1943,20 +2037,13 @@ extern "C" int yota_program_run(yota_program* p, void* const* in_ptrs, int64_t n
   YOTA_TRY(set_seed(P, seed));
   cudaStream_t s = P.ctx->stream;
   const bool with_comm = !P.allreduce_slots.empty() && P.ctx->nccl_comm;
-  // With reductions in the sweep the run is issued eagerly.  Experimental (YOTA_GRAPH_COMM=1, not
-  // yet validated on hardware): when every reduced output lives in symmetric memory the
-  // reductions are the library's own kernels and the two-stream sweep can be captured as well.
-  bool graph_comm = with_comm && getenv("YOTA_GRAPH_COMM") != nullptr;
-  if (graph_comm)
-    for (int slot : P.allreduce_slots) {
-      long long n = 0;
-      for (auto& t : P.T)
-        if (t.d.kind == YOTA_T_OUTPUT && t.d.slot == slot) n = t.numel;
-      graph_comm = graph_comm && symm_contains(P.ctx, P.bound_out[slot], (size_t)n * 4);
-    }
-  const bool use_graph = !(P.flags & YOTA_FLAG_NO_GRAPH) && (!with_comm || graph_comm);
+  // With reductions in the sweep the run is issued eagerly: a captured graph would have to join
+  // the communication stream before it ends, and the next launch would then wait for this eval's
+  // last reductions instead of overlapping them with its forward sweep (run_all_steps).
+  const bool use_graph = !(P.flags & YOTA_FLAG_NO_GRAPH) && !with_comm;
   (void)changed;
   if (!use_graph) return run_all_steps(P, s, with_comm);
+  YOTA_TRY(ctx_join_comm(P.ctx, s));  // a replayed graph carries no waits for reductions left in flight
   // one graph per pointer binding: eager on the first run with a binding (also the warm-up
   // that sets function attributes), captured on the second, replayed afterwards
   yota_program::GraphEntry* ge = nullptr;
@@ -2008,6 +2095,7 @@ extern "C" int yota_program_profile(yota_program* p, void* const* in_ptrs, int64
   YOTA_TRY(bind(P, in_ptrs, n_in, out_ptrs, n_out, &changed));
   YOTA_TRY(set_seed(P, seed));
   cudaStream_t s = P.ctx->stream;
+  YOTA_TRY(ctx_join_comm(P.ctx, s));
   const size_t n = P.steps.size();
   std::vector<cudaEvent_t> ev(n + 1);
   for (auto& e : ev) YOTA_CUDA(cudaEventCreate(&e));
@@ -2059,6 +2147,7 @@ extern "C" int yota_program_timeline(yota_program* p, void* const* in_ptrs, int6
   YOTA_CUDA(cudaEventRecord(end, s));
   YOTA_CUDA(cudaStreamSynchronize(s));
   YOTA_CUDA(cudaStreamSynchronize(P.ctx->comm_stream));
+  YOTA_TRY(ctx_join_comm(P.ctx, s));
   std::string nm;
   int64_t n = 0;
   for (auto& r : tl.recs) {
@@ -2122,8 +2211,14 @@ extern "C" int yota_program_set_update(yota_program* p, const int32_t* in_slots,
 extern "C" int yota_program_set_allreduce(yota_program* p, const int32_t* out_slots, int64_t n) {
   if (!p) YOTA_FAIL(YOTA_E_ARG, "null program");
   p->allreduce_slots.assign(out_slots, out_slots + n);
+  p->comm.valid = false;
   for (int s : p->allreduce_slots)
     if (s < 0 || s >= p->n_out) YOTA_FAIL(YOTA_E_ARG, "yota_program_set_allreduce: bad out slot %d", s);
+  if (plan_comm(*p) != YOTA_OK) {  // an all-reduced slot that no step writes
+    p->allreduce_slots.clear();
+    p->comm.valid = false;
+    return YOTA_E_ARG;
+  }
   for (auto& g : p->graphs)
     if (g.exec) cudaGraphExecDestroy(g.exec);
   p->graphs.clear();

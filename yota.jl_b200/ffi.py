@@ -77,6 +77,7 @@ SYMBOLS = {
 }
 
 FLAG_NO_FUSE, FLAG_NO_GRAPH, FLAG_GEMM_TF32, FLAG_GEMM_BF16, FLAG_NO_STATIC = 0x1, 0x2, 0x10, 0x20, 0x40
+FLAG_GEMM_TF32X3 = 0x80
 
 _lib = None
 
