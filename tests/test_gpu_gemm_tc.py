@@ -168,23 +168,28 @@ def test_tensor_core_truncates_float32_to_tf32():
 @pytest.mark.parametrize("tA,tB", [(0, 0), (0, 1), (1, 0), (1, 1)])
 def test_tf32x3_meets_the_fp32_tolerance(tA, tB):
     """Random data at every tile width (1-CTA 128 x 32 ... 256, and the 2-CTA kernel at the last
-    shape): the error against Float64 is that of an FP32 dot product, not of TF32 -- gated at
-    4e-6 * (|A| |B|) (TF32 alone: ~1e-3), next to the strict-FP32 FFMA kernel on the same data."""
+    shapes): the error against Float64, relative to max|result|, is that of an FP32 dot product
+    (<= 1e-5, the reference's rtol; plain TF32: ~1e-3) -- also for all-positive data at K = 8192,
+    where the tensor core's truncating accumulation would otherwise bias the sum by ~1e-4 (the
+    kernel hands the accumulator to the CUDA cores every 256 K-elements for that reason)."""
     r = cases.rng(25)
-    for m, n, k in [(128, 128, 32), (1024, 128, 1024), (384, 640, 160), (512, 768, 1024), (2048, 2560, 512)]:
-        A = r.standard_normal((k, m) if tA else (m, k)).astype(F32)
-        B = r.standard_normal((n, k) if tB else (k, n)).astype(F32)
-        a, b = (A.T if tA else A).astype(np.float64), (B.T if tB else B).astype(np.float64)
-        ref = a @ b
-        bound = np.abs(a) @ np.abs(b)
-        got = U.gemm(3, tA, tB, np.asfortranarray(A), np.asfortranarray(B))
-        e3 = float(np.max(np.abs(got - ref) / bound))
-        ffma = U.gemm(0, tA, tB, np.asfortranarray(A), np.asfortranarray(B))
-        e0 = float(np.max(np.abs(ffma - ref) / bound))
-        assert e3 <= 4e-6, (m, n, k, e3, e0)
-        C0 = np.asfortranarray(r.standard_normal((m, n)).astype(F32))
-        got = U.gemm(3, tA, tB, np.asfortranarray(A), np.asfortranarray(B), C0)
-        assert float(np.max(np.abs(got - (ref + C0)) / (bound + np.abs(C0)))) <= 4e-6
+    shapes = [(128, 128, 32), (1024, 128, 1024), (384, 640, 160), (512, 768, 1024), (2048, 2560, 512), (1024, 1280, 8192)]
+    for m, n, k in shapes:
+        for positive in (False, True):
+            gen = (lambda sh: r.random(sh)) if positive else (lambda sh: r.standard_normal(sh))
+            A = gen((k, m) if tA else (m, k)).astype(F32)
+            B = gen((n, k) if tB else (k, n)).astype(F32)
+            a, b = (A.T if tA else A).astype(np.float64), (B.T if tB else B).astype(np.float64)
+            ref = a @ b
+            scale = float(np.abs(ref).max())
+            got = U.gemm(3, tA, tB, np.asfortranarray(A), np.asfortranarray(B))
+            e3 = float(np.abs(got - ref).max()) / scale
+            ffma = U.gemm(0, tA, tB, np.asfortranarray(A), np.asfortranarray(B))
+            e0 = float(np.abs(ffma - ref).max()) / scale
+            assert e3 <= max(1e-5, 3 * e0), (m, n, k, positive, e3, e0)
+            C0 = np.asfortranarray(gen((m, n)).astype(F32))
+            got = U.gemm(3, tA, tB, np.asfortranarray(A), np.asfortranarray(B), C0)
+            assert float(np.abs(got - (ref + C0)).max()) / scale <= max(1e-5, 3 * e0)
 
 
 def test_mlp_gradients_in_tf32x3_mode(force_2cta):

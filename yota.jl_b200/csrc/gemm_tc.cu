@@ -137,6 +137,14 @@ struct Params {
   int accumulate;
   int num_m, num_n;
   int spread;  // 1: lane c of the producer warp issues TMA box c; 0: lane 0 issues all boxes
+  // Compensated (3xTF32) mode only: k-blocks per accumulation chunk.  The tensor core adds every
+  // MMA's partial sum into the FP32 accumulator with truncation, a bias that grows with the number
+  // of accumulations (measured: 1.7e-4 of max|g| at K = 8192 x 3 products).  The accumulator is
+  // therefore handed to the epilogue warps every `kchunk` k-blocks and added to C in the L2 with
+  // round-to-nearest (red.global.add.f32; the tile stays in L2 between chunks), so the truncation
+  // bias is bounded by the chunk length instead of K.
+  int kchunk;
+  int pace_ns;  // X3: pause of the epilogue warps after each 32-column slice of a chunk's drain
   // fused epilogue: store output `tsh_out` of the chain a second time, transposed (element (m, n)
   // at tsh[n + m * tsh_ld]): the K-major operand of the dW GEMM that would otherwise read this
   // tensor MN-major (see plan_transposed_shadows in program.cu)
@@ -283,11 +291,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int kc = X3 ? p.kchunk : nkb;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x)
+       for (int ch = 0; ch < (X3 ? (nkb + kc - 1) / kc : 1); ch++) {  // one accumulator per chunk of k-blocks (X3) / per tile
+        const int kb0 = X3 ? ch * kc : 0;
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * TN;
-        for (int kb = 0; kb < nkb; kb++) {
+        const int kend = kb0 + kc < nkb ? kb0 + kc : nkb;
+        for (int kb = kb0; kb < kend; kb++) {
           mbar_wait(&full[stage], phase);
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
@@ -299,9 +311,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const uint64_t db = B_MN ? make_desc(sb + k * E::MN_KSTEP, E::CHUNK_BYTES, E::MN_SBO, E::MN_LAYOUT)
                                      : make_desc(sb + k * 32, 16, 1024, 2);
             if (EB == 4)
-              umma_tf32(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_tf32(d_tmem, da, db, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
             else
-              umma_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_f16(d_tmem, da, db, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
             if constexpr (X3) {
               const uint32_t sal = sa + S::HALF, sbl = sal + S::A_BYTES;
               const uint64_t dal = A_MN ? make_desc(sal + k * E::MN_KSTEP, E::CHUNK_BYTES, E::MN_SBO, E::MN_LAYOUT)
@@ -330,9 +342,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    const int kc = X3 ? p.kchunk : nkb;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x)
+     for (int ch = 0; ch < (X3 ? (nkb + kc - 1) / kc : 1); ch++) {
+      const int kb0 = X3 ? ch * kc : 0;
       const long long m = (long long)(t % p.num_m) * TM + q * 32 + lane;
       const long long n0 = (long long)(t / p.num_m) * TN;
+      // X3: every chunk after the first (and the first too when C += ...) is ADDED to C by the L2
+      // (red.global.add.f32: round-to-nearest, no read on the SM side; one thread owns an element,
+      // so its adds arrive in chunk order -- deterministic)
+      const bool red = X3 && (p.accumulate || kb0 > 0);
+      const bool add_old = !X3 && p.accumulate;
       mbar_wait(&tfull[acc], acc_phase);
       tcgen05_fence_after();
       float* crow = p.C + m + n0 * p.ldc;
@@ -342,7 +362,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // C += ...: the 32 old values are requested before the accumulator read, all in flight at
         // once (left inside the store loop they serialise: load -> add -> store per element)
         float old[32];
-        if (p.accumulate) {
+        if (add_old) {
           const float* cp0 = crow + (long long)(c * 32) * p.ldc;
 #pragma unroll
           for (int j = 0; j < 32; j++) old[j] = __ldcg(cp0 + j * p.ldc);
@@ -360,7 +380,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         float* cp = crow + (long long)(c * 32) * p.ldc;
-        if (p.accumulate) {
+        if (X3 && red) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) atomicAdd(cp + j * p.ldc, __uint_as_float(v[j]));
+          if (p.pace_ns) __nanosleep(p.pace_ns);
+        } else if (add_old) {
 #pragma unroll
           for (int j = 0; j < 32; j++) cp[j * p.ldc] = __uint_as_float(v[j]) + old[j];
         } else {
@@ -433,6 +457,16 @@ static int make_map(CUtensorMap* map, const void* ptr, long long mn, long long k
   return YOTA_OK;
 }
 
+// k-blocks (of 32 K-elements) per accumulation chunk of the compensated mode: 4 = 128 K-elements
+// = 48 truncating accumulations per chunk (YOTA_X3_KCHUNK overrides, in k-blocks).  Measured on
+// B200, C3 at full size against the Float64 oracle: 8 k-blocks 1.17e-5 of max|g| at 28 evals/s
+// (just over the 1e-5 gate), 4 k-blocks 7.0e-6 at 25 evals/s, 2 k-blocks 4.5e-6 at 18.6 evals/s.
+static int x3_kchunk() {
+  const char* e = getenv("YOTA_X3_KCHUNK");
+  const int v = e && *e ? atoi(e) : 4;
+  return v < 1 ? 1 : v;
+}
+
 struct Maps {
   CUtensorMap a, b, al, bl;  // al / bl: the lo shadows of the compensated mode (copies of a / b otherwise)
 };
@@ -453,6 +487,8 @@ static int launch(const GemmArgs& g, const Maps& mp, int sm_count, cudaStream_t 
   p.ldc = g.ldc;
   p.accumulate = g.accumulate;
   p.spread = getenv("YOTA_TMA_SPREAD") ? 1 : 0;
+  p.kchunk = x3_kchunk();
+  p.pace_ns = getenv("YOTA_X3_PACE_NS") ? atoi(getenv("YOTA_X3_PACE_NS")) : 0;
   p.tsh = nullptr;
   p.tsh_ld = 0;
   p.tsh_out = -1;
@@ -783,11 +819,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = pair; t < num_tiles; t += num_pairs) {
+      const int kc = X3 ? p.kchunk : nkb;
+      for (int t = pair; t < num_tiles; t += num_pairs)
+       for (int ch = 0; ch < (X3 ? (nkb + kc - 1) / kc : 1); ch++) {  // one accumulator per chunk of k-blocks (X3) / per tile
+        const int kb0 = X3 ? ch * kc : 0;
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * TN2;
-        for (int kb = 0; kb < nkb; kb++) {
+        const int kend = kb0 + kc < nkb ? kb0 + kc : nkb;
+        for (int kb = kb0; kb < kend; kb++) {
           mbar_wait(&full[stage], phase);
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
@@ -798,7 +838,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                                      : make_desc(sa + k * 32, 16, 1024, 2);
             const uint64_t db = B_MN ? make_desc(sb + k * E::MN_KSTEP, E::CHUNK_BYTES, E::MN_SBO, E::MN_LAYOUT)
                                      : make_desc(sb + k * 32, 16, 1024, 2);
-            umma_2sm<EB>(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_2sm<EB>(d_tmem, da, db, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
             if constexpr (X3) {
               const uint32_t sal = sa + S::HALF, sbl = sal + S::A_BYTES;
               const uint64_t dal = A_MN ? make_desc(sal + k * E::MN_KSTEP, E::CHUNK_BYTES, E::MN_SBO, E::MN_LAYOUT)
@@ -827,25 +867,37 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int q = warp & 3;
     int acc = 0;
     uint32_t acc_phase = 0;
+    const int kc = X3 ? p.kchunk : nkb;
     for (int t = pair; t < num_tiles; t += num_pairs) {
       const long long m = (long long)(t % p.num_m) * (2 * TM) + (long long)rank * TM + q * 32 + lane;
       const long long n0 = (long long)(t / p.num_m) * TN2;
-      mbar_wait(&tfull[acc], acc_phase);
-      tcgen05_fence_after();
       float* crow = p.C + m + n0 * p.ldc;
       using EP = Epilogue<(EPI >= 0 ? EPI : 0), ZIN>;
       float ebase[EP::NS], eaccs[EP::NO];
       if constexpr (EPI >= 0) EP::begin_tile(rp, m, ebase, eaccs);
+     for (int ch = 0; ch < (X3 ? (nkb + kc - 1) / kc : 1); ch++) {
+      const int kb0 = X3 ? ch * kc : 0;
+      // X3: the tile arrives in chunks of k-blocks; every chunk but the first is added to the
+      // partial sums in C, the fused chain runs on the complete sum (C + last chunk)
+      bool add_old = EPI < 0 && p.accumulate;
+      bool last = true, red = false;
+      if constexpr (X3) {
+        last = kb0 + kc >= nkb;
+        // chunks are ADDED to C by the L2 (red.global.add.f32, round-to-nearest, nothing read on
+        // the SM side); only the fused chain's last chunk reads the partial sums back
+        red = (EPI < 0 && p.accumulate) || kb0 > 0;
+        add_old = EPI >= 0 && last && kb0 > 0;
+      }
+      mbar_wait(&tfull[acc], acc_phase);
+      tcgen05_fence_after();
 #pragma unroll 1
       for (int c = 0; c < TN2 / 32; c++) {
         uint32_t v[32];
         float old[32];
-        if constexpr (EPI < 0) {
-          if (p.accumulate) {  // see gemm_tc_kernel: old values of C in flight before the accumulator read
-            const float* cp0 = crow + (long long)(c * 32) * p.ldc;
+        if (add_old) {  // see gemm_tc_kernel: old values of C in flight before the accumulator read
+          const float* cp0 = crow + (long long)(c * 32) * p.ldc;
 #pragma unroll
-            for (int j = 0; j < 32; j++) old[j] = __ldcg(cp0 + j * p.ldc);
-          }
+          for (int j = 0; j < 32; j++) old[j] = __ldcg(cp0 + j * p.ldc);
         }
         const uint32_t taddr = tmem_base + (uint32_t)(acc * TN2 + c * 32) + ((uint32_t)(q * 32) << 16);
         asm volatile(
@@ -859,12 +911,22 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             : "r"(taddr)
             : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if constexpr (EPI >= 0) {
-          EP::chunk32(rp, v, m, n0 + c * 32, p.M, ebase, eaccs, p.tsh, p.tsh_ld, p.tsh_out,
-                      reinterpret_cast<float4*>(smem + S::TSH_OFF) + q * 256, p.bsh, p.bsh_out);
+        if (EPI >= 0 && last) {
+          if constexpr (EPI >= 0) {
+            if (add_old) {
+#pragma unroll
+              for (int j = 0; j < 32; j++) v[j] = __float_as_uint(__uint_as_float(v[j]) + old[j]);
+            }
+            EP::chunk32(rp, v, m, n0 + c * 32, p.M, ebase, eaccs, p.tsh, p.tsh_ld, p.tsh_out,
+                        reinterpret_cast<float4*>(smem + S::TSH_OFF) + q * 256, p.bsh, p.bsh_out);
+          }
         } else {
           float* cp = crow + (long long)(c * 32) * p.ldc;
-          if (p.accumulate) {
+          if (X3 && red) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) atomicAdd(cp + j * p.ldc, __uint_as_float(v[j]));
+            if (p.pace_ns) __nanosleep(p.pace_ns);
+          } else if (add_old) {
 #pragma unroll
             for (int j = 0; j < 32; j++) cp[j * p.ldc] = __uint_as_float(v[j]) + old[j];
           } else {
@@ -873,13 +935,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           }
         }
       }
-      if constexpr (EPI >= 0) EP::end_tile(rp, m, t / p.num_m, p.M, eaccs);
+      if constexpr (EPI >= 0) {
+        if (last) EP::end_tile(rp, m, t / p.num_m, p.M, eaccs);
+      }
       tcgen05_fence_before();
       mbar_arrive_remote(&tempty[acc], 0);  // the leader's MMA warp waits for both CTAs' epilogues
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
       }
+     }
     }
   }
   tcgen05_fence_before();
@@ -907,6 +972,8 @@ static int launch2(const GemmArgs& g, const Maps& mp, int sm_count, cudaStream_t
   p.ldc = g.ldc;
   p.accumulate = g.accumulate;
   p.spread = getenv("YOTA_TMA_SPREAD") ? 1 : 0;
+  p.kchunk = x3_kchunk();
+  p.pace_ns = getenv("YOTA_X3_PACE_NS") ? atoi(getenv("YOTA_X3_PACE_NS")) : 0;
   p.tsh = g.tsh;
   p.tsh_ld = g.tsh_ld;
   p.tsh_out = g.tsh_out;

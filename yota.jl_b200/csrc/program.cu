@@ -1381,7 +1381,9 @@ static int plan_gemm_epilogues(yota_program& P) {
       gs.writes.push_back(r.out_tensors[q]);
     }
     rs.writes.clear();
-    P.T[z].materialized = false;
+    // (compensated mode: z stays in the arena for the length of this step -- the partial sums of
+    // the K-chunks are accumulated there before the chain runs on the complete sum)
+    P.T[z].materialized = mode == 3;
     // row-sum partials: one row per 256-column tile of the GEMM
     const int P_tiles = (int)(g.N / 256);
     for (size_t q = 0; q < r.sums.size(); q++) {
