@@ -113,7 +113,8 @@ def force_2cta(monkeypatch):
 @pytest.mark.parametrize("tA,tB", [(0, 0), (0, 1), (1, 0), (1, 1)])
 def test_2cta_exact_on_small_integers(force_2cta, mode, tA, tB):
     r = cases.rng(24)
-    for m, n, k in [(256, 256, 64), (512, 768, 192), (1024, 512, 320)]:
+    # (n / 256 odd: one pair per cluster; even: two pairs per cluster sharing A by TMA multicast)
+    for m, n, k in [(256, 256, 64), (512, 768, 192), (1024, 512, 320), (512, 2048, 128), (256, 1024, 2048)]:
         A = r.integers(-3, 4, size=(k, m) if tA else (m, k)).astype(F32)
         B = r.integers(-3, 4, size=(n, k) if tB else (k, n)).astype(F32)
         ref = (A.T if tA else A).astype(np.float64) @ (B.T if tB else B).astype(np.float64)

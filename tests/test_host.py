@@ -148,10 +148,10 @@ def test_planner_c3_epilogues_and_k_major_shadows(built):
     mode they write the BF16 operand shadows."""
     av = [A((4096, 4096))] * 8 + [A((4096,))] * 8 + [A((4096, 8192))] * 2
     desc, (steps, launches, ws, regions, _) = _plan(cases.make_c3(8, 8192), *av, flags=ffi.FLAG_GEMM_TF32)
-    assert desc.count("matmul + epilogue{region[add,tanh]}") == 7 and desc.count("+sum} ->") == 7, desc
-    assert desc.count("(absorbed into step") == 15
+    assert desc.count("matmul + epilogue{region[add,tanh]}") == 7 and desc.count("+sum} +finish ->") == 7, desc
+    assert desc.count("(absorbed into step") == 15 and desc.count("(rowsum finished inside step") == 7
     assert desc.count("[K-major AB]") == 6 and desc.count("[K-major B]") == 1 and desc.count("[K-major A]") == 1, desc
-    assert launches == steps - 15  # absorbed regions launch nothing
+    assert launches == steps - 22  # absorbed regions and in-kernel finishers launch nothing
     desc16, _ = _plan(cases.make_c3(8, 8192), *av, flags=ffi.FLAG_GEMM_BF16)
     assert desc16.count("+bf16") == 14 and "K-major" not in desc16, desc16
     plain, (steps_p, *_r) = _plan(cases.make_c3(8, 8192), *av, flags=0)  # strict FP32: no tensor-core fusions

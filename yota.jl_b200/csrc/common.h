@@ -216,6 +216,11 @@ struct GemmArgs {
   // ... and BF16 copy of chain output `bsh_out` (BF16 mode: the operand shadow of later GEMMs)
   void* bsh = nullptr;
   int bsh_out = -1;
+  // fused epilogue with a row-sum sink: final output, scale and arrival counters of the in-kernel
+  // finisher (nullptr: the partials are reduced by a separate rowsum_finish launch)
+  float* rs_out = nullptr;
+  float rs_scale = 1.f;
+  unsigned* rs_cnt = nullptr;
   // mode 3: Float32 shadows  x - tf32(x)  of both operands (same dims / leading dimensions)
   const void* A_lo = nullptr;
   const void* B_lo = nullptr;

@@ -145,6 +145,13 @@ struct Params {
   // bias is bounded by the chunk length instead of K.
   int kchunk;
   int pace_ns;  // X3: pause of the epilogue warps after each 32-column slice of a chunk's drain
+  // fused epilogue with a row-sum sink (db): the CTA that delivers the LAST partial of a 128-row
+  // block also reduces the partials (same fixed order as rowsum_finish_kernel) and writes the
+  // result -- no separate finisher launch on the critical path.  rs_cnt: one self-resetting
+  // arrival counter per 128-row block.
+  float* rs_out;
+  float rs_scale;
+  unsigned* rs_cnt;
   // fused epilogue: store output `tsh_out` of the chain a second time, transposed (element (m, n)
   // at tsh[n + m * tsh_ld]): the K-major operand of the dW GEMM that would otherwise read this
   // tensor MN-major (see plan_transposed_shadows in program.cu)
@@ -494,6 +501,9 @@ static int launch(const GemmArgs& g, const Maps& mp, int sm_count, cudaStream_t 
   p.tsh_out = -1;
   p.bsh = nullptr;
   p.bsh_out = -1;
+  p.rs_out = nullptr;
+  p.rs_scale = 1.f;
+  p.rs_cnt = nullptr;
   p.num_m = (int)(g.M / TM);
   p.num_n = (int)(g.N / TN);
   const int tiles = p.num_m * p.num_n;
@@ -559,11 +569,23 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* ma
       "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
       : "memory");
 }
-__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+// arrive (when the MMAs issued so far have completed) on the barrier at this smem offset in every
+// CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask) {
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
           smem_u32(bar)),
-      "h"((uint16_t)3)
+      "h"(cta_mask)
+      : "memory");
+}
+// TMA load delivered to the same smem offset of every CTA in `cta_mask`; each copy's completion is
+// signalled on the mbarrier (same offset) of the leader of the receiving CTA's pair
+__device__ __forceinline__ void tma_load_2d_2sm_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                                   uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "h"(cta_mask)
       : "memory");
 }
 template <int EB>
@@ -604,9 +626,28 @@ struct Epilogue {
   static constexpr int N_IN = ChainOf<ID>::value.n_in, N_OPS = ChainOf<ID>::value.n_ops, N_OUT = ChainOf<ID>::value.n_out;
   static constexpr int NS = ChainOf<ID>::value.n_slots > 0 ? ChainOf<ID>::value.n_slots : 1;
   static constexpr int NO = N_OUT > 0 ? N_OUT : 1;
+  static constexpr int first_rowsum() {
+    for (int k = 0; k < N_OUT; k++)
+      if (ChainOf<ID>::value.out_kind[k] == OUT_ROWSUM) return k;
+    return -1;
+  }
+  static constexpr int RS_OUT = first_rowsum();  // the sink whose partials the kernel finishes itself
 
-  __device__ __forceinline__ static void begin_tile(const RegionParams& rp, long long m, float (&base)[NS],
-                                                    float (&accs)[NO]) {
+  __device__ __forceinline__ static void begin_tile(const RegionParams& rp, long long m, long long n0, long long R,
+                                                    float (&base)[NS], float (&accs)[NO]) {
+    // the tile's other FULL operands (h of the tanh' epilogue) are pulled into L2 while the
+    // mainloop runs: with one tile per CTA (small batches per GPU) nothing else hides the latency
+    // of the epilogue's operand loads, and beside an all-reduce that latency triples
+    static_for<N_IN>([&](auto k) {
+      constexpr int K = decltype(k)::value, cls = YCE(in_cls, k);
+      if constexpr (cls == CLS_FULL && K != Z_IN) {
+        const int lane = threadIdx.x & 31;
+        const float* line0 = rp.in[K].ptr + n0 * R + (m - lane);
+#pragma unroll
+        for (int i = 0; i < TN2 / 32; i++)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(line0 + (long long)(lane + 32 * i) * R));
+      }
+    });
     static_for<NS>([&](auto s) { base[decltype(s)::value] = 0.f; });
     static_for<NO>([&](auto k) { accs[decltype(k)::value] = 0.f; });
     static_for<N_IN>([&](auto k) {
@@ -687,17 +728,54 @@ struct Epilogue {
     }
   }
   __device__ __forceinline__ static void end_tile(const RegionParams& rp, long long m, long long tile_n, long long R,
-                                                  const float (&accs)[NO]) {
+                                                  const float (&accs)[NO], const Params& p, unsigned* flag) {
     static_for<N_OUT>([&](auto k) {
       constexpr int kind = YCE(out_kind, k);
       if constexpr (kind == OUT_ROWSUM) rp.out[decltype(k)::value].ptr[tile_n * R + m] = accs[decltype(k)::value];
     });
+    constexpr int RS = RS_OUT;
+    if constexpr (RS >= 0) {
+      if (p.rs_cnt) {
+        // threadFenceReduction: publish this CTA's partials, count the arrival; the last of the
+        // num_n CTAs covering these 128 rows sums all partials in the finisher's fixed order
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
+        const int et = (threadIdx.x - EPI_WARP0 * 32);
+        if (et == 0) *flag = atomicAdd(p.rs_cnt + (m >> 7), 1u) == (unsigned)(p.num_n - 1) ? 1u : 0u;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (*flag) {
+          __threadfence();
+          const float* part = rp.out[RS].ptr;
+          float sj[8];
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            float acc = 0.f;
+            for (int q = j; q < p.num_n; q += 8) acc = __fadd_rn(acc, __ldcg(part + (long long)q * R + m));
+            sj[j] = acc;
+          }
+          float t = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; j++) t = __fadd_rn(t, sj[j]);
+          p.rs_out[m] = p.rs_scale == 1.f ? t : __fmul_rn(t, p.rs_scale);
+          if (et == 0) p.rs_cnt[m >> 7] = 0u;  // ready for the next run
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // the flag word is reused by the next tile
+      }
+    }
   }
+
 };
 #undef YCE
 
-template <bool A_MN, bool B_MN, int EB, int EPI, int ZIN, bool X3>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+// MC = 2: clusters of FOUR CTAs -- two pairs computing the tiles (m, 2j) and (m, 2j + 1), which
+// read the same 256 rows of A.  Each CTA fetches only half of its 128-row A box and TMA-multicasts
+// it to the CTA holding the same rows in the other pair: per k-block a CTA pulls 8 + 16 KiB through
+// L2 instead of 16 + 16.  At 256 x 256 x 32 tiles with Float32 operands the L2 -> SM operand stream
+// (64 KiB per 4.2 MFLOP) is what bounds the kernel once the batch per GPU is small (N = 1024:
+// 520 TFLOP/s at 7.8 TB/s of L2 reads).  An smem stage is then written by TMA loads of BOTH
+// pairs, so empty[s] collects the commits of both pairs' MMA issuers (count MC).
+template <bool A_MN, bool B_MN, int EB, int EPI, int ZIN, bool X3, int MC>
+__global__ void __launch_bounds__(THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                 const __grid_constant__ CUtensorMap map_al, const __grid_constant__ CUtensorMap map_bl, const Params p,
                 const __grid_constant__ RegionParams rp) {
@@ -716,16 +794,21 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  const uint32_t crank = cluster_ctarank();
+  const uint32_t rank = crank & 1u;               // position inside the CTA pair
+  const uint32_t pp = MC > 1 ? crank >> 1 : 0u;   // which pair of the cluster
+  const uint32_t lead = crank & ~1u;              // cluster rank of this pair's leader
   const bool leader = rank == 0;
-  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
-  const int num_tiles = p.num_m * p.num_n;  // in 256 x 256 tiles
+  const int pair = blockIdx.x / (2 * MC), num_pairs = gridDim.x / (2 * MC);  // work units: MC tiles adjacent along N
+  const int num_tiles = p.num_m * (p.num_n / MC);
   const int nkb = (int)(p.K / TK);
+  const uint16_t mask_pair = (uint16_t)(3u << (2 * pp)), mask_all = (uint16_t)((1u << (2 * MC)) - 1u);
+  const uint16_t mask_same_rows = (uint16_t)((1u << rank) | (1u << (2 + rank)));  // MC = 2: this CTA and its twin
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES2; s++) {
       mbar_init(&full[s], 2);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], MC);
     }
     for (int a = 0; a < 2; a++) {
       mbar_init(&tfull[a], 1);
@@ -755,16 +838,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     constexpr int NB = B_MN ? TNH / E::CHUNK : 1;
     int stage = 0;
     uint32_t phase = 0;
+    constexpr int NAI = NA / MC > 0 ? NA / MC : 1;  // A boxes this CTA issues itself (MN-major A: half the chunks)
     for (int t = pair; t < num_tiles; t += num_pairs) {
       const int m0 = (t % p.num_m) * (2 * TM) + (int)rank * TM;
-      const int n0 = (t / p.num_m) * TN2 + (int)rank * TNH;
+      const int n0 = ((t / p.num_m) * MC + (int)pp) * TN2 + (int)rank * TNH;
       for (int kb = 0; kb < nkb; kb++) {
         if (lane == 0) {
           mbar_wait(&empty[stage], phase ^ 1);
           if (leader)
             mbar_expect_tx(&full[stage], 2 * S::STAGE_BYTES);
           else
-            mbar_arrive_remote(&full[stage], 0);
+            mbar_arrive_remote(&full[stage], lead);
         }
         __syncwarp();
         const int k0 = kb * TK;
@@ -774,33 +858,41 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           unsigned char* sb = sa + S::A_BYTES;
           const CUtensorMap* ma = part ? &map_al : &map_a;
           const CUtensorMap* mb = part ? &map_bl : &map_b;
-          const int l0 = part * (NA + NB);
-          if (!p.spread) {
-            if (lane == 0) {
-              if (A_MN) {
-#pragma unroll
-                for (int c = 0; c < NA; c++)
-                  tma_load_2d_2sm(sa + c * E::CHUNK_BYTES, ma, &full[stage], m0 + E::CHUNK * c, k0);
-              } else
+          const int l0 = part * (NAI + NB);
+          // A box c of this CTA (MC = 2: it issues boxes [pp * NAI, (pp + 1) * NAI) of the NA -- or
+          // rows [pp * 64, +64) of a K-major box -- and multicasts them to its twin in the other pair)
+          auto load_a = [&](int i) {
+            if constexpr (MC == 1) {
+              if (A_MN)
+                tma_load_2d_2sm(sa + i * E::CHUNK_BYTES, ma, &full[stage], m0 + E::CHUNK * i, k0);
+              else
                 tma_load_2d_2sm(sa, ma, &full[stage], k0, m0);
-              if (B_MN) {
-#pragma unroll
-                for (int c = 0; c < NB; c++)
-                  tma_load_2d_2sm(sb + c * E::CHUNK_BYTES, mb, &full[stage], n0 + E::CHUNK * c, k0);
+            } else {
+              if (A_MN) {
+                const int c = (int)pp * NAI + i;
+                tma_load_2d_2sm_mc(sa + c * E::CHUNK_BYTES, ma, &full[stage], m0 + E::CHUNK * c, k0, mask_same_rows);
               } else
-                tma_load_2d_2sm(sb, mb, &full[stage], k0, n0);
+                tma_load_2d_2sm_mc(sa + pp * (S::A_BYTES / MC), ma, &full[stage], k0, m0 + (int)pp * (TM / MC),
+                                   mask_same_rows);
             }
-          } else if (lane >= l0 && lane < l0 + NA) {
-            if (A_MN)
-              tma_load_2d_2sm(sa + (lane - l0) * E::CHUNK_BYTES, ma, &full[stage], m0 + E::CHUNK * (lane - l0), k0);
-            else
-              tma_load_2d_2sm(sa, ma, &full[stage], k0, m0);
-          } else if (lane >= l0 + NA && lane < l0 + NA + NB) {
-            const int c = lane - l0 - NA;
+          };
+          auto load_b = [&](int c) {
             if (B_MN)
               tma_load_2d_2sm(sb + c * E::CHUNK_BYTES, mb, &full[stage], n0 + E::CHUNK * c, k0);
             else
               tma_load_2d_2sm(sb, mb, &full[stage], k0, n0);
+          };
+          if (!p.spread) {
+            if (lane == 0) {
+#pragma unroll
+              for (int i = 0; i < NAI; i++) load_a(i);
+#pragma unroll
+              for (int c = 0; c < NB; c++) load_b(c);
+            }
+          } else if (lane >= l0 && lane < l0 + NAI) {
+            load_a(lane - l0);
+          } else if (lane >= l0 + NAI && lane < l0 + NAI + NB) {
+            load_b(lane - l0 - NAI);
           }
         }
         if (++stage == STAGES2) {
@@ -849,13 +941,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
               umma_2sm<EB>(d_tmem, dal, db, idesc, 1u);
             }
           }
-          umma_commit_2sm(&empty[stage]);
+          umma_commit_2sm(&empty[stage], mask_all);  // every CTA whose TMA loads write into these smem slots
           if (++stage == STAGES2) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit_2sm(&tfull[acc]);
+        umma_commit_2sm(&tfull[acc], mask_pair);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -870,11 +962,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int kc = X3 ? p.kchunk : nkb;
     for (int t = pair; t < num_tiles; t += num_pairs) {
       const long long m = (long long)(t % p.num_m) * (2 * TM) + (long long)rank * TM + q * 32 + lane;
-      const long long n0 = (long long)(t / p.num_m) * TN2;
+      const long long tile_n = (long long)(t / p.num_m) * MC + pp;
+      const long long n0 = tile_n * TN2;
       float* crow = p.C + m + n0 * p.ldc;
       using EP = Epilogue<(EPI >= 0 ? EPI : 0), ZIN>;
       float ebase[EP::NS], eaccs[EP::NO];
-      if constexpr (EPI >= 0) EP::begin_tile(rp, m, ebase, eaccs);
+      if constexpr (EPI >= 0) EP::begin_tile(rp, m, n0, p.M, ebase, eaccs);
      for (int ch = 0; ch < (X3 ? (nkb + kc - 1) / kc : 1); ch++) {
       const int kb0 = X3 ? ch * kc : 0;
       // X3: the tile arrives in chunks of k-blocks; every chunk but the first is added to the
@@ -936,10 +1029,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         }
       }
       if constexpr (EPI >= 0) {
-        if (last) EP::end_tile(rp, m, t / p.num_m, p.M, eaccs);
+        if (last) EP::end_tile(rp, m, tile_n, p.M, eaccs, p, reinterpret_cast<unsigned*>(smem + S::BAR_OFF + 200));
       }
       tcgen05_fence_before();
-      mbar_arrive_remote(&tempty[acc], 0);  // the leader's MMA warp waits for both CTAs' epilogues
+      mbar_arrive_remote(&tempty[acc], lead);  // the leader's MMA warp waits for both CTAs' epilogues
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
@@ -956,12 +1049,28 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   }
 }
 
-template <bool A_MN, bool B_MN, int EB, int EPI = -1, int ZIN = 0, bool X3 = false>
-static int launch2(const GemmArgs& g, const Maps& mp, int sm_count, cudaStream_t s, const RegionParams* rp = nullptr) {
+template <bool A_MN, bool B_MN, int EB, int EPI, int ZIN, bool X3, int MC>
+static int launch2_mc(const GemmArgs& g, const Maps& mp, int sm_count, cudaStream_t s, const RegionParams* rp) {
   static bool attr = false;
-  auto kern = gemm_tc2_kernel<A_MN, B_MN, EB, EPI, ZIN, X3>;
+  static int max_clusters = 0;  // co-resident clusters of 2 * MC CTAs the device can hold
+  auto kern = gemm_tc2_kernel<A_MN, B_MN, EB, EPI, ZIN, X3, MC>;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = Smem2T<X3>::TOTAL;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2 * MC;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
   if (!attr) {
     YOTA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem2T<X3>::TOTAL));
+    cfg.gridDim = dim3(2 * MC);
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n > 0) max_clusters = n;
+    (void)cudaGetLastError();
     attr = true;
   }
   Params p;
@@ -979,15 +1088,51 @@ static int launch2(const GemmArgs& g, const Maps& mp, int sm_count, cudaStream_t
   p.tsh_out = g.tsh_out;
   p.bsh = static_cast<__nv_bfloat16*>(g.bsh);
   p.bsh_out = g.bsh_out;
+  p.rs_out = g.rs_out;
+  p.rs_scale = g.rs_scale;
+  p.rs_cnt = g.rs_cnt;
   p.num_m = (int)(g.M / (2 * TM));
   p.num_n = (int)(g.N / TN2);
-  const int tiles = p.num_m * p.num_n;
-  int pairs = sm_count / 2;
-  if (tiles < pairs) pairs = tiles;
+  const int units = p.num_m * (p.num_n / MC);  // one unit = MC tiles adjacent along N = one cluster's work item
+  int clusters = sm_count / (2 * MC);
+  if (max_clusters > 0 && clusters > max_clusters) clusters = max_clusters;
+  if (units < clusters) clusters = units;
+  if (clusters < 1) clusters = 1;
+  cfg.gridDim = dim3(2 * MC * clusters);
   static const RegionParams no_rp{};
-  kern<<<2 * pairs, THREADS, Smem2T<X3>::TOTAL, s>>>(mp.a, mp.b, mp.al, mp.bl, p, rp ? *rp : no_rp);
-  YOTA_CUDA(cudaGetLastError());
+  YOTA_CUDA(cudaLaunchKernelEx(&cfg, kern, mp.a, mp.b, mp.al, mp.bl, p, rp ? *rp : no_rp));
   return YOTA_OK;
+}
+
+// tensor maps of both operands (mode 3: also of their lo shadows, same dims and strides);
+// a_rows: rows of A per TMA box of a K-major A tile (TM, or TM / 2 when two pairs share A)
+static int make_maps(Maps* mp, const GemmArgs& g, bool A_MN, bool B_MN, int tile_n, int a_rows = TM) {
+  const int eb = g.mode == 2 ? 2 : 4;
+  YOTA_TRY(make_map(&mp->a, g.A, g.M, g.K, g.lda, A_MN, a_rows, eb));
+  YOTA_TRY(make_map(&mp->b, g.B, g.N, g.K, g.ldb, B_MN, tile_n, eb));
+  if (g.mode == 3) {
+    if (!g.A_lo || !g.B_lo) YOTA_FAIL(YOTA_E_ARG, "internal: compensated GEMM without lo shadows");
+    YOTA_TRY(make_map(&mp->al, g.A_lo, g.M, g.K, g.lda, A_MN, a_rows, eb));
+    YOTA_TRY(make_map(&mp->bl, g.B_lo, g.N, g.K, g.ldb, B_MN, tile_n, eb));
+  } else {
+    mp->al = mp->a;
+    mp->bl = mp->b;
+  }
+  return YOTA_OK;
+}
+
+// two pairs per cluster share their A rows whenever the tiles pair up along N
+static bool use_mc2(const GemmArgs& g) { return (g.N / TN2) % 2 == 0 && !getenv("YOTA_GEMM_NO_MULTICAST"); }
+
+template <bool A_MN, bool B_MN, int EB, int EPI = -1, int ZIN = 0, bool X3 = false>
+static int launch2(const GemmArgs& g, int sm_count, cudaStream_t s, const RegionParams* rp = nullptr) {
+  Maps mp;
+  if (use_mc2(g)) {
+    YOTA_TRY(make_maps(&mp, g, A_MN, B_MN, TN2 / 2, TM / 2));
+    return launch2_mc<A_MN, B_MN, EB, EPI, ZIN, X3, 2>(g, mp, sm_count, s, rp);
+  }
+  YOTA_TRY(make_maps(&mp, g, A_MN, B_MN, TN2 / 2, TM));
+  return launch2_mc<A_MN, B_MN, EB, EPI, ZIN, X3, 1>(g, mp, sm_count, s, rp);
 }
 
 }  // namespace tc
@@ -1036,30 +1181,13 @@ bool gemm_epilogue_chain_ok(int static_id, int transA, int transB, int z_in) {
 }
 
 namespace tc {
-// tensor maps of both operands (mode 3: also of their lo shadows, same dims and strides)
-static int make_maps(Maps* mp, const GemmArgs& g, bool A_MN, bool B_MN, int tile_n) {
-  const int eb = g.mode == 2 ? 2 : 4;
-  YOTA_TRY(make_map(&mp->a, g.A, g.M, g.K, g.lda, A_MN, TM, eb));
-  YOTA_TRY(make_map(&mp->b, g.B, g.N, g.K, g.ldb, B_MN, tile_n, eb));
-  if (g.mode == 3) {
-    if (!g.A_lo || !g.B_lo) YOTA_FAIL(YOTA_E_ARG, "internal: compensated GEMM without lo shadows");
-    YOTA_TRY(make_map(&mp->al, g.A_lo, g.M, g.K, g.lda, A_MN, TM, eb));
-    YOTA_TRY(make_map(&mp->bl, g.B_lo, g.N, g.K, g.ldb, B_MN, tile_n, eb));
-  } else {
-    mp->al = mp->a;
-    mp->bl = mp->b;
-  }
-  return YOTA_OK;
-}
-
 template <int ID, int ZIN>
-static int launch_epi(const GemmArgs& g, const Maps& mp, int sm_count, cudaStream_t s, const RegionParams& rp,
-                      bool A_MN) {
+static int launch_epi(const GemmArgs& g, int sm_count, cudaStream_t s, const RegionParams& rp, bool A_MN) {
   if constexpr (epi_z_ok<ID>(ZIN)) {
 #define GOE(a)                                                                           \
-  return g.mode == 3   ? launch2<a, false, 4, ID, ZIN, true>(g, mp, sm_count, s, &rp)    \
-         : g.mode == 1 ? launch2<a, false, 4, ID, ZIN>(g, mp, sm_count, s, &rp)          \
-                       : launch2<a, false, 2, ID, ZIN>(g, mp, sm_count, s, &rp)
+  return g.mode == 3   ? launch2<a, false, 4, ID, ZIN, true>(g, sm_count, s, &rp)    \
+         : g.mode == 1 ? launch2<a, false, 4, ID, ZIN>(g, sm_count, s, &rp)          \
+                       : launch2<a, false, 2, ID, ZIN>(g, sm_count, s, &rp)
     if (A_MN) GOE(true);
     GOE(false);
 #undef GOE
@@ -1076,13 +1204,11 @@ int launch_gemm_tc_epilogue(yota_ctx* ctx, const GemmArgs& g, int static_id, con
       !gemm_epilogue_chain_ok(static_id, g.transA, g.transB, z_in))
     YOTA_FAIL(YOTA_E_ARG, "internal: GEMM epilogue fusion planned for an ineligible GEMM");
   const bool A_MN = !g.transA;
-  tc::Maps mp;
-  YOTA_TRY(tc::make_maps(&mp, g, A_MN, false, tc::TN2 / 2));
   switch (static_id) {
 #define X(ID)                                                                       \
   case ID:                                                                          \
-    return z_in == 0 ? tc::launch_epi<ID, 0>(g, mp, grid_sms(ctx), s, rp, A_MN)    \
-                     : tc::launch_epi<ID, 1>(g, mp, grid_sms(ctx), s, rp, A_MN);
+    return z_in == 0 ? tc::launch_epi<ID, 0>(g, grid_sms(ctx), s, rp, A_MN)    \
+                     : tc::launch_epi<ID, 1>(g, grid_sms(ctx), s, rp, A_MN);
     YOTA_EPI_CHAIN_LIST(X)
 #undef X
   }
@@ -1101,11 +1227,10 @@ int launch_gemm_tc(yota_ctx* ctx, const GemmArgs& g, cudaStream_t s) {
   const bool two_cta = gemm_tc2_eligible(g, ctx->sm_count);
   if (two_cta) {
     // each CTA of a pair loads a 128-row box of A and a 128-column box of B
-    YOTA_TRY(tc::make_maps(&mp, g, A_MN, B_MN, tc::TN2 / 2));
-#define GO2(a, b)                                                                         \
-  return g.mode == 3   ? tc::launch2<a, b, 4, -1, 0, true>(g, mp, grid_sms(ctx), s)       \
-         : g.mode == 1 ? tc::launch2<a, b, 4>(g, mp, grid_sms(ctx), s)                    \
-                       : tc::launch2<a, b, 2>(g, mp, grid_sms(ctx), s)
+#define GO2(a, b)                                                                     \
+  return g.mode == 3   ? tc::launch2<a, b, 4, -1, 0, true>(g, grid_sms(ctx), s)       \
+         : g.mode == 1 ? tc::launch2<a, b, 4>(g, grid_sms(ctx), s)                    \
+                       : tc::launch2<a, b, 2>(g, grid_sms(ctx), s)
     if (A_MN && B_MN) GO2(true, true);
     if (A_MN && !B_MN) GO2(true, false);
     if (!A_MN && B_MN) GO2(false, true);

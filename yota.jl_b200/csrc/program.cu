@@ -105,6 +105,8 @@ struct Step {
   int tsh_make = -1;      // fused-epilogue GEMM: transposed shadow it also writes ...
   int tsh_make_out = -1;  // ... of this store output of the chain
   int tsh_use[2] = {-1, -1};  // GEMM: operand A / B is read from this transposed shadow (K-major)
+  int rs_finish = -1;     // fused-epilogue GEMM: finisher step of its row-sum sink that runs inside the GEMM
+  bool fused_away = false;  // finisher: performed by the last CTA of the kernel that wrote the partials
   int bsh_make = -1;      // fused-epilogue GEMM (BF16 mode): BF16 shadow it writes itself ...
   int bsh_make_out = -1;  // ... of this store output of the chain
 };
@@ -124,6 +126,7 @@ struct yota_program {
   std::vector<int> op_scale;  // UNGETINDEX ops: scalar tensor multiplied into the source on load (-1: none)
   int n_in = 0, n_out = 0;
   size_t arena_bytes = 0, const_bytes = 0;
+  size_t counter_off = 0, counter_bytes = 0;  // arrival counters of in-kernel reduction finishers (zeroed once)
   std::vector<int> const_tensors;  // CONST / SEED tensors, in const-buffer order
   int n_launches = 0, n_static = 0;
   // runtime
@@ -1107,6 +1110,8 @@ static int plan_memory(yota_program& P) {
       P.const_tensors.push_back((int)t);
       coff += 256;  // one 256-byte line per scalar keeps every operand 16-byte aligned
     }
+  P.counter_off = coff;
+  coff += (P.counter_bytes + 255) & ~(size_t)255;
   P.const_bytes = coff;
   // last use per root tensor
   for (int s = 0; s < ns; s++) {
@@ -1392,6 +1397,17 @@ static int plan_gemm_epilogues(yota_program& P) {
       fs.P = P_tiles;
       fs.ws_bytes = (size_t)P_tiles * g.M * sizeof(float);
       fs.ws_owner_step = (int)si;
+      // the last CTA to deliver a partial also reduces them (gemm_tc.cu: Epilogue::end_tile): the
+      // finisher launch leaves the critical path (8 x 10-33 us of a C3 step on 8 GPUs)
+      if (q == 0 && gs.rs_finish < 0 && !getenv("YOTA_NO_FUSED_FINISH")) {
+        gs.rs_finish = r.finish_steps[q];
+        gs.label += " +finish";
+        fs.fused_away = true;
+        fs.label = "(rowsum finished inside step " + std::to_string(si) + ")";
+        gs.writes.push_back(fs.out_tensor);
+        P.T[fs.out_tensor].def_step = (int)si;
+        P.counter_bytes = std::max(P.counter_bytes, (size_t)(g.M / 128) * sizeof(unsigned));
+      }
     }
     r.step = (int)si;  // workspaces are allocated when the GEMM runs
   }
@@ -1509,7 +1525,7 @@ extern "C" int yota_program_build(yota_ctx* ctx, const yota_op_desc* ops, int64_
   if ((st = plan_memory(P))) return fail(st);
   P.n_launches = 0;
   for (auto& s : P.steps)  // absorbed regions launch nothing; BF16 operand casts are launches of their GEMM step
-    P.n_launches += s.kind == STEP_NOP ? 0 : (s.kind == STEP_UNGETINDEX ? 8 : 1) + (s.cast[0] ? 1 : 0) + (s.cast[1] ? 1 : 0);
+    P.n_launches += (s.kind == STEP_NOP || s.fused_away) ? 0 : (s.kind == STEP_UNGETINDEX ? 8 : 1) + (s.cast[0] ? 1 : 0) + (s.cast[1] ? 1 : 0);
   *out = Pp;
   return YOTA_OK;
 }
@@ -1588,6 +1604,7 @@ static int ensure_arena(yota_program& P) {
     P.arena = nullptr;
     YOTA_FAIL(YOTA_E_NOMEM, "cannot allocate the program arena (%zu bytes): %s", bytes, cudaGetErrorString(e));
   }
+  if (P.counter_bytes) YOTA_CUDA(cudaMemsetAsync(P.arena + P.counter_off, 0, P.counter_bytes, P.ctx->stream));
   for (size_t i = 0; i < P.const_tensors.size(); i++) {
     const TInfo& t = P.T[P.const_tensors[i]];
     if (t.d.kind == YOTA_T_CONST) {
@@ -1636,6 +1653,12 @@ static int run_gemm_epilogue(yota_program& P, Step& st, const GemmArgs& g_in, cu
     g.bsh = P.arena + P.shadows[st.bsh_make].arena_off;
     g.bsh_out = st.bsh_make_out;
   }
+  if (st.rs_finish >= 0) {
+    const Step& fs = P.steps[st.rs_finish];
+    g.rs_out = static_cast<float*>(tensor_ptr(P, fs.out_tensor));
+    g.rs_scale = fs.scale;
+    g.rs_cnt = reinterpret_cast<unsigned*>(P.arena + P.counter_off);
+  }
   Region& r = P.regions[st.epi_region];
   RegionLaunch L = r.L;
   L.p.in[st.epi_z_in].ptr = nullptr;  // the accumulator stands in for this operand
@@ -1658,6 +1681,7 @@ static int run_step(yota_program& P, Step& st, cudaStream_t s) {
     }
     case STEP_NOP: return YOTA_OK;
     case STEP_ROWSUM_FINISH:
+      if (st.fused_away) return YOTA_OK;  // reduced inside the GEMM that produced the partials
       return launch_rowsum_finish(static_cast<float*>(tensor_ptr(P, st.out_tensor)),
                                   reinterpret_cast<const float*>(P.arena + st.ws_off), st.R, st.P, st.scale, s);
     case STEP_SCALAR_FINISH:
@@ -1946,9 +1970,10 @@ static int run_all_steps(yota_program& P, cudaStream_t s, bool with_comm, Timeli
       ctx->sm_reserved = (in_flight || head_gemms > 0) ? reserve : 0;
       if (head_gemms > 0) head_gemms--;
     }
-    if (tl && st.kind != STEP_NOP) YOTA_TRY(tl->open(st.label, s));
+    const bool launches = st.kind != STEP_NOP && !st.fused_away;
+    if (tl && launches) YOTA_TRY(tl->open(st.label, s));
     YOTA_TRY(run_step(P, st, s));
-    if (tl && st.kind != STEP_NOP) YOTA_TRY(tl->close(s));
+    if (tl && launches) YOTA_TRY(tl->close(s));
     if (with_comm && !C.ar_at[q].empty()) {
       for (int slot : C.ar_at[q]) {
         pend_buf.push_back(static_cast<float*>(P.bound_out[slot]));
