@@ -334,3 +334,60 @@ def test_accumulation_never_lands_in_a_view_of_a_shared_array():
            r.random((256, 128)).astype(F32)]
     for flags in (0, ffi.FLAG_GEMM_TF32):
         U.check_parity(test_host.alias_hazard_loss, big, flags=flags, rtol=1e-5 if flags == 0 else 5e-3)
+
+
+# ---- the operator seam: statement-by-statement execution on the device (eager.play) --------
+def _cmp_play(f, args, seed=1, flags=0, tol=1e-6, bitwise=()):
+    d = [Y.cu(a) if isinstance(a, np.ndarray) else a for a in args]
+    dseed = Y.cu(np.asarray(seed, np.float32)) if isinstance(seed, np.ndarray) else seed
+    tape = Y.gradtape(f, *d, seed=dseed if not isinstance(dseed, Y.B200Array) else seed)
+    v1, g1 = Y.play(tape, *d, seed=dseed, flags=flags)
+    v2, g2 = Y.grad(f, *d, seed=dseed, flags=flags)
+    h = lambda x: x.to_host() if isinstance(x, Y.B200Array) else x  # noqa: E731
+    assert np.allclose(h(v1), h(v2), rtol=tol, atol=0)
+    for i, (a, b) in enumerate(zip(g1[1:], g2[1:])):
+        if isinstance(b, Y.B200Array):
+            a, b = a.to_host(), b.to_host()
+            if i in bitwise:
+                assert np.array_equal(U.bits(a), U.bits(b)), i
+            assert np.abs(a - b).max() <= tol * max(np.abs(b).max(), 1e-30), (i, np.abs(a - b).max())
+        else:
+            assert repr(a) == repr(b), (i, a, b)
+    return v1, g1
+
+
+@pytest.mark.parametrize("name,f,args", cases.gradcheck_cases(), ids=lambda v: v if isinstance(v, str) else "")
+def test_play_equals_compiled_on_the_reference_cases(name, f, args):
+    """compiled == play! == grad (test/test_grad.jl:271-289): the tape interpreted one rule at a
+    time on the device (every rrule forward and every pullback its own tiny program) against the
+    fused, graph-replayed program."""
+    _cmp_play(f, f32(args), tol=2e-5)
+
+
+def test_play_on_the_configs_and_seed_forms():
+    _cmp_play(cases.c1_mlp, list(cases.c1_args(48, 32, 10, 16)), tol=2e-5)
+    _cmp_play(cases.make_c3(3, 64), list(cases.c3_args(3, 32, 64)), tol=2e-5)
+    _cmp_play(cases.make_c4(4), list(cases.c4_args(32, 8, 4)), tol=2e-5)
+    E, idx, V = cases.c5_args(8, 64, 300)
+    _cmp_play(cases.c5_embed, [E, idx, V], bitwise=(0,), tol=2e-5)  # scatter-add: the same bits either way
+    x = np.array([1.0, 2, 3], F32)
+    _cmp_play(lambda x: 2 * x, [x], seed=np.ones(3, F32))
+    _cmp_play(lambda x: 2 * x, [x], seed="auto")
+    v, g = Y.grad(cases.loss_tanh, *map(Y.cu, f32(cases.gradcheck_cases()[1][2])), cold_opwise=True)
+    _, og = O.grad(cases.loss_tanh, *cases.gradcheck_cases()[1][2])
+    assert np.allclose(g[1].to_host(), og[1], rtol=1e-5, atol=1e-6)
+
+
+def test_eager_rrule_is_the_operator_api():
+    """rrule(cfg, *, A, B) on device arrays: value now, pullback later (src/grad.jl:147,173)."""
+    r = cases.rng(41)
+    A, B = r.random((256, 128)).astype(F32), r.random((128, 256)).astype(F32)
+    val, pb = Y.rrule("matmul", Y.cu(A), Y.cu(B))
+    assert np.allclose(val.to_host(), A @ B, rtol=1e-5)
+    dy = r.random((256, 256)).astype(F32)
+    _, dA, dB = pb(Y.cu(dy))
+    assert np.allclose(dA.to_host(), dy @ B.T, rtol=1e-5) and np.allclose(dB.to_host(), A.T @ dy, rtol=1e-5)
+    y, pb = Y.rrule("broadcasted", "tanh", Y.cu(A))
+    t = pb(Y.cu(np.ones_like(A)))
+    assert t[0] is Y.NoTangent and t[1] is Y.NoTangent
+    assert np.allclose(t[2].to_host(), 1 - np.tanh(A) ** 2, rtol=1e-5, atol=1e-6)

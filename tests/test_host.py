@@ -229,3 +229,71 @@ def test_compute_entry_fails_loudly_without_gpu(built):
     assert b"no CPU fallback" in lib.yota_last_error()
     with pytest.raises(Y.YotaError):
         Y.grad(cases.loss_tanh, np.ones((4, 3), np.float32), np.ones(4, np.float32), np.ones(3, np.float32))
+
+
+# ---- eager.play on the CPU: the statement-by-statement executor with its device programs
+# replaced by the test-only NumPy interpreter of the op program (host logic only) -------------
+class _FakeArr:
+    def __init__(self, a):
+        self.a = np.asarray(a) if np.ndim(a) == 0 else np.asfortranarray(a)
+        self.dims = tuple(self.a.shape)
+        self.dtype = "i64" if self.a.dtype.kind in "iu" else "f32"
+        self.ptr = None
+
+    def to_host(self):
+        return self.a if self.dims else self.a[()]
+
+
+class _FakeProgram:
+    def __init__(self, prog, ctx, flags):
+        self.prog = prog
+
+    def __call__(self, ins, seed=1.0):
+        outs = ir_interp.run(self.prog, [x.a for x in ins], seed=seed, dtype=np.float64)
+        return [_FakeArr(np.asarray(outs[s])) for s in range(self.prog.n_outputs)]
+
+
+@pytest.fixture
+def fake_device(monkeypatch):
+    from yota_b200 import eager
+
+    monkeypatch.setattr(eager, "DeviceProgram", _FakeProgram)
+    monkeypatch.setattr(eager, "B200Array", _FakeArr)
+    monkeypatch.setattr(eager, "context", lambda: None)
+    _FakeArr.from_host = staticmethod(lambda a, ctx=None: _FakeArr(a))
+    eager._PROGRAMS.clear()
+    yield eager
+    eager._PROGRAMS.clear()
+
+
+@pytest.mark.parametrize("name,f,args", cases.gradcheck_cases(), ids=lambda v: v if isinstance(v, str) else "")
+def test_play_statement_by_statement_matches_the_oracle(fake_device, name, f, args):
+    tape = Y.gradtape(f, *[A(a.shape) for a in args])
+    val, g = fake_device.play(tape, *[_FakeArr(a) for a in args])
+    oval, og = O.grad(f, *args, dtype=np.float64)
+    v = val.to_host() if isinstance(val, _FakeArr) else val
+    assert np.allclose(v, oval, rtol=1e-11)
+    for a, b in zip(g[1:], og[1:]):
+        if isinstance(a, _FakeArr):
+            assert np.allclose(a.to_host(), b, rtol=1e-11, atol=1e-13)
+        else:
+            assert repr(a) == repr(b)
+
+
+def test_play_configs_and_seeds(fake_device):
+    f64 = lambda xs: [x.astype(np.float64) if x.dtype.kind == "f" else x for x in xs]  # noqa: E731
+    for f, args in ((cases.c1_mlp, f64(cases.c1_args(6, 5, 3, 4))), (cases.make_c3(3, 4), f64(cases.c3_args(3, 5, 4))),
+                    (cases.make_c4(3), f64(cases.c4_args(4, 3, 3))), (cases.c5_embed, f64(cases.c5_args(3, 5, 8)))):
+        tape = Y.gradtape(f, *[A(a.shape, "i64" if a.dtype.kind == "i" else "f32") for a in args])
+        val, g = fake_device.play(tape, *[_FakeArr(a) for a in args])
+        oval, og = O.grad(f, *args, dtype=np.float64)
+        assert np.allclose(val.to_host() if isinstance(val, _FakeArr) else val, oval, rtol=1e-11)
+        for a, b in zip(g[1:], og[1:]):
+            if isinstance(a, _FakeArr):
+                assert np.allclose(a.to_host(), b, rtol=1e-11, atol=1e-13)
+            else:
+                assert repr(a) == repr(b)
+    x = np.array([1.0, 2, 3])
+    tape = Y.gradtape(lambda x: 2 * x, A((3,)), seed="auto")
+    _, g = fake_device.play(tape, _FakeArr(x), seed="auto")
+    assert np.allclose(g[1].to_host(), 2 * np.ones(3))

@@ -202,8 +202,13 @@ def _seed_key(seed):
     return ("arr", tuple(seed.shape))
 
 
-def grad(f, *args, seed=1, flags=None):
+def grad(f, *args, seed=1, flags=None, cold_opwise=False):
     """grad(f, args...; seed=1) -> (val, (ZeroTangent(), dargs...)).
+
+    cold_opwise=True mirrors the reference's cold call: on a cache miss the tape is executed
+    statement by statement on the device (eager.play, the analogue of the eager `mkcall`s at
+    src/grad.jl:145-147,173 and of `tape.retval`, :357-360) while the fused program is compiled
+    and cached for the warm calls.
 
     Gradients are returned for every argument (finalize_grad!, src/grad.jl:230-239);
     arguments the result does not depend on get ZeroTangent(), index arguments NoTangent()."""
@@ -221,6 +226,11 @@ def grad(f, *args, seed=1, flags=None):
         else:
             gf = CompiledGrad(tape, flags=flags)
         GRAD_CACHE[key] = gf
+        if cold_opwise and isinstance(gf, CompiledGrad):
+            from .eager import play
+
+            dargs = [a if isinstance(a, B200Array) or not isinstance(a, np.ndarray) else B200Array.from_host(a) for a in args]
+            return play(tape, *dargs, seed=seed, flags=flags & ~ffi.FLAG_NO_GRAPH)
     return gf(f, *args, seed=seed)
 
 

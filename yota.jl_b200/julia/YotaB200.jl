@@ -49,8 +49,15 @@ const F32, I64 = Int32(0), Int32(1)
 const T_INPUT, T_TEMP, T_OUTPUT, T_CONST, T_SEED = Int32.(0:4)
 const EW = (copy=1, add=2, sub=3, mul=4, div=5, neg=6, tanh=7, exp=8, log=9, sin=10, cos=11, sqrt=12,
             relu=13, sigmoid=14, square=15, gt0=16, addc=17, mulc=18, rsubc=19, rdivc=20, powc=21)
-const OP = (sum=64, matmul=65, getindex=66, ungetindex=67, logsoftmax=68, reshape=69, transpose=70)
+const OP = (sum=64, matmul=65, getindex=66, ungetindex=67, logsoftmax=68, reshape=69, transpose=70, cat=71, slice=72)
 const IDX_COLON, IDX_INT, IDX_RANGE, IDX_VEC = 0, 1, 2, 3
+# yota_program_build flags (include/yota_cuda.h; tests/test_abi.py compares the values with the header)
+const FLAG_NO_FUSE = UInt32(0x1)
+const FLAG_NO_GRAPH = UInt32(0x2)
+const FLAG_GEMM_TF32 = UInt32(0x10)
+const FLAG_GEMM_BF16 = UInt32(0x20)
+const FLAG_NO_STATIC = UInt32(0x40)
+const FLAG_GEMM_TF32X3 = UInt32(0x80)
 
 check(status::Integer) = status == 0 ? nothing :
     error("libyota_cuda: " * unsafe_string(ccall((:yota_last_error, LIB), Cstring, ())) * " (status $status)")
@@ -349,7 +356,7 @@ function lower(tape::Tape{GradCtx})
 end
 
 "Replacement for `Yota.grad_compile(tape)` (src/grad.jl:293-307) when the arguments are B200Arrays."
-function b200_compile(tape::Tape{GradCtx}; flags::UInt32=UInt32(0x10))   # YOTA_FLAG_GEMM_TF32
+function b200_compile(tape::Tape{GradCtx}; flags::UInt32=FLAG_GEMM_TF32)
     p, arg_slots, out_dims, v, gs = lower(tape)
     h = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:yota_program_build, LIB), Cint,
