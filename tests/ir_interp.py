@@ -21,7 +21,8 @@ def run(prog, inputs, seed=1.0, dtype=np.float32):
     for T in prog.tensors:
         if T.kind == ir.T_INPUT:
             a = np.asarray(inputs[T.slot])
-            vals[T.id] = np.asfortranarray(a.astype(dtype) if a.dtype.kind == "f" else a)
+            a = a.astype(dtype) if a.dtype.kind == "f" else a
+            vals[T.id] = np.asfortranarray(a) if a.ndim else a  # (asfortranarray promotes 0-d to 1-d)
             assert tuple(vals[T.id].shape) == T.dims, (vals[T.id].shape, T.dims)
         elif T.kind == ir.T_CONST:
             vals[T.id] = np.asarray(t(T.cval))
