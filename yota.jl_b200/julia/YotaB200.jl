@@ -382,24 +382,165 @@ function b200_compile(tape::Tape{GradCtx}; flags::UInt32=FLAG_GEMM_TF32)
     end
 end
 
-# Hook: route `Yota.grad` to the backend when any argument is a B200Array.  Tracing executes
-# every primitive once (Umlaut `mkcall`), so the cold call runs on host copies of the
-# arguments; warm calls (GRAD_CACHE hit, src/grad.jl:353-355) run entirely on the device.
-function Yota.grad(f, args::Vararg{Union{B200Array,Number}}; seed=1)
-    key = (f, map(a -> a isa B200Array ? (eltype(a), size(a)) : typeof(a), args))  # sizes too: the program is shape-specialised
-    gf = get!(Yota.GRAD_CACHE, key) do
-        host = map(a -> a isa B200Array ? Array(a) : a, args)
-        b200_compile(rebind_inputs(Yota.gradtape(f, host...; seed=seed), args))
+# ---------------------------------------------------------------------------------------
+# Operator seam (SURVEY.md §8(b), Seam 2): the primitives and their rrules on B200Arrays.
+#
+# Umlaut's tracer and Yota's tape builder EXECUTE every statement they record (`mkcall`:
+# the primal call while tracing, `rrule(cfg, f, args...)` in chainrules_transform!,
+# src/grad.jl:145-147, and every `pb(dy)` in back!, :173), which is how a cold `grad` call
+# returns `tape.retval` (:357-360).  With B200Array arguments those calls dispatch to the methods
+# below: each one builds the single-rule op program with the same `lower_fwd!` / `lower_pb!` the
+# fused path uses and runs it on the device (yota_program_build + yota_program_run, one launch
+# list per statement, no graph) -- the cold path never touches host copies of the data.
+# Python mirror (tested on the device): yota.jl_b200/eager.py `rrule` / `play`.
+# ---------------------------------------------------------------------------------------
+const EAGER_CACHE = Dict{Any,Any}()
+
+"Build (once per signature) and run a program whose inputs are `arrays`; returns the outputs."
+function run_program(key, build::Function, arrays::Vector)
+    ent = get!(EAGER_CACHE, key) do
+        p, out_dims, extra = build()
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:yota_program_build, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{OpDesc}, Int64, Ptr{TensorDesc}, Int64, UInt32, Ptr{Ptr{Cvoid}}),
+                    context().h, p.ops, length(p.ops), p.tensors, length(p.tensors), FLAG_NO_GRAPH, h))
+        (h[], out_dims, extra)
     end
-    return Base.invokelatest(gf, f, args...; seed=seed)
+    h, out_dims, extra = ent
+    ins = Ptr{Cvoid}[a.ptr for a in arrays]
+    outs = [B200Array{Float32,length(d)}(Tuple(Int.(d))) for d in out_dims]
+    optrs = Ptr{Cvoid}[o.ptr for o in outs]
+    check(ccall((:yota_program_run, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}, Int64, Ptr{Ptr{Cvoid}}, Int64, Cfloat),
+                h, ins, length(ins), optrs, length(optrs), 1f0))
+    return outs, extra
 end
 
-"Swap the traced host arrays of the tape inputs for the device arrays they were copied from."
-function rebind_inputs(tape::Tape{GradCtx}, args)
-    for (v, a) in zip(inputs(tape)[2:end], args)
-        tape[v].val = a
+sig(a::B200Array) = (eltype(a), size(a))
+sig(a) = a
+
+"Result dims of `f(args...; kw...)` on arrays of these sizes (what Julia itself would return)."
+function out_dims(f, args, kw)
+    sz(a) = a isa B200Array ? size(a) : ()
+    f === broadcasted && return Base.Broadcast.broadcast_shape(map(sz, args[2:end])...)
+    f === materialize && return sz(args[1])
+    f === (*) && return (size(args[1], 1), size(args[2])[2:end]...)
+    if f === sum || f === Statistics.mean
+        haskey(kw, :dims) || return ()
+        return ntuple(i -> i in kw[:dims] ? 1 : size(args[1], i), ndims(args[1]))
     end
-    return tape
+    f === getindex && return map(length, Base.index_shape(Base.to_indices(args[1], map(i -> i isa B200Array ? (1:length(i)) : i, args[2:end]))...))
+    f === NNlib.logsoftmax && return sz(args[1])
+    error("No derivative rule found for op $f on B200Array arguments (libyota_cuda has no lowering)")
+end
+
+"""
+    eager_rrule(f, args...; kw...) -> (value, pullback)
+
+`rrule(YotaRuleConfig(), f, args...)` for device arrays: the forward runs now as one tiny device
+program; `pullback(dy)` runs the rule's pullback as another and returns the tangent tuple.
+"""
+function eager_rrule(f, args...; kw...)
+    arrays = B200Array[a for a in args if a isa B200Array]
+    od = out_dims(f, args, kw)
+    outs, (pfwd, y, saved) = run_program((:fwd, f, map(sig, args), kw), arrays) do
+        p = Program()
+        vals = Any[a isa B200Array ? (t = tensor!(p, size(a); dtype=eltype(a) == Int64 ? I64 : F32, kind=T_INPUT, slot=p.n_in); p.n_in += 1; t) : a
+                   for a in args]
+        y, saved = lower_fwd!(p, f, vals, kw, od)
+        mark_output!(p, y)
+        (p, [od], (p, y, saved))
+    end
+    val = outs[1]
+    return val, dy -> run_pullback(f, args, kw, pfwd, y, saved, arrays, val, dy)
+end
+
+function mark_output!(p::Program, x)
+    d = p.tensors[x + 1]
+    if d.kind != T_TEMP
+        x = op!(p, EW.copy, (x,), d.dims[1:d.ndim]); d = p.tensors[x + 1]
+    end
+    p.tensors[x + 1] = TensorDesc(d.dtype, d.ndim, d.dims, T_OUTPUT, p.n_out, 0.0)
+    p.n_out += 1
+    return x
+end
+
+"Tangents of one rule on the device: builds/caches the pullback program, binds dy / the value / the arguments."
+function pullback_program(f, args, kw, pfwd::Program, y, saved, dyv)
+    p = Program()
+    binds = Any[]
+    memo = Dict{Int,Int}()
+    inp(dims, dtype, what) = (t = tensor!(p, dims; dtype=dtype, kind=T_INPUT, slot=p.n_in); p.n_in += 1; push!(binds, what); t)
+    function remap(x)
+        if x isa Integer && 0 <= x < length(pfwd.tensors)   # a tensor id of the forward program
+            haskey(memo, x) && return memo[x]
+            d = pfwd.tensors[x + 1]
+            r = d.kind == T_CONST ? const!(p, d.cval) :
+                d.kind == T_INPUT ? inp(d.dims[1:d.ndim], d.dtype, d.slot + 1) : inp(d.dims[1:d.ndim], d.dtype, :val)
+            return memo[x] = r
+        end
+        return x isa Tuple ? map(remap, x) : x isa Vector ? map(remap, x) : x
+    end
+    # which entries of `saved` are tensor ids depends on the rule (dims tuples and counts are Ints too)
+    k = saved[1]
+    saved2 = k === :sum ? saved :
+             k === :idx ? (k, saved[2], saved[3], map(remap, saved[4])) :
+             k === :powc ? (k, remap(saved[2]), saved[3]) :
+             (k, map(x -> x isa Integer ? remap(x) : x, saved[2:end])...)
+    d2 = dyv isa B200Array ? inp(size(dyv), F32, :dy) : const!(p, dyv)
+    tangents = lower_pb!(p, f, saved2, d2)
+    out_dims_ = Tuple[]
+    for t in tangents
+        t isa Integer || continue
+        mark_output!(p, t); push!(out_dims_, dims(p, t))
+    end
+    return p, out_dims_, (binds, tangents)
+end
+
+function run_pullback(f, args, kw, pfwd::Program, y, saved, arrays, val, dy)
+    (dy isa ZeroTangent || dy isa NoTangent) && return ntuple(_ -> ZeroTangent(), length(args) + 1)
+    dyv = unthunk(dy)
+    key = (:pb, f, map(sig, args), kw, sig(dyv))
+    ent = get(EAGER_CACHE, key, nothing)
+    binds = ent === nothing ? pullback_program(f, args, kw, pfwd, y, saved, dyv)[3][1] : ent[3][1]
+    ins = B200Array[w === :dy ? dyv : w === :val ? val : arrays[w] for w in binds]
+    outs, (_, tangents) = run_program(() -> pullback_program(f, args, kw, pfwd, y, saved, dyv), key, ins)
+    k = 0
+    return map(t -> t isa Integer ? outs[k += 1] : t, tangents)
+end
+run_program(build::Function, key, arrays) = run_program(key, build, arrays)
+
+# the primitives themselves (what `mkcall` executes while TRACING) and their rules
+const DeviceRules = Union{typeof(*),typeof(sum),typeof(Statistics.mean),typeof(getindex),typeof(NNlib.logsoftmax)}
+for f in (:(Base.:*), :(Base.sum), :(Statistics.mean), :(NNlib.logsoftmax))
+    @eval $f(a::B200Array, rest...; kw...) = eager_rrule($f, a, rest...; kw...)[1]
+    @eval ChainRulesCore.rrule(::YotaRuleConfig, ::typeof($f), a::B200Array, rest...; kw...) =
+        eager_rrule($f, a, rest...; kw...)
+end
+Base.getindex(a::B200Array, I::Union{Colon,Integer,AbstractUnitRange,B200Array{Int64,1}}...) = eager_rrule(getindex, a, I...)[1]
+ChainRulesCore.rrule(::YotaRuleConfig, ::typeof(getindex), a::B200Array, I...) = eager_rrule(getindex, a, I...)
+# dotted calls: a broadcast over device arrays is executed at once (the "lazy" Broadcasted of the
+# reference's fast rules is an array here; `materialize` is the identity both ways, src/rulesets.jl:27-29)
+Base.Broadcast.broadcasted(f, a::B200Array, rest...) = eager_rrule(broadcasted, f, a, rest...)[1]
+Base.Broadcast.broadcasted(f, x::Number, a::B200Array, rest...) = eager_rrule(broadcasted, f, x, a, rest...)[1]
+Base.Broadcast.materialize(a::B200Array) = a
+ChainRulesCore.rrule(::YotaRuleConfig, ::typeof(broadcasted), f, a::B200Array, rest...) = eager_rrule(broadcasted, f, a, rest...)
+ChainRulesCore.rrule(::YotaRuleConfig, ::typeof(broadcasted), f, x::Number, a::B200Array, rest...) =
+    eager_rrule(broadcasted, f, x, a, rest...)
+ChainRulesCore.rrule(::YotaRuleConfig, ::typeof(materialize), a::B200Array) = (a, dy -> (NoTangent(), dy))
+Base.broadcast(::typeof(+), a::B200Array, b::B200Array) = eager_rrule(broadcasted, +, a, b)[1]   # src/grad.jl:91
+
+# Hook: `Yota.grad` on device arrays.  The cold call traces and builds the tape ON THE DEVICE
+# through the methods above (no host copies); the finished tape is compiled into the fused
+# program, which serves every warm call (GRAD_CACHE hit, src/grad.jl:353-355).
+function Yota.grad(f, args::Vararg{Union{B200Array,Number}}; seed=1)
+    key = (f, map(a -> a isa B200Array ? (eltype(a), size(a)) : typeof(a), args))  # sizes too: the program is shape-specialised
+    if haskey(Yota.GRAD_CACHE, key)
+        return Base.invokelatest(Yota.GRAD_CACHE[key], f, args...; seed=seed)
+    end
+    tape = Yota.gradtape(f, args...; seed=seed)          # executes statement by statement on the device
+    Yota.GRAD_CACHE[key] = b200_compile(tape)
+    return tape.retval                                   # src/grad.jl:357-360
 end
 
 "update!(x, gx): x .= x .- gx on the device (src/update.jl:42-49)."
