@@ -229,6 +229,11 @@ int yota_gather_cols(yota_ctx* ctx, float* y, const float* x, int64_t rows, int6
                      const int64_t* idx, int64_t n_src);
 /* x .= x .- lr .* gx   (update!(x, gx, (x,g) -> x .- lr.*g); lr = 1 is the reference default) */
 int yota_update_sgd(yota_ctx* ctx, float* x, const float* gx, int64_t n, float lr);
+/* One Adam step on the device, as Optimisers.jl's Adam applies it (the optimiser of the reference's
+ * examples: examples/flux/mlp.jl:82, utils.jl:5): m, v are the caller's first / second moment
+ * arrays (zero before step 1), t >= 1 the step number (bias correction 1 - beta^t). */
+int yota_update_adam(yota_ctx* ctx, float* x, const float* gx, float* m, float* v, int64_t n, float lr,
+                     float beta1, float beta2, float eps, int t);
 
 /* ---- multi-GPU: batch-sharded data parallelism, NCCL all-reduce of parameter grads ------ */
 /* 128-byte ncclUniqueId created on rank 0 and shipped to the others by the caller. */
@@ -246,6 +251,11 @@ int yota_allreduce_f32(yota_ctx* ctx, float* buf, int64_t n);
  * then is one training step; n = 0 clears the marks. */
 int yota_program_set_update(yota_program* p, const int32_t* in_slots, const int32_t* out_slots,
                             int64_t n, float lr);
+/* Same marks, Adam instead of SGD: the moments and the step counter are owned by the program
+ * (device memory, zero-initialised here; the counter advances once per run, on the device, so a
+ * replayed CUDA graph takes correct steps).  Calling it again resets the optimiser state. */
+int yota_program_set_update_adam(yota_program* p, const int32_t* in_slots, const int32_t* out_slots,
+                                 int64_t n, float lr, float beta1, float beta2, float eps);
 /* Symmetric memory for buffers that are all-reduced: collective (every rank calls it with the
  * same size, in the same order, after yota_comm_init).  Buffers carved from it are reduced by
  * the library's own NVSwitch kernel (multimem.ld_reduce / multimem.st over NCCL symmetric

@@ -391,6 +391,16 @@ def rrule_transpose(x):
     return y, pb
 
 
+def rrule_reshape(x, dims):
+    """ChainRules rrule(reshape, A, dims...): column-major reshape; the pullback reshapes back."""
+    y = np.asfortranarray(x.reshape(tuple(int(d) for d in dims), order="F"))
+
+    def pb(d):
+        return (NoTangent, np.asfortranarray(unthunk(d).reshape(x.shape, order="F"))) + (NoTangent,) * len(dims)
+
+    return y, pb
+
+
 def rrule_cat(dim, *xs):
     nd = max(dim, max(x.ndim for x in xs))
     ps = [_pad(x, nd) for x in xs]
@@ -568,6 +578,8 @@ class OracleTape:
                 y, pb = rrule_logsoftmax(vals[0], kw.get("dims", 1))
             elif name in ("transpose", "adjoint"):
                 y, pb = rrule_transpose(vals[0])
+            elif name == "reshape":
+                y, pb = rrule_reshape(vals[0], vals[1:])
             elif name in ("vcat", "hcat", "cat"):
                 dim = {"vcat": 1, "hcat": 2}.get(name) or kw["dims"]
                 y, pb = rrule_cat(dim, *vals)

@@ -194,3 +194,31 @@ def linreg2_data(n_vars=10, n_out=2, n_obs=1000, seed=2):  # test/test_examples.
     W_true, b_true = r.random((n_out, n_vars)), r.random(n_out)
     Yv = W_true @ X + b_true[:, None] + 0.1 * r.standard_normal((n_out, n_obs))
     return X, Yv, W_true, b_true, r.random((n_out, n_vars)), r.random(n_out)
+
+
+# ---- the reference's examples: convnet (examples/flux/convnet.jl:53-66) and the MLP loss
+# (examples/flux/mlp.jl:54,81) over the composite layers of yota_b200.jl ---------------------
+def convnet_loss(w1, b1, Wd, bd, x, y):
+    """Conv((3,3), C=>8, relu) -> MaxPool((2,2)) -> flatten -> Dense -> logitcrossentropy."""
+    h = jl.relu(jl.conv(x, w1) + jl.reshape(b1, 1, 1, b1.shape[0], 1))
+    h = jl.maxpool2(h)
+    W, H, C, N = h.shape
+    return jl.logitcrossentropy(Wd @ jl.reshape(h, W * H * C, N) + bd, y)
+
+
+def convnet_args(W=10, H=10, C=3, N=4, CO=8, classes=5, seed=7):
+    r = rng(seed)
+    OW, OH = (W - 2) // 2, (H - 2) // 2
+    lab = r.integers(0, classes, size=N)
+    y = np.zeros((classes, N), order="F")
+    y[lab, np.arange(N)] = 1
+    return (r.standard_normal((3, 3, C, CO)) / 5, 0.1 * r.standard_normal(CO), r.standard_normal((classes, OW * OH * CO)) / 8,
+            0.1 * r.standard_normal(classes), r.standard_normal((W, H, C, N)), y)
+
+
+def mlp_relu_loss(W1, b1, W2, b2, x, y):  # examples/flux/mlp.jl:52-56, 81: Dense(relu) -> Dense, logitcrossentropy
+    return jl.logitcrossentropy(W2 @ jl.relu(W1 @ x + b1) + b2, y)
+
+
+def sum_of_f(x):  # sum(f, xs) with a non-primitive f: the nested tape of f (src/chainrules.jl:101-124), inlined
+    return jl.sum(lambda t: jl.sin(t) * t + 1.0, x)

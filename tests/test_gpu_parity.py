@@ -391,3 +391,56 @@ def test_eager_rrule_is_the_operator_api():
     t = pb(Y.cu(np.ones_like(A)))
     assert t[0] is Y.NoTangent and t[1] is Y.NoTangent
     assert np.allclose(t[2].to_host(), 1 - np.tanh(A) ** 2, rtol=1e-5, atol=1e-6)
+
+
+# ---- the reference's example models and optimiser on the device ------------------------------
+def test_convnet_and_relu_mlp_examples():
+    """examples/flux/convnet.jl:53-66 (Conv + relu, MaxPool, flatten, Dense, logitcrossentropy) and
+    examples/flux/mlp.jl:52-56,81 through the composite layers: conv = linear-index gather + GEMM +
+    permuting gather, so its pullback is the bit-exact scatter-add (col2im) + two GEMMs."""
+    U.check_parity(cases.convnet_loss, f32(cases.convnet_args()))
+    big = f32(cases.convnet_args(W=18, H=18, C=4, N=16, CO=16, classes=10))
+    U.check_parity(cases.convnet_loss, big)
+    a = cases.c1_args(48, 32, 10, 64)
+    y = np.eye(10, dtype=F32)[:, cases.rng(5).integers(0, 10, 64)]
+    U.check_parity(cases.mlp_relu_loss, list(a[:5]) + [np.asfortranarray(y)])
+    U.check_parity(cases.sum_of_f, [cases.rng(6).standard_normal((33, 20)).astype(F32)])
+
+
+def _adam_host(x, g, m, v, t, lr, b1, b2, eps):
+    f = F32
+    m = f(b1) * m + (f(1) - f(b1)) * g
+    v = f(b2) * v + (f(1) - f(b2)) * (g * g)
+    c1, c2 = f(1) - f(b1) ** f(t), f(1) - f(b2) ** f(t)
+    return x - (m / c1) / (np.sqrt(v / c2) + f(eps)) * f(lr), m, v
+
+
+def test_adam_standalone_and_folded_into_the_run():
+    """Optimisers.Adam (examples/flux/mlp.jl:82): the stand-alone step against the Float32 host
+    formula, then folded into the run -- program-owned moments, device-side step counter -- over an
+    eager run, the captured run and two graph replays (the counter must advance inside the graph)."""
+    r = cases.rng(13)
+    n = 1000
+    x, g = r.standard_normal(n).astype(F32), r.standard_normal(n).astype(F32)
+    m, v = np.zeros(n, F32), np.zeros(n, F32)
+    dx, dg, dm, dv = Y.cu(x), Y.cu(g), Y.cu(m), Y.cu(v)
+    for t in (1, 2, 3):
+        Y.update_adam(dx, dg, dm, dv, t, lr=0.01)
+        x, m, v = _adam_host(x, g, m, v, t, 0.01, 0.9, 0.999, 1e-8)
+        assert np.allclose(dx.to_host(), x, rtol=2e-6, atol=1e-7) and np.allclose(dm.to_host(), m, rtol=1e-6)
+    W, b, xx = r.random((4, 3)).astype(F32), r.random(4).astype(F32), r.random((3, 5)).astype(F32)
+    dW, db, dxx = Y.cu(W), Y.cu(b), Y.cu(xx)
+    gf = Y.CompiledGrad(Y.gradtape(cases.loss_tanh, dW, db, dxx))
+    gf.set_update([0, 1], lr=0.05, optimizer="adam")
+    mW, vW, mb, vb = np.zeros_like(W), np.zeros_like(W), np.zeros_like(b), np.zeros_like(b)
+    for t in (1, 2, 3, 4):
+        _, g_ = gf.run([dW, db, dxx])
+        gW, gb = g_[0].to_host(), g_[1].to_host()
+        W, mW, vW = _adam_host(W, gW, mW, vW, t, 0.05, 0.9, 0.999, 1e-8)
+        b, mb, vb = _adam_host(b, gb, mb, vb, t, 0.05, 0.9, 0.999, 1e-8)
+        assert np.allclose(dW.to_host(), W, rtol=5e-6, atol=1e-7), t
+        assert np.allclose(db.to_host(), b, rtol=5e-6, atol=1e-7), t
+    gf.set_update([], lr=1.0)
+    before = dW.to_host()
+    gf.run([dW, db, dxx])
+    assert np.array_equal(before, dW.to_host())

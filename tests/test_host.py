@@ -297,3 +297,42 @@ def test_play_configs_and_seeds(fake_device):
     tape = Y.gradtape(lambda x: 2 * x, A((3,)), seed="auto")
     _, g = fake_device.play(tape, _FakeArr(x), seed="auto")
     assert np.allclose(g[1].to_host(), 2 * np.ones(3))
+
+
+# ---- composite layers (conv / maxpool / logitcrossentropy), reshape, sum(f, x) ----------------
+def test_conv_composite_is_nnlib_conv():
+    """The gather + GEMM + gather composite against an independent reference: scipy's true
+    convolution per (input channel, output channel) pair -- NNlib.conv flips the kernel."""
+    from scipy.signal import convolve
+
+    r = cases.rng(3)
+    x, w = r.standard_normal((7, 6, 3, 2)), r.standard_normal((3, 2, 3, 4))
+    val, g = O.grad(lambda x, w: jl.sum(jl.conv(x, w) ** 2), x, w, dtype=np.float64)
+    y = np.zeros((5, 5, 4, 2))
+    for n in range(2):
+        for co in range(4):
+            y[:, :, co, n] = sum(convolve(x[:, :, ci, n], w[:, :, ci, co], mode="valid") for ci in range(3))
+    assert np.isclose(val, (y ** 2).sum(), rtol=1e-12)
+    # dw against the definition: dw[kw,kh,ci,co] = sum 2 y[ow,oh,co,n] x[ow+KW-1-kw, oh+KH-1-kh, ci, n]
+    dw = np.zeros_like(w)
+    for kw in range(3):
+        for kh in range(2):
+            xs = x[2 - kw:2 - kw + 5, 1 - kh:1 - kh + 5]
+            dw[kw, kh] = np.einsum("abin,abon->io", xs, 2 * y)
+    assert np.allclose(g[2], dw, rtol=1e-11)
+
+
+def test_maxpool_logitcrossentropy_reshape_sum_of_f_on_the_oracle_and_lowered():
+    r = cases.rng(4)
+    xm = r.standard_normal((4, 6, 2, 3))
+    val, _ = O.grad(lambda x: jl.sum(jl.maxpool2(x) ** 2), xm, dtype=np.float64)
+    assert np.isclose(val, (xm.reshape(2, 2, 2, 3, 2, 3, order="F").max(axis=(0, 2)) ** 2).sum(), rtol=1e-12)
+    _lowered_vs_oracle(lambda x: jl.sum(jl.maxpool2(x) ** 2), (xm,))
+    _lowered_vs_oracle(cases.convnet_loss, cases.convnet_args())
+    a = cases.c1_args(6, 5, 4, 7)
+    y = np.eye(4)[:, cases.rng(5).integers(0, 4, 7)]
+    _lowered_vs_oracle(cases.mlp_relu_loss, [x.astype(np.float64) for x in a[:5]] + [y])
+    _lowered_vs_oracle(cases.sum_of_f, (r.standard_normal((3, 4)),))
+    _lowered_vs_oracle(lambda x: jl.sum(jl.reshape(x, 6, 2) @ jl.reshape(x, 2, 6)), (r.standard_normal((3, 4)),))
+    with pytest.raises(ValueError):
+        Y.gradtape(lambda x: jl.sum(jl.reshape(x, 5, 2)), A((3, 4)))

@@ -5,7 +5,7 @@ Same surface as the reference for the hot path -- `grad`, `gradtape`, `compile`,
 ABI of `include/yota_cuda.h`.  See DESIGN.md and INTEGRATION.md.
 """
 from . import jl  # noqa: F401
-from .api import GRAD_CACHE, CompiledGrad, compile, grad, grad_compile, gradtape, reset, update  # noqa: F401
+from .api import GRAD_CACHE, CompiledGrad, compile, grad, grad_compile, gradtape, reset, update, update_adam  # noqa: F401
 from .device import B200Array, context, cu  # noqa: F401
 from .eager import play, rrule  # noqa: F401
 from .ffi import YotaError  # noqa: F401

@@ -160,9 +160,11 @@ class CompiledGrad:
         labels = names.value.decode().split("\n")
         return [(labels[i] if i < len(labels) else "?", rec[3 * i], rec[3 * i + 1], rec[3 * i + 2]) for i in range(n)]
 
-    def set_update(self, arg_indices, lr=1.0):
+    def set_update(self, arg_indices, lr=1.0, optimizer="sgd", beta=(0.9, 0.999), eps=1e-8):
         """Fold update!(arg, grad) into every run for these argument positions (0-based):
-        arg .= arg .- lr .* grad after the sweep (and after the all-reduce, if marked)."""
+        arg .= arg .- lr .* grad after the sweep (and after the all-reduce, if marked).
+        optimizer="adam": Optimisers.jl's Adam with program-owned moments and a device-side step
+        counter (one optimiser step per run; call again to reset the state)."""
         ins = [self.low.arg_slots[i] for i in arg_indices]
         outs = []
         for i in arg_indices:
@@ -172,7 +174,12 @@ class CompiledGrad:
             outs.append(g[1])
         a = (C.c_int32 * max(1, len(ins)))(*ins)
         b = (C.c_int32 * max(1, len(outs)))(*outs)
-        ffi.check(ffi.lib().yota_program_set_update(self.h, a, b, len(ins), float(lr)))
+        if optimizer == "adam":
+            ffi.check(ffi.lib().yota_program_set_update_adam(self.h, a, b, len(ins), float(lr), float(beta[0]), float(beta[1]), float(eps)))
+        elif optimizer == "sgd":
+            ffi.check(ffi.lib().yota_program_set_update(self.h, a, b, len(ins), float(lr)))
+        else:
+            raise ValueError(f"unknown optimizer {optimizer!r}")
 
     def set_allreduce(self, out_slots):
         arr = (C.c_int32 * max(1, len(out_slots)))(*out_slots)
@@ -246,6 +253,14 @@ class _TrivialGrad:
             return self.res.val, (ZeroTangent,) + tuple(ZeroTangent for _ in args)
         k = self.pos.index(self.res.id)
         return args[k], (ZeroTangent,) + tuple(seed if i == k else ZeroTangent for i in range(len(args)))
+
+
+def update_adam(x, gx, m, v, t, lr=1e-3, beta=(0.9, 0.999), eps=1e-8):
+    """One Adam step on device arrays (Optimisers.jl semantics; t >= 1 is the step number)."""
+    assert all(isinstance(a, B200Array) for a in (x, gx, m, v)) and x.dims == gx.dims == m.dims == v.dims
+    ffi.check(ffi.lib().yota_update_adam(x.ctx.h, x.ptr, gx.ptr, m.ptr, v.ptr, x.numel, float(lr), float(beta[0]),
+                                         float(beta[1]), float(eps), int(t)))
+    return x
 
 
 def update(x, gx, lr=1.0):

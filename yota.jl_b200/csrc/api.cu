@@ -387,4 +387,12 @@ int yota_update_sgd(yota_ctx* ctx, float* x, const float* gx, int64_t n, float l
   return launch_axpy(x, gx, n, lr, ctx->stream);
 }
 
+int yota_update_adam(yota_ctx* ctx, float* x, const float* gx, float* m, float* v, int64_t n, float lr, float beta1,
+                     float beta2, float eps, int t) {
+  if (!ctx || t < 1) YOTA_FAIL(YOTA_E_ARG, "yota_update_adam: bad arguments");
+  YOTA_TRY(ctx_ensure_device(ctx));
+  YOTA_TRY(ctx_join_comm(ctx, ctx->stream));
+  return launch_adam(x, gx, m, v, n, lr, beta1, beta2, eps, nullptr, t, ctx->stream);
+}
+
 }  // extern "C"

@@ -267,6 +267,9 @@ int launch_transpose(float* y, const float* x, long long R, long long C, cudaStr
 int launch_copy_strided(float* dst, const float* src, int nd, const long long* dims, const long long* dst_stride,
                         const long long* src_stride, cudaStream_t s);
 int launch_axpy(float* x, const float* g, long long n, float lr, cudaStream_t s);
+int launch_adam(float* x, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
+                const int* t_dev, int t_host, cudaStream_t s);
+int launch_tick(int* t, cudaStream_t s);
 
 // ---- NCCL (comm.cu) ---------------------------------------------------------------------
 int comm_reserved_sms(yota_ctx* ctx);

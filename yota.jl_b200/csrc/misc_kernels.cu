@@ -106,4 +106,42 @@ int launch_axpy(float* x, const float* g, long long n, float lr, cudaStream_t s)
   return YOTA_OK;
 }
 
+// Adam as Optimisers.jl applies it (examples/flux/mlp.jl:82, utils.jl:5 use Optimisers.Adam):
+//   m = b1 m + (1 - b1) g;  v = b2 v + (1 - b2) g^2;  x -= m / (1 - b1^t) / (sqrt(v / (1 - b2^t)) + eps) * lr
+// The step number lives on the device (t_dev: steps taken so far) so that a replayed CUDA graph
+// advances it; t_host >= 1 is used by the stand-alone entry.  Non-contracted arithmetic: a Float32
+// host evaluation of the same expression gives the same bits up to the libm powf / sqrtf.
+__global__ void adam_kernel(float* __restrict__ x, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
+                            const int* __restrict__ t_dev, int t_host) {
+  const int t = t_dev ? *t_dev + 1 : t_host;
+  const float c1 = __fsub_rn(1.f, powf(b1, (float)t)), c2 = __fsub_rn(1.f, powf(b2, (float)t));
+  const float o1 = __fsub_rn(1.f, b1), o2 = __fsub_rn(1.f, b2);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i];
+    const float mi = __fadd_rn(__fmul_rn(b1, m[i]), __fmul_rn(o1, gi));
+    const float vi = __fadd_rn(__fmul_rn(b2, v[i]), __fmul_rn(o2, __fmul_rn(gi, gi)));
+    m[i] = mi;
+    v[i] = vi;
+    const float step = __fmul_rn(__fdiv_rn(__fdiv_rn(mi, c1), __fadd_rn(__fsqrt_rn(__fdiv_rn(vi, c2)), eps)), lr);
+    x[i] = __fsub_rn(x[i], step);
+  }
+}
+__global__ void tick_kernel(int* t) { *t += 1; }
+
+int launch_adam(float* x, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
+                const int* t_dev, int t_host, cudaStream_t s) {
+  if (n == 0) return YOTA_OK;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  adam_kernel<<<(unsigned)blocks, 256, 0, s>>>(x, g, m, v, n, lr, b1, b2, eps, t_dev, t_host);
+  YOTA_CUDA(cudaGetLastError());
+  return YOTA_OK;
+}
+int launch_tick(int* t, cudaStream_t s) {
+  tick_kernel<<<1, 1, 0, s>>>(t);
+  YOTA_CUDA(cudaGetLastError());
+  return YOTA_OK;
+}
+
 }  // namespace yota

@@ -164,6 +164,11 @@ struct yota_program {
   // update!(x, gx) folded into the run (yota_program_set_update): param input slot, grad output slot
   std::vector<std::pair<int, int>> updates;
   float update_lr = 1.f;
+  // Adam state of the marked pairs (yota_program_set_update_adam): per pair m and v, one step counter
+  bool adam = false;
+  float adam_b1 = 0.9f, adam_b2 = 0.999f, adam_eps = 1e-8f;
+  std::vector<float*> adam_m, adam_v;
+  int* adam_t = nullptr;
 };
 
 namespace yota {
@@ -1561,11 +1566,22 @@ extern "C" int yota_program_stats(yota_program* p, int64_t* n_steps, int64_t* n_
   return YOTA_OK;
 }
 
+static void free_adam_state(yota_program* p) {
+  for (float* q : p->adam_m) cudaFree(q);
+  for (float* q : p->adam_v) cudaFree(q);
+  if (p->adam_t) cudaFree(p->adam_t);
+  p->adam_m.clear();
+  p->adam_v.clear();
+  p->adam_t = nullptr;
+  p->adam = false;
+}
+
 extern "C" int yota_program_destroy(yota_program* p) {
   if (!p) return YOTA_OK;
   for (auto& g : p->graphs)
     if (g.exec) cudaGraphExecDestroy(g.exec);
   for (auto e : p->ar_events) cudaEventDestroy(e);
+  free_adam_state(p);
   if (p->arena) cudaFree(p->arena);
   delete p;
   return YOTA_OK;
@@ -2015,10 +2031,16 @@ static int run_all_steps(yota_program& P, cudaStream_t s, bool with_comm, Timeli
     const long long n = C.out_bytes[u.second] / 4;
     YOTA_TRY(ctx_wait_pending(ctx, P.bound_out[u.second], (size_t)n * 4, s));
     if (tl) YOTA_TRY(tl->open("update! input " + std::to_string(u.first), s));
-    YOTA_TRY(launch_axpy(static_cast<float*>(P.bound_in[u.first]), static_cast<const float*>(P.bound_out[u.second]), n,
-                         P.update_lr, s));
+    float* x = static_cast<float*>(P.bound_in[u.first]);
+    const float* gx = static_cast<const float*>(P.bound_out[u.second]);
+    if (P.adam) {
+      const size_t k = (size_t)(&u - P.updates.data());
+      YOTA_TRY(launch_adam(x, gx, P.adam_m[k], P.adam_v[k], n, P.update_lr, P.adam_b1, P.adam_b2, P.adam_eps, P.adam_t, 0, s));
+    } else
+      YOTA_TRY(launch_axpy(x, gx, n, P.update_lr, s));
     if (tl) YOTA_TRY(tl->close(s));
   }
+  if (P.adam && !P.updates.empty()) YOTA_TRY(launch_tick(P.adam_t, s));  // one optimiser step per run
   return YOTA_OK;
 }
 
@@ -2211,6 +2233,34 @@ extern "C" int yota_program_timeline(yota_program* p, void* const* in_ptrs, int6
   return (int)std::min<int64_t>(n, cap_recs);
 }
 
+extern "C" int yota_program_set_update_adam(yota_program* p, const int32_t* in_slots, const int32_t* out_slots,
+                                            int64_t n, float lr, float beta1, float beta2, float eps) {
+  YOTA_TRY(yota_program_set_update(p, in_slots, out_slots, n, lr));  // validates the pairs, clears graphs and old state
+  if (n == 0) return YOTA_OK;
+  YOTA_TRY(ctx_ensure_device(p->ctx));
+  YOTA_TRY(plan_comm(*p));
+  for (auto& u : p->updates) {
+    const size_t bytes = (size_t)p->comm.out_bytes[u.second];
+    float *m = nullptr, *v = nullptr;
+    if (cudaMalloc((void**)&m, bytes ? bytes : 4) != cudaSuccess || cudaMalloc((void**)&v, bytes ? bytes : 4) != cudaSuccess) {
+      if (m) cudaFree(m);
+      free_adam_state(p);
+      YOTA_FAIL(YOTA_E_NOMEM, "yota_program_set_update_adam: cannot allocate the moment arrays");
+    }
+    YOTA_CUDA(cudaMemsetAsync(m, 0, bytes, p->ctx->stream));
+    YOTA_CUDA(cudaMemsetAsync(v, 0, bytes, p->ctx->stream));
+    p->adam_m.push_back(m);
+    p->adam_v.push_back(v);
+  }
+  YOTA_CUDA(cudaMalloc((void**)&p->adam_t, sizeof(int)));
+  YOTA_CUDA(cudaMemsetAsync(p->adam_t, 0, sizeof(int), p->ctx->stream));
+  p->adam = true;
+  p->adam_b1 = beta1;
+  p->adam_b2 = beta2;
+  p->adam_eps = eps;
+  return YOTA_OK;
+}
+
 extern "C" int yota_program_set_update(yota_program* p, const int32_t* in_slots, const int32_t* out_slots, int64_t n,
                                        float lr) {
   if (!p || n < 0 || (n > 0 && (!in_slots || !out_slots))) YOTA_FAIL(YOTA_E_ARG, "yota_program_set_update: bad arguments");
@@ -2227,6 +2277,7 @@ extern "C" int yota_program_set_update(yota_program* p, const int32_t* in_slots,
       YOTA_FAIL(YOTA_E_SHAPE, "yota_program_set_update: input %d and output %d are not Float32 arrays of one size", a, b);
     ups.push_back({a, b});
   }
+  free_adam_state(p);
   p->updates = ups;
   p->update_lr = lr;
   for (auto& g : p->graphs)

@@ -65,6 +65,8 @@ SYMBOLS = {
     "yota_scatter_add_cols": (_i, [_vp, _vp, _i64, _i64, _vp, _vp, _i64]),
     "yota_gather_cols": (_i, [_vp, _vp, _vp, _i64, _i64, _vp, _i64]),
     "yota_update_sgd": (_i, [_vp, _vp, _vp, _i64, _f]),
+    "yota_update_adam": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _i]),
+    "yota_program_set_update_adam": (_i, [_vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _i64, _f, _f, _f, _f]),
     "yota_comm_unique_id": (_i, [_vp]),
     "yota_comm_init": (_i, [_vp, _i, _i, _vp]),
     "yota_comm_destroy": (_i, [_vp]),

@@ -101,6 +101,11 @@ def infer(fn, avals, kw):
     if fn in ("transpose", "adjoint"):
         d = _dims(avals[0])
         return AVal((1, d[0]) if len(d) == 1 else (d[1], d[0]))
+    if fn == "reshape":
+        d = tuple(int(n) for n in avals[1:])
+        if int(np.prod(d)) != int(np.prod(_dims(avals[0]))):
+            raise ValueError(f"DimensionMismatch: new dimensions {d} must be consistent with array size {_dims(avals[0])}")
+        return AVal(d, avals[0].dtype)
     if fn in ("vcat", "hcat", "cat"):
         dim = {"vcat": 1, "hcat": 2}.get(fn) or int(kw["dims"])
         ds = [_dims(a) for a in avals]
@@ -234,6 +239,8 @@ def lower_fwd(b, fn, vals, kw, out):
         return y, ("lsm", y)
     if fn in ("transpose", "adjoint"):
         return b.op(ir.OP_TRANSPOSE, (vals[0],), od), ("tr", b.dims(vals[0]))
+    if fn == "reshape":
+        return b.op(ir.OP_RESHAPE, (vals[0],), od), ("rs", b.dims(vals[0]), len(vals) - 1)
     if fn in ("vcat", "hcat", "cat"):
         dim = {"vcat": 1, "hcat": 2}.get(fn) or int(kw["dims"])
         return b.op(ir.OP_CAT, tuple(vals), od, iattr=(dim,)), ("cat", dim, [b.dims(v) for v in vals])
@@ -340,6 +347,8 @@ def lower_pb(b, fn, saved, d):
         return (N, b.op(ir.EW_SUB, (d, _mul(b, s, e)), yd))
     if k == "tr":
         return (N, b.op(ir.OP_TRANSPOSE, (d,), saved[1]))
+    if k == "rs":
+        return (N, b.op(ir.OP_RESHAPE, (d,), saved[1])) + (N,) * saved[2]
     if k == "cat":
         _, dim, dlist = saved
         outs, off = [], 1
