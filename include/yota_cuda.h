@@ -224,6 +224,13 @@ int yota_gemm(yota_ctx* ctx, int mode, int transA, int transB, int64_t m, int64_
  * sequential fold; src/helpers.jl:7-11).  idx is 1-based Int64 on the device. */
 int yota_scatter_add_cols(yota_ctx* ctx, float* dx, int64_t rows, int64_t n_dst, const float* dy,
                           const int64_t* idx, int64_t n_src);
+/* Destination-sharded form for multi-GPU use: this rank owns the table
+ * columns dst_lo <= j < dst_hi (0-based, half open) of the n_dst and computes only them,
+ * dx_shard[rows x (dst_hi - dst_lo)], from ALL sources (dy, idx replicated or gathered by the
+ * caller).  No exchange and no reduction: every destination's fold keeps its global source
+ * order, so the concatenation of the shards is bit-identical to yota_scatter_add_cols. */
+int yota_scatter_add_cols_sharded(yota_ctx* ctx, float* dx_shard, int64_t rows, int64_t n_dst, int64_t dst_lo,
+                                  int64_t dst_hi, const float* dy, const int64_t* idx, int64_t n_src);
 /* y[:, k] = x[:, idx[k]] */
 int yota_gather_cols(yota_ctx* ctx, float* y, const float* x, int64_t rows, int64_t n_dst,
                      const int64_t* idx, int64_t n_src);

@@ -75,3 +75,24 @@ for mode, flags, tol in (("fp32", 0, 2e-5), ("tf32", ffi.FLAG_GEMM_TF32, 5e-3)):
         if rank == 0:
             print(f"DP_GPU_OK mode={mode} allreduce={variant} nranks={nranks} symm={ffi.lib().yota_comm_symm_available(ctx.h)}", flush=True)
 
+
+# destination-sharded, bit-exact scatter-add over the ranks: each rank folds its
+# slice of the table from the replicated (dy, idx); gathered over ranks it equals the one-GPU result
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+r_ = np.random.default_rng(99)
+rows, n_dst, n_src = 64, 4096, 50000
+V = r_.standard_normal((rows, n_src)).astype(np.float32)
+idx = r_.integers(1, n_dst + 1, size=n_src).astype(np.int64)
+dV, di = Y.cu(V), Y.cu(idx)
+full = Y.B200Array((rows, n_dst))
+ffi.check(ffi.lib().yota_scatter_add_cols(ctx.h, full.ptr, rows, n_dst, dV.ptr, di.ptr, n_src))
+shard, (lo, hi) = dp.scatter_add_cols_sharded(dV, di, n_dst)
+mine = torch.from_numpy(np.ascontiguousarray(shard.to_host().T))  # (hi - lo, rows): rows of the gather are destinations
+parts = [torch.empty((dp.dest_shard(n_dst, q, nranks)[1] - dp.dest_shard(n_dst, q, nranks)[0], rows)) for q in range(nranks)]
+dist.all_gather(parts, mine)
+got = torch.cat(parts, dim=0).numpy().T
+assert np.array_equal(np.ascontiguousarray(got).view(np.uint32), np.ascontiguousarray(full.to_host()).view(np.uint32)), "sharded scatter-add differs"
+if rank == 0:
+    print(f"DP_GPU_OK dest_sharded_scatter nranks={nranks}", flush=True)

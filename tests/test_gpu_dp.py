@@ -28,5 +28,6 @@ def test_sharded_gradients_with_allreduce_match_the_full_batch():
            "127.0.0.1", "--master-port", str(port), os.path.join(HERE, "dp_gpu_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert f"DP_GPU_OK dest_sharded_scatter nranks={n}" in r.stdout, r.stdout[-3000:]
     for mode in ("fp32", "tf32"):
         assert f"DP_GPU_OK mode={mode} allreduce=nccl nranks={n}" in r.stdout, r.stdout[-3000:]

@@ -444,3 +444,29 @@ def test_adam_standalone_and_folded_into_the_run():
     before = dW.to_host()
     gf.run([dW, db, dxx])
     assert np.array_equal(before, dW.to_host())
+
+
+def test_destination_sharded_scatter_add_is_bit_exact():
+    """the scatter-add pullback sharded by destination over G ranks (emulated here
+    rank by rank on one GPU; tests/dp_gpu_check.py runs it on real ranks): the shards concatenate
+    to the one-GPU result bit for bit, duplicates, a hot destination, ragged splits and all."""
+    from yota_b200 import dp
+
+    r = cases.rng(17)
+    rows, n_dst, n_src = 64, 1000, 20000
+    V = r.standard_normal((rows, n_src)).astype(F32)
+    idx = r.integers(1, n_dst + 1, size=n_src).astype(np.int64)
+    idx[:500] = 7
+    ref = c_oracle.scatter_add_cols(np.asfortranarray(V), idx, n_dst)
+    dV, di = Y.cu(V), Y.cu(idx)
+    for G in (1, 2, 3, 8):
+        parts = []
+        for rank in range(G):
+            shard, (lo, hi) = dp.scatter_add_cols_sharded(dV, di, n_dst, rank, G)
+            assert shard.dims == (rows, hi - lo)
+            parts.append(shard.to_host())
+        assert np.array_equal(U.bits(np.concatenate(parts, axis=1)), U.bits(ref)), G
+    bad = idx.copy()
+    bad[3] = n_dst + 1
+    with pytest.raises(Y.YotaError, match="BoundsError"):
+        dp.scatter_add_cols_sharded(dV, Y.cu(bad), n_dst, 0, 2)[0].to_host()

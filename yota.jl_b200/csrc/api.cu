@@ -372,6 +372,18 @@ int yota_scatter_add_cols(yota_ctx* ctx, float* dx, int64_t rows, int64_t n_dst,
   return launch_scatter_add_cols(dx, rows, n_dst, dy, idx, n_src, w, ws, ctx->stream, nullptr, ctx->err_dev);
 }
 
+int yota_scatter_add_cols_sharded(yota_ctx* ctx, float* dx_shard, int64_t rows, int64_t n_dst, int64_t dst_lo,
+                                  int64_t dst_hi, const float* dy, const int64_t* idx, int64_t n_src) {
+  if (!ctx || dst_lo < 0 || dst_hi < dst_lo || dst_hi > n_dst) YOTA_FAIL(YOTA_E_ARG, "yota_scatter_add_cols_sharded: bad destination range");
+  YOTA_TRY(ctx_ensure_device(ctx));
+  YOTA_TRY(ctx_join_comm(ctx, ctx->stream));
+  const size_t ws = scatter_cols_workspace_bytes(dst_hi - dst_lo, n_src);
+  void* w = nullptr;
+  YOTA_TRY(ctx_scratch(ctx, ws, &w));
+  return launch_scatter_add_cols(dx_shard, rows, dst_hi - dst_lo, dy, idx, n_src, w, ws, ctx->stream, nullptr,
+                                 ctx->err_dev, dst_lo, n_dst);
+}
+
 int yota_gather_cols(yota_ctx* ctx, float* y, const float* x, int64_t rows, int64_t n_dst, const int64_t* idx,
                      int64_t n_src) {
   if (!ctx) YOTA_FAIL(YOTA_E_ARG, "null ctx");

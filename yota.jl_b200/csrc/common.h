@@ -257,7 +257,8 @@ size_t scatter_cols_workspace_bytes(long long n_dst, long long n_src);
 // been materialised first): the seed-scaled source of a scatter-add pullback read in place
 int launch_scatter_add_cols(float* dx, long long rows, long long n_dst, const float* dy, const int64_t* idx,
                             long long n_src, void* workspace, size_t ws_bytes, cudaStream_t s,
-                            const float* scale = nullptr, long long* err = nullptr);
+                            const float* scale = nullptr, long long* err = nullptr, long long dst_lo = 0,
+                            long long n_total = -1);
 int launch_gather_cols(float* y, const float* x, long long rows, long long n_dst, const int64_t* idx,
                        long long n_src, cudaStream_t s, long long* err = nullptr);
 

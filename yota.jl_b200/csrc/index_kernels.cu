@@ -265,24 +265,33 @@ static int exclusive_scan_u32(unsigned* data, long long n, unsigned* ws, cudaStr
 // ------------------------------------------------------------------------------------------
 constexpr int RS_T = 256, RS_WARPS = 8, RS_ROUNDS = 16, RS_TILE = RS_T * RS_ROUNDS;  // 4096 keys per CTA
 
-__device__ __forceinline__ unsigned key_of_idx(const int64_t* __restrict__ idx, long long i, long long n_dst,
+// Destination range of a scatter-add: all of 0..n_total-1, or -- destination-sharded over GPUs --
+// the slice [lo, lo + n_local) this rank owns.  Sources aimed elsewhere are skipped (they belong
+// to another rank's slice); every rank scans all indices, nobody exchanges or reduces anything,
+// and each destination's fold keeps its global source order: bit-identical to one GPU.
+struct DstRange {
+  long long n_total, lo, n_local;
+};
+
+__device__ __forceinline__ unsigned key_of_idx(const int64_t* __restrict__ idx, long long i, DstRange dr,
                                                long long* err = nullptr) {
-  const long long j = __ldg(idx + i) - 1;
+  long long j = __ldg(idx + i) - 1;
   // out-of-range indices (a BoundsError in Julia, src/helpers.jl:7-11 -> NNlib.scatter!) are
   // reported by the first histogram pass (err != nullptr there) and go to an overflow bucket
   // that is never read, so the fold itself stays in bounds
-  if (j < 0 || j >= n_dst) {
-    report_index_error(err, j + 1, n_dst);
-    return (unsigned)n_dst;
+  if (j < 0 || j >= dr.n_total) {
+    report_index_error(err, j + 1, dr.n_total);
+    return (unsigned)dr.n_local;
   }
-  return (unsigned)j;
+  j -= dr.lo;
+  return (j < 0 || j >= dr.n_local) ? (unsigned)dr.n_local : (unsigned)j;
 }
 
 // FROM_IDX: first pass -- keys are derived from the Int64 index vector on the fly and the value
 // is the source position itself, so no separate (key, value) initialisation pass is needed.
 template <int BITS, bool FROM_IDX>
 __global__ void __launch_bounds__(RS_T) radix_hist_kernel(const unsigned* __restrict__ keys,
-                                                          const int64_t* __restrict__ idx, long long n_dst,
+                                                          const int64_t* __restrict__ idx, DstRange n_dst,
                                                           long long n, int shift, unsigned* __restrict__ hist,
                                                           int nblocks, long long* err) {
   constexpr int ND = 1 << BITS;
@@ -309,7 +318,7 @@ __global__ void __launch_bounds__(RS_T) radix_hist_kernel(const unsigned* __rest
 template <int BITS, bool FROM_IDX>
 __global__ void __launch_bounds__(RS_T) radix_scatter_kernel(const unsigned* __restrict__ keys_in,
                                                              const unsigned* __restrict__ vals_in,
-                                                             const int64_t* __restrict__ idx, long long n_dst,
+                                                             const int64_t* __restrict__ idx, DstRange n_dst,
                                                              unsigned* __restrict__ keys_out,
                                                              unsigned* __restrict__ vals_out, long long n, int shift,
                                                              const unsigned* __restrict__ hist, int nblocks) {
@@ -424,7 +433,7 @@ static SortPlan sort_plan(long long n_dst, long long n_src) {
 }
 
 template <int BITS, bool FROM_IDX>
-static int radix_pass(const unsigned* kin, const unsigned* vin, const int64_t* idx, long long n_dst, unsigned* kout,
+static int radix_pass(const unsigned* kin, const unsigned* vin, const int64_t* idx, DstRange n_dst, unsigned* kout,
                       unsigned* vout, long long n, int shift, unsigned* hist, int nblocks, unsigned* scan_ws,
                       cudaStream_t s, long long* err) {
   constexpr int ND = 1 << BITS;
@@ -439,8 +448,10 @@ static int radix_pass(const unsigned* kin, const unsigned* vin, const int64_t* i
 // Sort (idx -> dest key, position) and build segment starts.  Results: *perm (source
 // positions grouped by destination, ascending inside a group), *seg (n_dst + 1 starts).
 static int sort_by_destination(const int64_t* idx, long long n_src, long long n_dst, void* ws, const unsigned** perm,
-                               const unsigned** seg, cudaStream_t s, long long* err) {
+                               const unsigned** seg, cudaStream_t s, long long* err, long long dst_lo = 0,
+                               long long n_total = -1) {
   const SortPlan sp = sort_plan(n_dst, n_src);
+  const DstRange dr{n_total < 0 ? n_dst : n_total, dst_lo, n_dst};
   char* base = static_cast<char*>(ws);
   unsigned* keys[2] = {reinterpret_cast<unsigned*>(base + sp.off_keys[0]),
                        reinterpret_cast<unsigned*>(base + sp.off_keys[1])};
@@ -456,9 +467,9 @@ static int sort_by_destination(const int64_t* idx, long long n_src, long long n_
     switch (sp.bits) {
 #define RP(B)                                                                                                     \
   case B:                                                                                                         \
-    st = pass == 0 ? radix_pass<B, true>(nullptr, nullptr, idx, n_dst, keys[0], vals[0], n_src, shift, hist,      \
+    st = pass == 0 ? radix_pass<B, true>(nullptr, nullptr, idx, dr, keys[0], vals[0], n_src, shift, hist,         \
                                          (int)sp.nblocks, scan_ws, s, err)                                        \
-                   : radix_pass<B, false>(keys[cur], vals[cur], idx, n_dst, keys[cur ^ 1], vals[cur ^ 1], n_src,  \
+                   : radix_pass<B, false>(keys[cur], vals[cur], idx, dr, keys[cur ^ 1], vals[cur ^ 1], n_src,     \
                                           shift, hist, (int)sp.nblocks, scan_ws, s, nullptr);                     \
     break;
       RP(4) RP(5) RP(6) RP(7) RP(8)
@@ -540,13 +551,13 @@ __global__ void __launch_bounds__(256) scatter_fold_cols_kernel(typename FV<V>::
 
 int launch_scatter_add_cols(float* dx, long long rows, long long n_dst, const float* dy, const int64_t* idx,
                             long long n_src, void* workspace, size_t ws_bytes, cudaStream_t s, const float* scale,
-                            long long* err) {
+                            long long* err, long long dst_lo, long long n_total) {
   if (rows * n_dst == 0) return YOTA_OK;
   if (n_src >= (1ll << 32) - 1 || n_dst >= (1ll << 32) - 2)
     YOTA_FAIL(YOTA_E_SHAPE, "scatter-add: more than 2^32 sources/destinations are not supported");
   if (ws_bytes < scatter_cols_workspace_bytes(n_dst, n_src)) YOTA_FAIL(YOTA_E_ARG, "scatter-add: workspace too small");
   const unsigned *perm, *seg;
-  YOTA_TRY(sort_by_destination(idx, n_src, n_dst, workspace, &perm, &seg, s, err));
+  YOTA_TRY(sort_by_destination(idx, n_src, n_dst, workspace, &perm, &seg, s, err, dst_lo, n_total));
   const bool v4 = (rows % 4 == 0) && ((reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(dy)) % 16 == 0);
   if (v4) {
     const int RV = (int)(rows / 4);

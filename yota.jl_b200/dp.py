@@ -121,3 +121,28 @@ def barrier():
     rank, nranks, _ = world()
     if nranks > 1:
         init_process_group().barrier()
+
+
+def dest_shard(n_dst, rank, nranks):
+    """Contiguous 0-based [lo, hi) slice of the n_dst destinations owned by `rank` (ragged tails
+    to the first ranks, like shard_columns)."""
+    base, extra = divmod(n_dst, nranks)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def scatter_add_cols_sharded(dy, idx, n_dst, rank=None, nranks=None, ctx=None):
+    """This rank's slice of  dx = zero(rows, n_dst); dx[:, idx[k]] += dy[:, k]  (the embedding
+    pullback, src/helpers.jl:7-11) sharded by DESTINATION: every rank scans all (dy, idx), folds only
+    the table columns it owns, exchanges nothing -- the concatenation over ranks equals the one-GPU
+    result bit for bit.  Returns (B200Array rows x (hi - lo), (lo, hi))."""
+    from .device import B200Array
+
+    ctx = ctx or context()
+    r, n, _ = world()
+    rank, nranks = (r if rank is None else rank), (n if nranks is None else nranks)
+    lo, hi = dest_shard(n_dst, rank, nranks)
+    rows, n_src = dy.dims
+    out = B200Array((rows, hi - lo), "f32", ctx)
+    ffi.check(ffi.lib().yota_scatter_add_cols_sharded(ctx.h, out.ptr, rows, n_dst, lo, hi, dy.ptr, idx.ptr, n_src))
+    return out, (lo, hi)

@@ -63,6 +63,7 @@ SYMBOLS = {
     "yota_program_timeline": (_i, [_vp, _pp, _i64, _pp, _i64, _f, _i, C.POINTER(_f), _i64, C.c_char_p, _i64]),
     "yota_gemm": (_i, [_vp, _i, _i, _i, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i]),
     "yota_scatter_add_cols": (_i, [_vp, _vp, _i64, _i64, _vp, _vp, _i64]),
+    "yota_scatter_add_cols_sharded": (_i, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _i64]),
     "yota_gather_cols": (_i, [_vp, _vp, _vp, _i64, _i64, _vp, _i64]),
     "yota_update_sgd": (_i, [_vp, _vp, _vp, _i64, _f]),
     "yota_update_adam": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _i]),
