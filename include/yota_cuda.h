@@ -189,6 +189,10 @@ int yota_program_destroy(yota_program* p);
 /* Human-readable plan (steps, fused regions, chosen kernels, workspace bytes).  Returns the
  * number of bytes needed (excluding NUL); writes at most cap bytes. */
 int64_t yota_program_describe(yota_program* p, char* buf, int64_t cap);
+/* The op list as the planner sees it after its rewrite passes (unrolled-loop batching ...), one
+ * tensor / op per text line (format: csrc/program.cu).  Diagnostic: lets a test execute the
+ * rewritten program with an independent interpreter.  Same return convention as describe. */
+int64_t yota_program_dump_ops(yota_program* p, char* buf, int64_t cap);
 /* Counters: n_launches = kernels launched per run; workspace_bytes = program-owned memory. */
 int yota_program_stats(yota_program* p, int64_t* n_steps, int64_t* n_launches,
                        int64_t* workspace_bytes, int64_t* n_fused_regions,

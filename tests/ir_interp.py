@@ -80,6 +80,8 @@ def run(prog, inputs, seed=1.0, dtype=np.float32):
             dim = o.iattr[0]
             nd = max(dim, max(a.ndim for a in ins))
             y = np.concatenate([_pad(a, nd) for a in ins], axis=dim - 1)
+        elif o.opcode == 200:  # internal zero-copy concatenation of the planner (members side by side)
+            y = np.concatenate([vals[m] for m in o.members], axis=1)
         elif o.opcode == ir.OP_SLICE:
             dim, a, b = o.iattr[:3]
             x = _pad(ins[0], max(dim, ins[0].ndim))

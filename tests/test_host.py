@@ -170,11 +170,19 @@ def test_planner_c5_gathers_in_the_region_and_scales_in_the_fold(built):
     assert ": getindex ->" in unf and ws_u > 8 << 30
 
 
-def test_planner_c4_slices_are_views_and_accumulation_is_in_place(built):
+def test_planner_c4_slices_are_views_and_accumulation_is_in_place(built, monkeypatch):
     av = [A((1024, 1024)), A((1024, 1024)), A((1024,)), A((1024, 128, 16))]
-    desc, _ = _plan(cases.make_c4(16), *av)
+    desc, (steps, *_r) = _plan(cases.make_c4(16), *av)
     assert ": getindex ->" not in desc, "x[:, :, t] must be a view, not a copy"
-    assert desc.count("(+= in place)") >= 3 * 15 - 2 and "slice += in place" in desc, desc
+    assert "unrolled loops: 5 " in desc and steps <= 4 * 16 + 8, desc  # batched: 2 GEMMs + 2 regions per step remain
+    # BF16 / 3xTF32 keep whole-array operand shadows: the loop stays unrolled there and the tape's
+    # accumulation is done in place (GEMM C += ..., slice +=) -- also the plan with the pass disabled
+    for flags, env in ((ffi.FLAG_GEMM_BF16, None), (0, "1")):
+        if env:
+            monkeypatch.setenv("YOTA_NO_LOOP_BATCHING", env)
+        desc, _ = _plan(cases.make_c4(16), *av, flags=flags)
+        assert "unrolled loops" not in desc and ": getindex ->" not in desc
+        assert desc.count("(+= in place)") >= 3 * 15 - 2 and "slice += in place" in desc, desc
 
 
 def alias_hazard_loss(X3, W, h):
@@ -336,3 +344,71 @@ def test_maxpool_logitcrossentropy_reshape_sum_of_f_on_the_oracle_and_lowered():
     _lowered_vs_oracle(lambda x: jl.sum(jl.reshape(x, 6, 2) @ jl.reshape(x, 2, 6)), (r.standard_normal((3, 4)),))
     with pytest.raises(ValueError):
         Y.gradtape(lambda x: jl.sum(jl.reshape(x, 5, 2)), A((3, 4)))
+
+
+# ---- unrolled-loop batching (C4): the op list AFTER the planner's rewrite, executed by the test
+# interpreter, against the oracle ---------------------------------------------------------------
+def _planned_ops(f, avals, flags=0):
+    """(IRProgram of the rewritten op list, Lowered, describe text)."""
+    lib = ffi.lib()
+    ctx = C.c_void_p()
+    ffi.check(lib.yota_init(0, C.byref(ctx)))
+    L = lower(Y.gradtape(f, *avals))
+    ops, tens = ffi.pack_program(L.prog)
+    h = C.c_void_p()
+    ffi.check(lib.yota_program_build(ctx, ops, len(L.prog.ops), tens, len(L.prog.tensors), flags, C.byref(h)))
+    n = lib.yota_program_dump_ops(h, None, 0)
+    buf = C.create_string_buffer(n + 1)
+    lib.yota_program_dump_ops(h, buf, n + 1)
+    nd = lib.yota_program_describe(h, None, 0)
+    dbuf = C.create_string_buffer(nd + 1)
+    lib.yota_program_describe(h, dbuf, nd + 1)
+    lib.yota_program_destroy(h)
+    lib.yota_shutdown(ctx)
+    prog = ir.IRProgram()
+    for line in buf.value.decode().splitlines():
+        if line.startswith("T "):
+            _, tid, dtype, ndim, d0, d1, d2, d3, kind, slot, cval = line.split()
+            prog.tensors.append(ir.IRTensor(int(tid), int(dtype), tuple(int(x) for x in (d0, d1, d2, d3))[:int(ndim)], int(kind),
+                                            int(slot), float(cval)))
+        else:
+            head, ia, fa, mem = line[2:].split("|")
+            hs = [int(x) for x in head.split()]
+            op = ir.IROp(hs[0], tuple(hs[3:3 + hs[2]]), hs[1], tuple(int(x) for x in ia.split()), tuple(float(x) for x in fa.split()))
+            op.members = [int(x) for x in mem.split()]
+            prog.ops.append(op)
+    prog.n_inputs, prog.n_outputs = L.prog.n_inputs, L.prog.n_outputs
+    return prog, L, dbuf.value.decode()
+
+
+@pytest.mark.parametrize("T,H,B", [(4, 8, 4), (7, 16, 8)])
+def test_unrolled_rnn_is_batched_and_still_the_same_function(built, T, H, B):
+    """C4: the T products Wx*x[:,:,t] become one GEMM, the accumulation chains of dWx, dWh, db and dx
+    one contraction each over the concatenated dz_t (placed side by side, no copies); the rewritten
+    op list computes what the tape computes (Float64, against the oracle)."""
+    f = cases.make_c4(T)
+    args = [a.astype(np.float64) for a in cases.c4_args(H, B, T)]
+    prog, L, desc = _planned_ops(f, [A(a.shape) for a in args])
+    assert "unrolled loops: 5 " in desc, desc
+    n_mm = sum(o.opcode == ir.OP_MATMUL for o in prog.ops)
+    outs = ir_interp.run(prog, args, dtype=np.float64)
+    val, g = O.grad(f, *args, dtype=np.float64)
+    assert np.allclose(outs[L.val[1]], val, rtol=1e-11)
+    for spec, gg in zip(L.grads, g[1:]):
+        assert np.allclose(outs[spec[1]], gg, rtol=1e-9, atol=1e-12), spec
+    # the serial part that remains: Wh*h_{t-1} and Wh'*dz_t per step, plus the batched ones
+    steps = [l for l in desc.splitlines() if l.strip().startswith("step")]
+    assert sum(": matmul" in l for l in steps) == 2 * (T - 1) + 4, desc
+    assert "in place" not in desc
+
+
+def test_loop_batching_leaves_other_programs_alone(built):
+    desc, _ = _plan(cases.make_c3(3, 64), *[A(a.shape) for a in cases.c3_args(3, 32, 64)])
+    assert "unrolled loops" not in desc
+    # an index-VECTOR scatter chain is never batched (its pullback is bit-exact, src/helpers.jl:7-11)
+    desc, _ = _plan(lambda E, i1, i2, i3, V: jl.sum((E[colon_, i1] + E[colon_, i2] + E[colon_, i3]) * V),
+                    A((8, 16)), A((12,), "i64"), A((12,), "i64"), A((12,), "i64"), A((8, 12)))
+    assert "unrolled loops" not in desc and desc.count("ungetindex") == 3, desc
+
+
+colon_ = jl.colon

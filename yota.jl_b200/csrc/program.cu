@@ -53,6 +53,7 @@ struct TInfo {
   int alias_of = -1;  // tensor whose storage this one shares: RESHAPE outputs, contiguous getindex slices
   long long alias_elem_off = 0;  // ... starting this many elements into it
   bool inplace_alias = false;    // alias made by an in-place accumulation: the whole buffer, rewritten
+  int alloc_step = -1;           // container of a zero-copy concatenation: first step that writes a member
   bool needed = false;
   bool materialized = false;
   int region = -1;  // region index if produced by a fused EW op
@@ -123,6 +124,11 @@ struct yota_program {
   std::vector<Region> regions;
   std::vector<Step> steps;
   std::vector<char> op_needed;
+  // zero-copy concatenations made by rewrite_unrolled_loops: container tensor -> members, in order
+  std::map<int, std::vector<int>> catv;
+  // a concatenation that is a column range of an earlier one: (container tensor, element offset)
+  std::map<int, std::pair<int, long long>> catv_view;
+  int n_batched = 0;  // accumulation chains / slice families the rewrite collapsed into one contraction
   std::vector<int> op_scale;  // UNGETINDEX ops: scalar tensor multiplied into the source on load (-1: none)
   int n_in = 0, n_out = 0;
   size_t arena_bytes = 0, const_bytes = 0;
@@ -301,6 +307,7 @@ static const char* opname(int opc) {
     case YOTA_OP_TRANSPOSE: return "transpose";
     case YOTA_OP_CAT: return "cat";
     case YOTA_OP_SLICE: return "slice";
+    case 200: return "concat (members placed in one buffer)";
   }
   return "?";
 }
@@ -357,6 +364,14 @@ static int validate(yota_program& P) {
       if (P.T[o.in[0]].numel != out.numel) YOTA_FAIL(YOTA_E_SHAPE, "op %zu (reshape): numel mismatch", i);
     } else if (opc == YOTA_OP_LOGSOFTMAX || opc == YOTA_OP_TRANSPOSE) {
       if (P.T[o.in[0]].numel != out.numel) YOTA_FAIL(YOTA_E_SHAPE, "op %zu (%s): numel mismatch", i, opname(opc));
+    } else if (opc == 200 /* OP_CATV: made by rewrite_unrolled_loops, never by the caller */ && P.catv.count(o.out)) {
+      long long cols = 0;
+      for (int m : P.catv[o.out]) {
+        if (m < 0 || m >= nt || P.T[m].producer < 0 || P.T[m].producer >= (int)i)
+          YOTA_FAIL(YOTA_E_ARG, "internal: concatenation member %%%d is not defined before op %zu", m, i);
+        cols += P.T[m].d.dims[1];
+      }
+      if (cols != out.d.dims[1]) YOTA_FAIL(YOTA_E_ARG, "internal: concatenation width mismatch");
     } else if (opc == YOTA_OP_GETINDEX || opc == YOTA_OP_UNGETINDEX || opc == YOTA_OP_CAT || opc == YOTA_OP_SLICE) {
       // checked when the step is built
     } else {
@@ -616,6 +631,40 @@ static int plan_fusion(yota_program& P) {
     TInfo& out = P.T[o.out];
     if (!is_ew(o.opcode))
       for (int j = 0; j < o.n_in; j++) F.force(root_of(P, o.in[j]));
+    if (o.opcode == 200 /* OP_CATV */) {
+      // zero-copy concatenation: every member becomes a view of the container and is written
+      // there by its own producer; the container is allocated when the first member is written
+      if (P.catv_view.count(o.out)) {  // a column range of another concatenation: just an alias of it
+        int last = -1;
+        for (int m : P.catv[o.out]) {
+          F.force(m);
+          last = std::max(last, P.T[m].def_step);
+        }
+        out.alias_of = P.catv_view[o.out].first;
+        out.alias_elem_off = P.catv_view[o.out].second;
+        out.def_step = last;
+        continue;
+      }
+      long long off = 0;
+      int first = 1 << 30, last = -1;
+      bool ok = true;
+      for (int m : P.catv[o.out]) {
+        F.force(m);
+        TInfo& mt = P.T[m];
+        ok = ok && mt.alias_of < 0 && mt.d.kind == YOTA_T_TEMP && mt.def_step >= 0;
+        mt.alias_of = o.out;
+        mt.alias_elem_off = off;
+        mt.materialized = true;
+        off += mt.numel;
+        first = std::min(first, mt.def_step);
+        last = std::max(last, mt.def_step);
+      }
+      if (!ok) YOTA_FAIL(YOTA_E_ARG, "internal: a concatenation member cannot be placed (alias / not a temporary)");
+      out.def_step = last;
+      out.alloc_step = first;
+      out.materialized = true;
+      continue;
+    }
     if (o.opcode == YOTA_OP_RESHAPE) {
       out.alias_of = o.in[0];
       const int r = root_of(P, o.in[0]);
@@ -1140,7 +1189,7 @@ static int plan_memory(yota_program& P) {
     if (ti.alias_of >= 0 || ti.d.kind != YOTA_T_TEMP || !ti.materialized || ti.def_step < 0) continue;
     if (ti.fwd_out_slot >= 0) continue;  // lives in the caller's output buffer
     if (ti.last_step < ti.def_step) ti.last_step = ti.def_step;
-    defs[ti.def_step].push_back((int)t);
+    defs[ti.alloc_step >= 0 ? ti.alloc_step : ti.def_step].push_back((int)t);
     frees[ti.last_step].push_back((int)t);
   }
   FreeList fl;
@@ -1229,6 +1278,365 @@ static int index_spec_of(const yota_program& P, const yota_op_desc& o, const TIn
   sp.nd_x = sp.n;
   *n_sel = nsel;
   return YOTA_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// unrolled loops: batching of the time-independent contractions
+// ------------------------------------------------------------------------------------------
+// Umlaut unrolls `for t in 1:T` at trace time, so an Elman RNN arrives as
+// T copies of  Wx*x[:,:,t],  and its pullback as T-term accumulation chains
+//     dWx = sum_t dz_t * x[:,:,t]',  dWh = sum_t dz_t * h_{t-1}',  db = sum_t sum(dz_t; dims=2),
+//     dx  = sum_t ungetindex(Wx' * dz_t, :, :, t)
+// built from `broadcast(+, dx, old)` ops (src/grad.jl:83-95).  Only  Wh*h_{t-1}  and  Wh'*dz_t
+// are truly serial.  This pass rewrites the op list (before DCE / fusion):
+//   * the T forward products become ONE  Wx * reshape(x, D, B*T)  whose result is read through
+//     slice views;
+//   * every accumulation chain whose leaves are per-step contractions of members of one family
+//     becomes ONE contraction over the concatenation  [dz_1 ... dz_T]  (K = T*B) -- and the
+//     concatenation costs nothing: the members are PLACED in one buffer (internal op OP_CATV:
+//     each member becomes a view of the container, written there by its own producer).
+// The summation order of the batched sums differs from the tape's left fold: this is the rtol
+// contract of the contraction modes (never applied to index-vector scatter-adds, whose pullbacks
+// are bit-exact), SURVEY §7 "Tape accumulation" (iii).  C4: 1290 -> ~520 steps.
+constexpr int OP_CATV = 200;
+
+static void init_tinfo(TInfo& ti) {
+  ti.numel = 1;
+  int nd = ti.d.ndim;
+  for (int d = 0; d < ti.d.ndim; d++) ti.numel *= ti.d.dims[d];
+  while (nd > 0 && ti.d.dims[nd - 1] == 1) nd--;
+  ti.nd = nd;
+  for (int d = 0; d < 4; d++) ti.dims[d] = d < nd ? ti.d.dims[d] : 1;
+}
+
+static void link_ops(yota_program& P) {
+  for (auto& t : P.T) {
+    t.producer = -1;
+    t.consumers.clear();
+  }
+  for (size_t i = 0; i < P.ops.size(); i++) {
+    const yota_op_desc& o = P.ops[i];
+    P.T[o.out].producer = (int)i;
+    for (int j = 0; j < o.n_in; j++) P.T[o.in[j]].consumers.push_back((int)i);
+    if (o.opcode == OP_CATV)
+      for (int m : P.catv[o.out]) P.T[m].consumers.push_back((int)i);
+  }
+}
+
+static int add_tensor(yota_program& P, std::initializer_list<long long> dims) {
+  TInfo t;
+  memset(&t.d, 0, sizeof(t.d));
+  t.d.dtype = YOTA_F32;
+  t.d.kind = YOTA_T_TEMP;
+  t.d.slot = -1;
+  t.d.ndim = (int)dims.size();
+  int k = 0;
+  for (long long v : dims) t.d.dims[k++] = v;
+  init_tinfo(t);
+  P.T.push_back(t);
+  return (int)P.T.size() - 1;
+}
+
+static yota_op_desc mk_op(int opcode, std::initializer_list<int> ins, int out) {
+  yota_op_desc o;
+  memset(&o, 0, sizeof(o));
+  o.opcode = opcode;
+  o.n_in = (int)ins.size();
+  int k = 0;
+  for (int v : ins) o.in[k++] = v;
+  o.out = out;
+  return o;
+}
+
+static bool same_shape(const TInfo& a, const TInfo& b) {
+  if (a.nd != b.nd) return false;
+  for (int d = 0; d < a.nd; d++)
+    if (a.dims[d] != b.dims[d]) return false;
+  return true;
+}
+
+static void rewrite_unrolled_loops(yota_program& P) {
+  const int mode = gemm_mode_of(P.flags);
+  // (BF16 / 3xTF32 keep whole-array operand shadows that are cast at first use: a container whose
+  //  members appear over time cannot be shadowed that way)
+  if ((P.flags & YOTA_FLAG_NO_FUSE) || mode == 2 || mode == 3 || getenv("YOTA_NO_LOOP_BATCHING")) return;
+  const int n_ops = (int)P.ops.size();
+  auto uses = [&](int t) { return (int)P.T[t].consumers.size(); };
+  struct Sl {
+    int X;
+    long long t;
+  };
+  auto slice_of = [&](int t, Sl* s) {
+    const int p = P.T[t].producer;
+    if (p < 0) return false;
+    const yota_op_desc& o = P.ops[p];
+    if (o.opcode != YOTA_OP_GETINDEX || o.iattr[0] != 3) return false;
+    const TInfo& x = P.T[o.in[0]];
+    if (x.d.ndim != 3 || x.d.dtype != YOTA_F32) return false;
+    if (o.iattr[1] != YOTA_IDX_COLON || o.iattr[4] != YOTA_IDX_COLON || o.iattr[7] != YOTA_IDX_INT) return false;
+    s->X = o.in[0];
+    s->t = o.iattr[8];
+    return s->t >= 1 && s->t <= x.d.dims[2];
+  };
+  std::map<int, std::vector<yota_op_desc>> ins_before, ins_after;
+  std::map<int, yota_op_desc> replace;
+  std::map<int, int> x2_of;  // 3-d array -> its (D, B*T) reshape (made by the forward batching, reused by dWx)
+  int n_batched = 0;
+
+  // ---- forward: A * x[:, :, t] for all t of an INPUT array -> one A * reshape(x) ----------------
+  {
+    std::map<std::pair<int, int>, std::vector<std::pair<long long, int>>> fam;
+    for (int i = 0; i < n_ops; i++) {
+      const yota_op_desc& o = P.ops[i];
+      Sl s;
+      if (o.opcode != YOTA_OP_MATMUL || o.iattr[0] || o.iattr[1] || !slice_of(o.in[1], &s)) continue;
+      if (P.T[o.in[0]].d.kind != YOTA_T_INPUT || P.T[s.X].d.kind != YOTA_T_INPUT || P.T[o.in[0]].d.ndim != 2) continue;
+      fam[{o.in[0], s.X}].push_back({s.t, i});
+    }
+    for (auto& kv : fam) {
+      auto& v = kv.second;
+      const TInfo &A = P.T[kv.first.first], &X = P.T[kv.first.second];
+      const long long D = X.d.dims[0], B = X.d.dims[1], T = X.d.dims[2], M = A.d.dims[0];
+      if ((long long)v.size() != T || T < 2 || A.d.dims[1] != D || (M * B) % 4) continue;
+      std::sort(v.begin(), v.end());
+      bool ok = true;
+      int first = n_ops;
+      for (long long k = 0; k < T; k++) {
+        ok = ok && v[k].first == k + 1;
+        first = std::min(first, v[k].second);
+      }
+      if (!ok) continue;
+      const int X2 = add_tensor(P, {D, B * T}), Zall = add_tensor(P, {M, B * T}), Z3 = add_tensor(P, {M, B, T});
+      x2_of[kv.first.second] = X2;
+      auto& pre = ins_before[first];
+      pre.push_back(mk_op(YOTA_OP_RESHAPE, {kv.first.second}, X2));
+      pre.push_back(mk_op(YOTA_OP_MATMUL, {kv.first.first, X2}, Zall));
+      pre.push_back(mk_op(YOTA_OP_RESHAPE, {Zall}, Z3));
+      for (auto& m : v) {
+        yota_op_desc g = mk_op(YOTA_OP_GETINDEX, {Z3}, P.ops[m.second].out);
+        g.iattr[0] = 3;
+        g.iattr[1] = YOTA_IDX_COLON;
+        g.iattr[4] = YOTA_IDX_COLON;
+        g.iattr[7] = YOTA_IDX_INT;
+        g.iattr[8] = g.iattr[9] = m.first;
+        replace[m.second] = g;
+      }
+      n_batched++;
+    }
+  }
+
+  // ---- pullback: accumulation chains  acc = leaf_n + (... + (leaf_1 + leaf_0)) ------------------
+  struct Chain {
+    std::vector<int> leaves, adds;
+    int tail;
+  };
+  std::vector<Chain> chains;
+  {
+    std::vector<int> tail_of(P.T.size(), -1);
+    for (int i = 0; i < n_ops; i++) {
+      const yota_op_desc& o = P.ops[i];
+      if (o.opcode != YOTA_EW_ADD || o.in[0] == o.in[1]) continue;
+      const int a = o.in[0], b = o.in[1];
+      if (!same_shape(P.T[a], P.T[o.out]) || !same_shape(P.T[b], P.T[o.out])) continue;
+      int c = -1, leaf = -1;
+      if (tail_of[a] >= 0 && uses(a) == 1) c = tail_of[a], leaf = b;
+      else if (tail_of[b] >= 0 && uses(b) == 1) c = tail_of[b], leaf = a;
+      if (c >= 0) {
+        chains[c].leaves.push_back(leaf);
+        chains[c].adds.push_back(i);
+        chains[c].tail = o.out;
+      } else {
+        chains.push_back({{a, b}, {i}, o.out});
+        c = (int)chains.size() - 1;
+      }
+      tail_of[o.out] = c;
+    }
+  }
+  enum { NT_SLICE, NT_PLAIN, UNGET_TN, SUMK };
+  struct Leaf {
+    int kind, dz, other;  // other: X (NT_SLICE), h (NT_PLAIN), W (UNGET_TN)
+    long long t;
+  };
+  auto classify = [&](int l, Leaf* lf) {
+    if (uses(l) != 1 || P.T[l].producer < 0) return false;
+    const yota_op_desc& o = P.ops[P.T[l].producer];
+    Sl s;
+    if (o.opcode == YOTA_OP_MATMUL && !o.iattr[0] && o.iattr[1]) {
+      if (slice_of(o.in[1], &s))
+        *lf = {NT_SLICE, o.in[0], s.X, s.t};
+      else
+        *lf = {NT_PLAIN, o.in[0], o.in[1], 0};
+      return true;
+    }
+    if (o.opcode == YOTA_OP_UNGETINDEX && o.iattr[0] == 3 && o.iattr[1] == YOTA_IDX_COLON && o.iattr[4] == YOTA_IDX_COLON &&
+        o.iattr[7] == YOTA_IDX_INT && o.n_in == 1) {
+      const int src = o.in[0];
+      if (uses(src) != 1 || P.T[src].producer < 0) return false;
+      const yota_op_desc& m = P.ops[P.T[src].producer];
+      if (m.opcode != YOTA_OP_MATMUL || !m.iattr[0] || m.iattr[1]) return false;
+      *lf = {UNGET_TN, m.in[1], m.in[0], o.iattr[8]};
+      return true;
+    }
+    if (o.opcode == YOTA_OP_SUM && o.iattr[0] == 2 && o.fattr[0] == 1.0 && P.T[o.in[0]].d.ndim == 2) {
+      *lf = {SUMK, o.in[0], -1, 0};
+      return true;
+    }
+    return false;
+  };
+  // containers (zero-copy concatenations) made so far
+  struct Cont {
+    int tensor;
+    std::vector<int> members;
+  };
+  std::vector<Cont> conts;
+  std::map<int, std::pair<int, int>> where;  // member -> (container, position)
+  auto placeable = [&](int m, const TInfo& like) {
+    const TInfo& t = P.T[m];
+    if (t.d.kind != YOTA_T_TEMP || t.d.dtype != YOTA_F32 || t.d.ndim != 2 || t.producer < 0) return false;
+    if (t.d.dims[0] != like.d.dims[0] || t.d.dims[1] != like.d.dims[1] || (t.numel % 4)) return false;
+    const int opc = P.ops[t.producer].opcode;
+    return is_ew(opc) || opc == YOTA_OP_MATMUL;  // written whole by its own kernel (not a view)
+  };
+  // 0: a new container can be made, 1: a view of an existing one, -1: neither
+  auto contain_kind = [&](const std::vector<int>& ms) {
+    int in = 0;
+    for (int m : ms) in += where.count(m) ? 1 : 0;
+    if (in == 0) {
+      std::vector<int> sorted = ms;
+      std::sort(sorted.begin(), sorted.end());
+      if (std::adjacent_find(sorted.begin(), sorted.end()) != sorted.end()) return -1;
+      for (int m : ms)
+        if (!placeable(m, P.T[ms[0]])) return -1;
+      return 0;
+    }
+    if (in != (int)ms.size()) return -1;
+    const auto w0 = where[ms[0]];
+    for (size_t k = 0; k < ms.size(); k++)
+      if (where[ms[k]] != std::make_pair(w0.first, w0.second + (int)k)) return -1;
+    return 1;
+  };
+  // tensor holding [ms...] side by side; new ops go before op `at` (views) / after the last producer (containers)
+  auto container_of = [&](const std::vector<int>& ms, int at) {
+    const TInfo& m0 = P.T[ms[0]];
+    const long long M = m0.d.dims[0], B = m0.d.dims[1], n = (long long)ms.size();
+    if (contain_kind(ms) == 0) {
+      const int ct = add_tensor(P, {M, B * n});
+      P.catv[ct] = ms;
+      int last = 0;
+      for (size_t k = 0; k < ms.size(); k++) {
+        where[ms[k]] = {(int)conts.size(), (int)k};
+        last = std::max(last, P.T[ms[k]].producer);
+      }
+      conts.push_back({ct, ms});
+      ins_after[last].push_back(mk_op(OP_CATV, {}, ct));
+      return ct;
+    }
+    const auto w0 = where[ms[0]];
+    const Cont& c = conts[w0.first];
+    if (w0.second == 0 && ms.size() == c.members.size()) return c.tensor;
+    // a column range of the container: usable as soon as ITS members exist (the chain that sums
+    // dz_2 .. dz_T closes before dz_1 -- and with it the whole container -- has been produced)
+    (void)at;
+    const int v = add_tensor(P, {M, B * n});
+    P.catv[v] = ms;
+    P.catv_view[v] = {c.tensor, (long long)w0.second * M * B};
+    int last = 0;
+    for (int m : ms) last = std::max(last, P.T[m].producer);
+    ins_after[last].push_back(mk_op(OP_CATV, {}, v));
+    return v;
+  };
+  for (int round = 0; round < 2; round++)
+    for (Chain& ch : chains) {
+      if (ch.leaves.size() < 3 || ch.tail < 0) continue;
+      std::vector<Leaf> lf(ch.leaves.size());
+      bool ok = true;
+      for (size_t k = 0; k < ch.leaves.size() && ok; k++) ok = classify(ch.leaves[k], &lf[k]) && lf[k].kind == lf[0].kind;
+      if (!ok) continue;
+      const int kind = lf[0].kind, at = ch.adds.back();
+      if ((round == 0) != (kind == NT_SLICE || kind == UNGET_TN)) continue;
+      for (auto& l : lf)
+        ok = ok && (kind == NT_PLAIN || l.other == lf[0].other) && P.T[l.dz].d.ndim == 2 && same_shape(P.T[l.dz], P.T[lf[0].dz]);
+      if (!ok) continue;
+      std::vector<int> dzs;
+      yota_op_desc rep;
+      if (kind == NT_SLICE || kind == UNGET_TN) {
+        std::sort(lf.begin(), lf.end(), [](const Leaf& a, const Leaf& b) { return a.t < b.t; });
+        for (size_t k = 0; k < lf.size(); k++) ok = ok && lf[k].t == lf[0].t + (long long)k;
+        for (auto& l : lf) dzs.push_back(l.dz);
+        if (!ok || contain_kind(dzs) < 0) continue;
+        if (kind == NT_SLICE) {
+          const TInfo& X = P.T[lf[0].other];
+          const long long D = X.d.dims[0], B = X.d.dims[1], T = X.d.dims[2], n = (long long)lf.size();
+          if (P.T[dzs[0]].d.dims[1] != B) continue;
+          const int dZ = container_of(dzs, at);
+          int X2;
+          if (x2_of.count(lf[0].other) && X.d.kind == YOTA_T_INPUT)
+            X2 = x2_of[lf[0].other];
+          else {
+            X2 = add_tensor(P, {D, B * T});
+            ins_before[at].push_back(mk_op(YOTA_OP_RESHAPE, {lf[0].other}, X2));
+          }
+          int Bop = X2;
+          if (n != T) {
+            Bop = add_tensor(P, {D, B * n});
+            yota_op_desc g = mk_op(YOTA_OP_GETINDEX, {X2}, Bop);
+            g.iattr[0] = 2;
+            g.iattr[1] = YOTA_IDX_COLON;
+            g.iattr[4] = YOTA_IDX_RANGE;
+            g.iattr[5] = (lf[0].t - 1) * B + 1;
+            g.iattr[6] = (lf[0].t - 1 + n) * B;
+            ins_before[at].push_back(g);
+          }
+          rep = mk_op(YOTA_OP_MATMUL, {dZ, Bop}, ch.tail);
+          rep.iattr[1] = 1;
+        } else {
+          const TInfo& out = P.T[ch.tail];
+          const long long T = out.d.ndim == 3 ? out.d.dims[2] : 0;
+          if ((long long)lf.size() != T || lf[0].t != 1 || P.T[dzs[0]].d.dims[1] != out.d.dims[1]) continue;
+          const int dZ = container_of(dzs, at);
+          const int mm = add_tensor(P, {out.d.dims[0], out.d.dims[1] * T});
+          yota_op_desc g = mk_op(YOTA_OP_MATMUL, {lf[0].other, dZ}, mm);
+          g.iattr[0] = 1;
+          ins_before[at].push_back(g);
+          rep = mk_op(YOTA_OP_RESHAPE, {mm}, ch.tail);
+        }
+      } else {
+        // the members must already sit side by side in a container (made by a chain that knows t)
+        for (auto& l : lf) ok = ok && where.count(l.dz);
+        if (!ok) continue;
+        std::sort(lf.begin(), lf.end(), [&](const Leaf& a, const Leaf& b) { return where[a.dz] < where[b.dz]; });
+        for (auto& l : lf) dzs.push_back(l.dz);
+        if (contain_kind(dzs) != 1) continue;
+        if (kind == NT_PLAIN) {
+          std::vector<int> hs;
+          for (auto& l : lf) hs.push_back(l.other);
+          ok = true;  // every leaf has its own h: same shapes, one column block per dz
+          for (int h : hs) ok = ok && P.T[h].d.ndim == 2 && same_shape(P.T[h], P.T[hs[0]]) && P.T[h].d.dims[1] == P.T[dzs[0]].d.dims[1];
+          if (!ok || contain_kind(hs) < 0) continue;
+          const int dZ = container_of(dzs, at), H = container_of(hs, at);
+          rep = mk_op(YOTA_OP_MATMUL, {dZ, H}, ch.tail);
+          rep.iattr[1] = 1;
+        } else {
+          const int dZ = container_of(dzs, at);
+          rep = mk_op(YOTA_OP_SUM, {dZ}, ch.tail);
+          rep.iattr[0] = 2;
+          rep.fattr[0] = 1.0;
+        }
+      }
+      replace[at] = rep;
+      ch.tail = -1;  // done
+      n_batched++;
+    }
+  if (!n_batched) return;
+  std::vector<yota_op_desc> ops;
+  for (int i = 0; i < n_ops; i++) {
+    for (auto& o : ins_before[i]) ops.push_back(o);
+    ops.push_back(replace.count(i) ? replace[i] : P.ops[i]);
+    for (auto& o : ins_after[i]) ops.push_back(o);
+  }
+  P.ops.swap(ops);
+  P.n_batched = n_batched;
+  link_ops(P);
 }
 
 // Peephole on the op list (before dead-code elimination): the scatter-add pullback of
@@ -1504,6 +1912,21 @@ extern "C" int yota_program_build(yota_ctx* ctx, const yota_op_desc* ops, int64_
   }
   int st = validate(P);
   if (st) return fail(st);
+  {  // batching of unrolled loops; an op list the pass got wrong (it is re-validated) is discarded
+    const std::vector<yota_op_desc> ops0 = P.ops;
+    const size_t nt0 = P.T.size();
+    rewrite_unrolled_loops(P);
+    if (getenv("YOTA_DEBUG_REWRITE")) fprintf(stderr, "rewrite_unrolled_loops: %d batched, %zu ops\n", P.n_batched, P.ops.size());
+    if (P.n_batched && validate(P) != YOTA_OK) {
+      if (getenv("YOTA_DEBUG_REWRITE")) fprintf(stderr, "  rewritten program rejected: %s\n", yota_last_error());
+      P.ops = ops0;
+      P.T.resize(nt0);
+      P.catv.clear();
+      P.catv_view.clear();
+      P.n_batched = 0;
+      link_ops(P);
+    }
+  }
   rewrite_scaled_scatter(P);
   // dead-code elimination
   P.op_needed.assign(P.ops.size(), 0);
@@ -1542,10 +1965,49 @@ extern "C" int64_t yota_program_describe(yota_program* p, char* buf, int64_t cap
   snprintf(line, sizeof(line), "program: %zu ops, %zu steps, %zu regions (%d static), arena %zu bytes\n", p->ops.size(),
            p->steps.size(), p->regions.size(), p->n_static, p->arena_bytes);
   s += line;
+  if (p->n_batched) {
+    snprintf(line, sizeof(line), "  unrolled loops: %d slice families / accumulation chains batched into single contractions\n", p->n_batched);
+    s += line;
+  }
   for (size_t i = 0; i < p->steps.size(); i++) {
     snprintf(line, sizeof(line), "  step %zu: %s\n", i, p->steps[i].label.c_str());
     s += line;
     if (p->steps[i].kind == STEP_REGION) s += "    sig " + p->regions[p->steps[i].region].sig + "\n";
+  }
+  if (buf && cap > 0) {
+    const size_t n = std::min((size_t)cap - 1, s.size());
+    memcpy(buf, s.data(), n);
+    buf[n] = 0;
+  }
+  return (int64_t)s.size();
+}
+
+// The op list the planner actually works on (after the rewrite passes), as text:
+//   T id dtype ndim d0 d1 d2 d3 kind slot cval
+//   O opcode out n_in in... | iattr[16] | fattr[2] | members of a concatenation...
+// Lets the CPU-side tests run the REWRITTEN program through their NumPy interpreter.
+extern "C" int64_t yota_program_dump_ops(yota_program* p, char* buf, int64_t cap) {
+  if (!p) return 0;
+  std::string s;
+  char line[1024];
+  for (size_t t = 0; t < p->T.size(); t++) {
+    const yota_tensor_desc& d = p->T[t].d;
+    snprintf(line, sizeof(line), "T %zu %d %d %lld %lld %lld %lld %d %d %.17g\n", t, d.dtype, d.ndim, (long long)d.dims[0],
+             (long long)d.dims[1], (long long)d.dims[2], (long long)d.dims[3], d.kind, d.slot, d.cval);
+    s += line;
+  }
+  for (size_t i = 0; i < p->ops.size(); i++) {
+    const yota_op_desc& o = p->ops[i];
+    std::string l = "O " + std::to_string(o.opcode) + " " + std::to_string(o.out) + " " + std::to_string(o.n_in);
+    for (int j = 0; j < o.n_in; j++) l += " " + std::to_string(o.in[j]);
+    l += " |";
+    for (int j = 0; j < YOTA_N_IATTR; j++) l += " " + std::to_string((long long)o.iattr[j]);
+    snprintf(line, sizeof(line), " | %.17g %.17g |", o.fattr[0], o.fattr[1]);
+    l += line;
+    auto it = p->catv.find(o.out);
+    if (o.opcode == 200 && it != p->catv.end())
+      for (int m : it->second) l += " " + std::to_string(m);
+    s += l + "\n";
   }
   if (buf && cap > 0) {
     const size_t n = std::min((size_t)cap - 1, s.size());

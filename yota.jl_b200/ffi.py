@@ -54,6 +54,7 @@ SYMBOLS = {
     "yota_program_run": (_i, [_vp, _pp, _i64, _pp, _i64, _f]),
     "yota_program_destroy": (_i, [_vp]),
     "yota_program_describe": (_i64, [_vp, C.c_char_p, _i64]),
+    "yota_program_dump_ops": (_i64, [_vp, C.c_char_p, _i64]),
     "yota_program_stats": (_i, [_vp] + [C.POINTER(_i64)] * 5),
     "yota_event_create": (_i, [_vp, _pp]),
     "yota_event_record": (_i, [_vp, _vp]),
