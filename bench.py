@@ -301,6 +301,15 @@ def cublas_peaks():
                 e1.synchronize()
                 best = min(best, e0.elapsed_time(e1))
             out[name] = 2 * n ** 3 / (best * 1e-3) / 1e12
+            if name == "tf32":  # ... and back to back for ~2 s: what the same library holds under the power cap
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                reps = max(20, int(2000 / best))
+                e0.record()
+                for _ in range(reps):
+                    torch.matmul(a, b)
+                e1.record()
+                e1.synchronize()
+                out["tf32_sustained"] = 2 * n ** 3 * reps / (e0.elapsed_time(e1) * 1e-3) / 1e12
             del a, b
         torch.backends.cuda.matmul.allow_tf32 = False
         torch.cuda.empty_cache()
@@ -488,6 +497,7 @@ def main():
                 "frac": ach / peak, "traffic": tr["bytes"] if tr else None, "traffic_source": tr["source"] if tr else None,
                 "algorithmic_flops_per_launch": wl["gemm_flops"] / n_g,
                 "frac_of_bf16_burst_derived": ach / derived_burst, "frac_of_bf16_sustained_derived": ach / derived_sust,
+                "frac_of_cublas_tf32_sustained_in_run": (ach / cub["tf32_sustained"]) if tf32_like and cub.get("tf32_sustained") else None,
                 "avg_launch_ms": avg_ms, "avg_launch_ms_isolated": groups[dom][0] / n_g, "launches_per_step": n_g,
                 "share_of_step": share,
                 "peak_source": (f"cuBLAS {'TF32' if tf32_like else 'BF16'} 8192^3 best of 10, measured in this run" if own else

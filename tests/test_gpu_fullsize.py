@@ -68,12 +68,35 @@ def test_c5_full_size_bit_exact():
     assert abs(float(val) - ref_val) <= 1e-5 * abs(ref_val) + 0.5  # 2^30 products of magnitude <= 0.25
 
 
-def test_c4_full_size_vs_oracle():
-    """Unrolled Elman RNN, H = 1024, T = 128, B = 128 (strict-FP32 contractions): 127-fold
-    gradient accumulation of Wx, Wh, b and the slice-wise dx against the oracle."""
+@pytest.fixture(scope="module")
+def c4_oracle():
     args = cases.c4_args(1024, 128, 128)
     f = cases.make_c4(128)
-    U.check_parity(f, list(args), flags=0, o64=O.grad(f, *U.to_f64(list(args)), dtype=np.float64))
+    return args, f, O.grad(f, *args, dtype=np.float32), O.grad(f, *U.to_f64(list(args)), dtype=np.float64)
+
+
+@pytest.mark.parametrize("mode", ["fp32_batched", "fp32_unrolled", "tf32_batched"])
+def test_c4_full_size_vs_oracle(mode, c4_oracle, monkeypatch):
+    """Unrolled Elman RNN, H = 1024, T = 128, B = 128: the 127-fold accumulation of Wx, Wh, b and
+    the slice-wise dx against the oracle -- with the loop batched by the planner (one K = T*B
+    contraction per weight gradient, the default), left unrolled (in-place accumulation in tape
+    order), and batched with TF32 contractions (stated tolerance 2e-2 of max|g|: 128 recurrent steps
+    compound the 2^-11 operand rounding)."""
+    args, f, o32, o64 = c4_oracle
+    if mode == "fp32_unrolled":
+        monkeypatch.setenv("YOTA_NO_LOOP_BATCHING", "1")
+    Y.reset()
+    if mode.startswith("fp32"):
+        U.check_parity(f, list(args), flags=0, o32=o32, o64=o64)
+    else:
+        val, g = Y.grad(f, *[Y.cu(a) for a in args], flags=ffi.FLAG_GEMM_TF32)
+        assert abs(val - float(o64[0])) <= 2e-2 * abs(float(o64[0]))
+        worst = 0.0
+        for a, b in zip(g[1:], o64[1][1:]):
+            worst = max(worst, float(np.abs(a.to_host() - b).max() / np.abs(b).max()))
+        print(f"C4 full size, tf32 batched: worst err / max|g| = {worst:.3e}")
+        assert worst <= 2e-2, worst
+    Y.reset()
 
 
 @pytest.fixture(scope="module")

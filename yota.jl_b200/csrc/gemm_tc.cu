@@ -620,6 +620,39 @@ __device__ __forceinline__ void umma_2sm(uint32_t d_tmem, uint64_t a_desc, uint6
 // row m, walking the tile's columns) is the region kernel's mapping, so ROWVEC operands (bias)
 // are loaded once per tile and row sums (db) accumulate per thread in column order and leave
 // as partial[tile_n][m] for the same fixed-order finisher.
+// Out of line on purpose: the epilogue's hot loop keeps its register allocation (inlined, this tail
+// pushed the tanh'/db epilogue kernel from 208 registers to 255 with spills and from 360 to 427 us).
+// threadFenceReduction: publish this CTA's partials, count the arrival; the last of the num_n CTAs
+// covering these 128 rows sums all partials in rowsum_finish_kernel's fixed order.
+__device__ __noinline__ void finish_rowsum(const float* part, long long m, long long R, int num_n, float* out, float scale,
+                                           unsigned* cnt, unsigned* flag) {
+  __threadfence();
+  asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
+  const int et = (threadIdx.x - EPI_WARP0 * 32);
+  if (et == 0) *flag = atomicAdd(cnt + (m >> 7), 1u) == (unsigned)(num_n - 1) ? 1u : 0u;
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  if (*flag) {
+    __threadfence();
+    float sj[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      float acc = 0.f;
+      for (int q = j; q < num_n; q += 8) acc = __fadd_rn(acc, __ldcg(part + (long long)q * R + m));
+      sj[j] = acc;
+    }
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; j++) t = __fadd_rn(t, sj[j]);
+    out[m] = scale == 1.f ? t : __fmul_rn(t, scale);
+    if (et == 0) cnt[m >> 7] = 0u;  // ready for the next run
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");  // the flag word is reused by the next tile
+}
+__device__ __noinline__ void prefetch_tile_l2(const float* line0, long long R, int lane) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) asm volatile("prefetch.global.L2 [%0];" ::"l"(line0 + (long long)(lane + 32 * i) * R));
+}
+
 #define YCE(field, i) (ChainOf<ID>::value.field[decltype(i)::value])
 template <int ID, int Z_IN>
 struct Epilogue {
@@ -634,18 +667,17 @@ struct Epilogue {
   static constexpr int RS_OUT = first_rowsum();  // the sink whose partials the kernel finishes itself
 
   __device__ __forceinline__ static void begin_tile(const RegionParams& rp, long long m, long long n0, long long R,
-                                                    float (&base)[NS], float (&accs)[NO]) {
-    // the tile's other FULL operands (h of the tanh' epilogue) are pulled into L2 while the
-    // mainloop runs: with one tile per CTA (small batches per GPU) nothing else hides the latency
-    // of the epilogue's operand loads, and beside an all-reduce that latency triples
+                                                    float (&base)[NS], float (&accs)[NO], bool prefetch) {
+    // With ONE tile per CTA (small batches per GPU) nothing hides the latency of the epilogue's
+    // operand loads -- beside an all-reduce that latency triples -- so the tile's other FULL
+    // operands (h of the tanh' epilogue) are pulled into L2 while the mainloop runs.  With several
+    // tiles per CTA the next mainloop hides the epilogue and a prefetch would only be evicted by
+    // the operand stream before it is used (measured: +180 MB of DRAM reads, 360 -> 426 us).
     static_for<N_IN>([&](auto k) {
       constexpr int K = decltype(k)::value, cls = YCE(in_cls, k);
-      if constexpr (cls == CLS_FULL && K != Z_IN) {
+      if constexpr (cls == CLS_FULL && K != Z_IN) if (prefetch) {
         const int lane = threadIdx.x & 31;
-        const float* line0 = rp.in[K].ptr + n0 * R + (m - lane);
-#pragma unroll
-        for (int i = 0; i < TN2 / 32; i++)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(line0 + (long long)(lane + 32 * i) * R));
+        prefetch_tile_l2(rp.in[K].ptr + n0 * R + (m - lane), R, lane);
       }
     });
     static_for<NS>([&](auto s) { base[decltype(s)::value] = 0.f; });
@@ -735,32 +767,7 @@ struct Epilogue {
     });
     constexpr int RS = RS_OUT;
     if constexpr (RS >= 0) {
-      if (p.rs_cnt) {
-        // threadFenceReduction: publish this CTA's partials, count the arrival; the last of the
-        // num_n CTAs covering these 128 rows sums all partials in the finisher's fixed order
-        __threadfence();
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
-        const int et = (threadIdx.x - EPI_WARP0 * 32);
-        if (et == 0) *flag = atomicAdd(p.rs_cnt + (m >> 7), 1u) == (unsigned)(p.num_n - 1) ? 1u : 0u;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (*flag) {
-          __threadfence();
-          const float* part = rp.out[RS].ptr;
-          float sj[8];
-#pragma unroll
-          for (int j = 0; j < 8; j++) {
-            float acc = 0.f;
-            for (int q = j; q < p.num_n; q += 8) acc = __fadd_rn(acc, __ldcg(part + (long long)q * R + m));
-            sj[j] = acc;
-          }
-          float t = 0.f;
-#pragma unroll
-          for (int j = 0; j < 8; j++) t = __fadd_rn(t, sj[j]);
-          p.rs_out[m] = p.rs_scale == 1.f ? t : __fmul_rn(t, p.rs_scale);
-          if (et == 0) p.rs_cnt[m >> 7] = 0u;  // ready for the next run
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // the flag word is reused by the next tile
-      }
+      if (p.rs_cnt) finish_rowsum(rp.out[RS].ptr, m, R, p.num_n, p.rs_out, p.rs_scale, p.rs_cnt, flag);
     }
   }
 
@@ -967,7 +974,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       float* crow = p.C + m + n0 * p.ldc;
       using EP = Epilogue<(EPI >= 0 ? EPI : 0), ZIN>;
       float ebase[EP::NS], eaccs[EP::NO];
-      if constexpr (EPI >= 0) EP::begin_tile(rp, m, n0, p.M, ebase, eaccs);
+      if constexpr (EPI >= 0) EP::begin_tile(rp, m, n0, p.M, ebase, eaccs, num_tiles <= num_pairs);
      for (int ch = 0; ch < (X3 ? (nkb + kc - 1) / kc : 1); ch++) {
       const int kb0 = X3 ? ch * kc : 0;
       // X3: the tile arrives in chunks of k-blocks; every chunk but the first is added to the
