@@ -1,21 +1,9 @@
 #!/bin/bash
-cat > /tmp/prof.py <<'PY'
-import sys, os
-sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
-import cases, yota_b200 as Y
-from yota_b200 import ffi
-args = cases.c3_args(8, 4096, 8192)
-d = [Y.cu(a) for a in args]
-gf = Y.CompiledGrad(Y.gradtape(cases.make_c3(8, 8192), *d), flags=ffi.FLAG_GEMM_TF32)
-outs = [Y.B200Array(gf._out_dims[s], "f32") for s in range(gf.n_out)]
-for _ in range(4): prof = gf.profile(d, out=outs)
-g = {}
-for l, t in prof:
-    k = l.split(" ->")[0][:60]
-    a = g.setdefault(k, [0, 0.0]); a[0] += 1; a[1] += t
-print(os.environ.get("TAG"), " ".join(f"{a[0]}x{1e3*a[1]/a[0]:.0f}" for k, a in sorted(g.items(), key=lambda kv: -kv[1][1])[:4]))
-PY
-for i in 1 2; do
-TAG=mc_on python /tmp/prof.py
-TAG=mc_off YOTA_GEMM_NO_MULTICAST=1 python /tmp/prof.py
-done
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_gemm_tc.py -m gpu -x -q --timeout 120 > gpurun_out/pytest_j.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/pytest_j.log
+for i in 1 2; do for v in preferred strict4 nomc; do
+  case $v in preferred) E=X=1;; strict4) E=YOTA_GEMM_STRICT_CLUSTER4=1;; nomc) E=YOTA_GEMM_NO_MULTICAST=1;; esac
+  for m in tf32 bf16; do
+  env $E timeout 300 python bench.py --gemm $m --quick --steps 30 | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$v $m', round(d['value'],2), 'evals/s', round(d['ms_per_step'],3),'ms')"
+  done
+done; done

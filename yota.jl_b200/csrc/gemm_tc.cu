@@ -803,19 +803,28 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();
   const uint32_t rank = crank & 1u;               // position inside the CTA pair
-  const uint32_t pp = MC > 1 ? crank >> 1 : 0u;   // which pair of the cluster
+  // MC = 2 launches ask for clusters of 4 as the PREFERRED size over regular clusters of 2
+  // (cudaLaunchAttributePreferredClusterDimension): the GPCs of a B200 hold an odd number of TPCs,
+  // so only 33 four-SM clusters fit on the 148 SMs -- the 8 TPCs left over run as regular pairs,
+  // which fetch all of their A rows themselves.  A group of 4 consecutive CTAs is either one
+  // preferred cluster or two regular ones and does the same work either way (static schedule).
+  uint32_t csize;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(csize));
+  const int mc = MC > 1 ? (int)(csize >> 1) : 1;            // pairs in THIS cluster
+  const uint32_t pp = MC > 1 ? (blockIdx.x & 3u) >> 1 : 0u;  // pair index inside the group: which of the MC tiles
+  const uint32_t cpp = crank >> 1;                          // pair index inside the cluster
   const uint32_t lead = crank & ~1u;              // cluster rank of this pair's leader
   const bool leader = rank == 0;
   const int pair = blockIdx.x / (2 * MC), num_pairs = gridDim.x / (2 * MC);  // work units: MC tiles adjacent along N
   const int num_tiles = p.num_m * (p.num_n / MC);
   const int nkb = (int)(p.K / TK);
-  const uint16_t mask_pair = (uint16_t)(3u << (2 * pp)), mask_all = (uint16_t)((1u << (2 * MC)) - 1u);
+  const uint16_t mask_pair = (uint16_t)(3u << (2 * cpp)), mask_all = (uint16_t)((1u << (2 * mc)) - 1u);
   const uint16_t mask_same_rows = (uint16_t)((1u << rank) | (1u << (2 + rank)));  // MC = 2: this CTA and its twin
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES2; s++) {
       mbar_init(&full[s], 2);
-      mbar_init(&empty[s], MC);
+      mbar_init(&empty[s], mc);
     }
     for (int a = 0; a < 2; a++) {
       mbar_init(&tfull[a], 1);
@@ -874,13 +883,22 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 tma_load_2d_2sm(sa + i * E::CHUNK_BYTES, ma, &full[stage], m0 + E::CHUNK * i, k0);
               else
                 tma_load_2d_2sm(sa, ma, &full[stage], k0, m0);
-            } else {
+            } else if (mc == 2) {  // preferred cluster: half of the boxes, multicast to the twin CTA
               if (A_MN) {
                 const int c = (int)pp * NAI + i;
                 tma_load_2d_2sm_mc(sa + c * E::CHUNK_BYTES, ma, &full[stage], m0 + E::CHUNK * c, k0, mask_same_rows);
               } else
                 tma_load_2d_2sm_mc(sa + pp * (S::A_BYTES / MC), ma, &full[stage], k0, m0 + (int)pp * (TM / MC),
                                    mask_same_rows);
+            } else {  // regular pair of a multicast-capable launch: both halves, no multicast
+#pragma unroll
+              for (int h = 0; h < MC; h++) {
+                if (A_MN) {
+                  const int c = h * NAI + i;
+                  tma_load_2d_2sm(sa + c * E::CHUNK_BYTES, ma, &full[stage], m0 + E::CHUNK * c, k0);
+                } else
+                  tma_load_2d_2sm(sa + h * (S::A_BYTES / MC), ma, &full[stage], k0, m0 + h * (TM / MC));
+              }
             }
           };
           auto load_b = [&](int c) {
@@ -1065,18 +1083,29 @@ static int launch2_mc(const GemmArgs& g, const Maps& mp, int sm_count, cudaStrea
   cfg.blockDim = dim3(THREADS);
   cfg.dynamicSmemBytes = Smem2T<X3>::TOTAL;
   cfg.stream = s;
-  cudaLaunchAttribute at[1];
+  // regular clusters are CTA pairs; MC = 2 prefers clusters of four (two pairs sharing A by
+  // multicast) wherever the GPC has room for them
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = 2 * MC;
+  at[0].val.clusterDim.x = 2;
   at[0].val.clusterDim.y = 1;
   at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributePreferredClusterDimension;
+  at[1].val.preferredClusterDim.x = 2 * MC;
+  at[1].val.preferredClusterDim.y = 1;
+  at[1].val.preferredClusterDim.z = 1;
   cfg.attrs = at;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = MC > 1 && !getenv("YOTA_GEMM_STRICT_CLUSTER4") ? 2 : 1;
+  if (cfg.numAttrs == 1) at[0].val.clusterDim.x = 2 * MC;
   if (!attr) {
     YOTA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem2T<X3>::TOTAL));
     cfg.gridDim = dim3(2 * MC);
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n > 0) max_clusters = n;
+    const int numAttrs = cfg.numAttrs;
+    cfg.numAttrs = 1;  // co-resident REGULAR clusters (pairs, or fours with YOTA_GEMM_STRICT_CLUSTER4)
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n > 0)
+      max_clusters = numAttrs == 2 ? n / MC : n;  // groups of MC pairs
+    cfg.numAttrs = numAttrs;
     (void)cudaGetLastError();
     attr = true;
   }
