@@ -412,3 +412,28 @@ def test_loop_batching_leaves_other_programs_alone(built):
 
 
 colon_ = jl.colon
+
+
+def test_allreduce_marks_are_validated_and_destination_shards_cover_the_table(built):
+    """Host logic of the multi-GPU paths that needs no device: a marked slot must be written by
+    some step; dest_shard partitions 0..n exactly (ragged tails to the first ranks)."""
+    from yota_b200 import dp
+
+    lib = ffi.lib()
+    ctx = C.c_void_p()
+    ffi.check(lib.yota_init(0, C.byref(ctx)))
+    L = lower(Y.gradtape(cases.loss_tanh, A((4, 3)), A((4,)), A((3,))))
+    ops, tens = ffi.pack_program(L.prog)
+    h = C.c_void_p()
+    ffi.check(lib.yota_program_build(ctx, ops, len(L.prog.ops), tens, len(L.prog.tensors), 0, C.byref(h)))
+    good = (C.c_int32 * 2)(L.grads[0][1], L.grads[1][1])
+    assert lib.yota_program_set_allreduce(h, good, 2) == 0
+    bad = (C.c_int32 * 1)(99)
+    assert lib.yota_program_set_allreduce(h, bad, 1) == -6 and b"bad out slot" in lib.yota_last_error()
+    lib.yota_program_destroy(h)
+    lib.yota_shutdown(ctx)
+    for n_dst, G in ((10, 3), (1 << 20, 8), (7, 8)):
+        edges = [dp.dest_shard(n_dst, r, G) for r in range(G)]
+        assert edges[0][0] == 0 and edges[-1][1] == n_dst
+        assert all(a[1] == b[0] for a, b in zip(edges, edges[1:]))
+        assert max(hi - lo for lo, hi in edges) - min(hi - lo for lo, hi in edges) <= 1
