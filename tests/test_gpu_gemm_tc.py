@@ -200,3 +200,30 @@ def test_mlp_gradients_in_tf32x3_mode(force_2cta):
     gf = Y.CompiledGrad(Y.gradtape(f, *[Y.cu(a) for a in args]), flags=ffi.FLAG_GEMM_TF32X3)
     assert "epilogue{region[add,tanh]}" in gf.describe()
     U.check_parity(f, list(args), flags=ffi.FLAG_GEMM_TF32X3)
+
+
+def test_recurrence_epilogues_of_the_1cta_kernel(monkeypatch):
+    """C4 at a tile-aligned mid size (H = 256, B = 128, T = 6), TF32: the per-step regions
+    h = tanh.(zx .+ Wh*h .+ b) and dz = (Wh'*dz) .* (1 .- h.^2) run as epilogues of the skinny
+    128 x 32-tile GEMMs, reading / writing the views of the batched containers.  Same numbers as
+    with the regions as separate passes (identical arithmetic on identical accumulators), and
+    within the TF32 tolerance of the Float64 oracle."""
+    T, H, B = 6, 256, 128
+    f, args = cases.make_c4(T), cases.c4_args(H, B, T)
+    d = [Y.cu(a) for a in args]
+    gf = Y.CompiledGrad(Y.gradtape(f, *d), flags=ffi.FLAG_GEMM_TF32)
+    desc = gf.describe()
+    assert desc.count("epilogue{region[add,add,tanh]}") == T - 1 and desc.count("epilogue{region[square,rsubc,mul]}") >= T - 2, desc
+    v1, g1 = gf.run(d)
+    g1 = [x.to_host() for x in g1]
+    monkeypatch.setenv("YOTA_NO_EPILOGUE1", "1")
+    gu = Y.CompiledGrad(Y.gradtape(f, *d), flags=ffi.FLAG_GEMM_TF32)
+    assert "epilogue" not in gu.describe()
+    v2, g2 = gu.run(d)
+    assert abs(float(v1.to_host()) - float(v2.to_host())) <= 1e-6 * abs(float(v2.to_host()))
+    for a, b in zip(g1, g2):
+        b = b.to_host()
+        assert np.max(np.abs(a - b)) <= 1e-6 * np.max(np.abs(b)), np.max(np.abs(a - b)) / np.max(np.abs(b))
+    v64, g64 = O.grad(f, *U.to_f64(list(args)), dtype=np.float64)
+    for a, b in zip(g1, g64[1:]):
+        assert np.max(np.abs(a - b)) <= 5e-3 * np.max(np.abs(b))

@@ -230,6 +230,8 @@ int launch_gemm_tc(yota_ctx* ctx, const GemmArgs& g, cudaStream_t s);  // return
 bool gemm_tc_eligible(const GemmArgs& g);
 bool gemm_tc2_eligible(const GemmArgs& g, int sm_count);
 bool gemm_epilogue_chain_ok(int static_id, int transA, int transB, int z_in);
+// ... as an epilogue of the 1-CTA kernel (skinny outputs: TF32, 128 x 32 tiles, store-only chains)
+bool gemm_epilogue1_chain_ok(const GemmArgs& g, int sm_count, int static_id, int z_in);
 int launch_gemm_tc_epilogue(yota_ctx* ctx, const GemmArgs& g, int static_id, const RegionParams& rp, int z_in,
                             cudaStream_t s);
 int launch_cast_bf16(void* dst, const float* src, long long n, cudaStream_t s);

@@ -164,6 +164,168 @@ struct Params {
   int bsh_out;
 };
 
+// ---- fused epilogues -------------------------------------------------------------------------
+// The consumer region of a GEMM output (bias [+ tanh] after W*h; tanh'(h) * delta + db after
+// W'*dz) runs on the accumulator tile instead of as a separate pass: the SAME ahead-of-time
+// micro-program (ChainOf<ID>) the region kernel would execute, with the accumulator element
+// standing in for the region's FULL operand `z_in`.  The epilogue's thread mapping (thread =
+// row m, walking the tile's columns) is the region kernel's mapping, so ROWVEC operands (bias)
+// are loaded once per tile and row sums (db) accumulate per thread in column order and leave
+// as partial[tile_n][m] for the same fixed-order finisher.
+// Out of line on purpose: the epilogue's hot loop keeps its register allocation (inlined, this tail
+// pushed the tanh'/db epilogue kernel from 208 registers to 255 with spills and from 360 to 427 us).
+// threadFenceReduction: publish this CTA's partials, count the arrival; the last of the num_n CTAs
+// covering these 128 rows sums all partials in rowsum_finish_kernel's fixed order.
+__device__ __noinline__ void finish_rowsum(const float* part, long long m, long long R, int num_n, float* out, float scale,
+                                           unsigned* cnt, unsigned* flag) {
+  __threadfence();
+  asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
+  const int et = (threadIdx.x - EPI_WARP0 * 32);
+  if (et == 0) *flag = atomicAdd(cnt + (m >> 7), 1u) == (unsigned)(num_n - 1) ? 1u : 0u;
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  if (*flag) {
+    __threadfence();
+    float sj[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      float acc = 0.f;
+      for (int q = j; q < num_n; q += 8) acc = __fadd_rn(acc, __ldcg(part + (long long)q * R + m));
+      sj[j] = acc;
+    }
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; j++) t = __fadd_rn(t, sj[j]);
+    out[m] = scale == 1.f ? t : __fmul_rn(t, scale);
+    if (et == 0) cnt[m >> 7] = 0u;  // ready for the next run
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");  // the flag word is reused by the next tile
+}
+__device__ __noinline__ void prefetch_tile_l2(const float* line0, long long R, int lane) {
+#pragma unroll
+  for (int i = 0; i < 8; i++) asm volatile("prefetch.global.L2 [%0];" ::"l"(line0 + (long long)(lane + 32 * i) * R));
+}
+
+#define YCE(field, i) (ChainOf<ID>::value.field[decltype(i)::value])
+template <int ID, int Z_IN>
+struct Epilogue {
+  static constexpr int N_IN = ChainOf<ID>::value.n_in, N_OPS = ChainOf<ID>::value.n_ops, N_OUT = ChainOf<ID>::value.n_out;
+  static constexpr int NS = ChainOf<ID>::value.n_slots > 0 ? ChainOf<ID>::value.n_slots : 1;
+  static constexpr int NO = N_OUT > 0 ? N_OUT : 1;
+  static constexpr int first_rowsum() {
+    for (int k = 0; k < N_OUT; k++)
+      if (ChainOf<ID>::value.out_kind[k] == OUT_ROWSUM) return k;
+    return -1;
+  }
+  static constexpr int RS_OUT = first_rowsum();  // the sink whose partials the kernel finishes itself
+
+  __device__ __forceinline__ static void begin_tile(const RegionParams& rp, long long m, long long n0, long long R,
+                                                    float (&base)[NS], float (&accs)[NO], bool prefetch) {
+    // With ONE tile per CTA (small batches per GPU) nothing hides the latency of the epilogue's
+    // operand loads -- beside an all-reduce that latency triples -- so the tile's other FULL
+    // operands (h of the tanh' epilogue) are pulled into L2 while the mainloop runs.  With several
+    // tiles per CTA the next mainloop hides the epilogue and a prefetch would only be evicted by
+    // the operand stream before it is used (measured: +180 MB of DRAM reads, 360 -> 426 us).
+    static_for<N_IN>([&](auto k) {
+      constexpr int K = decltype(k)::value, cls = YCE(in_cls, k);
+      if constexpr (cls == CLS_FULL && K != Z_IN) if (prefetch) {
+        const int lane = threadIdx.x & 31;
+        prefetch_tile_l2(rp.in[K].ptr + n0 * R + (m - lane), R, lane);
+      }
+    });
+    static_for<NS>([&](auto s) { base[decltype(s)::value] = 0.f; });
+    static_for<NO>([&](auto k) { accs[decltype(k)::value] = 0.f; });
+    static_for<N_IN>([&](auto k) {
+      constexpr int cls = YCE(in_cls, k), slot = YCE(in_slot, k);
+      if constexpr (cls == CLS_ROWVEC) base[slot] = __ldg(rp.in[decltype(k)::value].ptr + m);
+      if constexpr (cls == CLS_SCALAR) base[slot] = __ldg(rp.in[decltype(k)::value].ptr);
+    });
+  }
+  // one chunk of 32 consecutive columns: accumulator values z[j] at (m, n0 + j).  The other FULL
+  // operands of the chunk are loaded up front (32 independent loads in flight per operand) --
+  // left per element, each load sits between the previous element's store and its own use and
+  // the epilogue runs at one DRAM latency per element.
+  __device__ __forceinline__ static void chunk32(const RegionParams& rp, const uint32_t (&z)[32], long long m,
+                                                 long long n0, long long R, const float (&base)[NS], float (&accs)[NO],
+                                                 float* tsh, long long tsh_ld, int tsh_out, float4* stage,
+                                                 __nv_bfloat16* bsh, int bsh_out) {
+    const int lane = threadIdx.x & 31;
+    float tv[4];
+    constexpr int NI = N_IN > 0 ? N_IN : 1;
+    float pre[NI][32];
+    static_for<N_IN>([&](auto k) {
+      constexpr int K = decltype(k)::value, cls = YCE(in_cls, k);
+      if constexpr (cls == CLS_FULL && K != Z_IN) {
+        const float* src = rp.in[K].ptr + n0 * R + m;
+#pragma unroll
+        for (int j = 0; j < 32; j++) pre[K][j] = __ldg(src + (long long)j * R);
+      }
+      if constexpr (cls == CLS_COLVEC) {
+        // lanes read consecutive entries once and broadcast them with shuffles
+        const float mine = __ldg(rp.in[K].ptr + n0 + (threadIdx.x & 31));
+#pragma unroll
+        for (int j = 0; j < 32; j++) pre[K][j] = __shfl_sync(0xffffffffu, mine, j);
+      }
+    });
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+      float v[NS];
+      static_for<NS>([&](auto s) { v[decltype(s)::value] = base[decltype(s)::value]; });
+      const long long off = (n0 + j) * R + m;
+      static_for<N_IN>([&](auto k) {
+        constexpr int K = decltype(k)::value, cls = YCE(in_cls, k), slot = YCE(in_slot, k);
+        if constexpr (cls == CLS_FULL) v[slot] = (K == Z_IN) ? __uint_as_float(z[j]) : pre[K][j];
+        if constexpr (cls == CLS_COLVEC) v[slot] = pre[K][j];
+      });
+      float acc = 0.f;
+      static_for<N_OPS>([&](auto i) {
+        constexpr int OP = YCE(op, i), D = YCE(dst, i), A = YCE(a, i), B = YCE(b, i);
+        float a, b;
+        if constexpr (A == RG_ACC) a = acc; else a = v[A];
+        if constexpr (B == RG_ACC) b = acc; else b = v[B];
+        acc = ew_v<OP>(a, b, rp.ops[decltype(i)::value].imm);
+        if constexpr (D != RG_NONE) v[D] = acc;
+      });
+      static_for<N_OUT>([&](auto k) {
+        constexpr int kind = YCE(out_kind, k), src = YCE(out_src, k);
+        if constexpr (kind == OUT_STORE) {
+          rp.out[decltype(k)::value].ptr[off] = v[src];
+          if (decltype(k)::value == tsh_out) tv[j & 3] = v[src];
+          if (bsh && decltype(k)::value == bsh_out) bsh[off] = __float2bfloat16_rn(v[src]);
+        } else
+          accs[decltype(k)::value] = __fadd_rn(accs[decltype(k)::value], v[src]);
+      });
+      // this thread's 32 columns of row m are one 128-byte line of the transposed copy: staged in
+      // shared memory (16-byte pieces XOR-swizzled by row: conflict-free both ways) ...
+      if ((j & 3) == 3 && tsh) stage[lane * 8 + ((j >> 2) ^ (lane & 7))] = make_float4(tv[0], tv[1], tv[2], tv[3]);
+    }
+    if (tsh) {
+      // ... and written out 4 whole lines per warp instruction (8 lanes x 16 bytes each) instead of
+      // 32 quarter-sector stores to 32 different lines
+      __syncwarp();
+      float* base_row = tsh + (m - lane) * tsh_ld + n0;
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int rr = 4 * i + (lane >> 3), piece = lane & 7;
+        reinterpret_cast<float4*>(base_row + (long long)rr * tsh_ld)[piece] = stage[rr * 8 + (piece ^ (rr & 7))];
+      }
+      __syncwarp();
+    }
+  }
+  __device__ __forceinline__ static void end_tile(const RegionParams& rp, long long m, long long tile_n, long long R,
+                                                  const float (&accs)[NO], const Params& p, unsigned* flag) {
+    static_for<N_OUT>([&](auto k) {
+      constexpr int kind = YCE(out_kind, k);
+      if constexpr (kind == OUT_ROWSUM) rp.out[decltype(k)::value].ptr[tile_n * R + m] = accs[decltype(k)::value];
+    });
+    constexpr int RS = RS_OUT;
+    if constexpr (RS >= 0) {
+      if (p.rs_cnt) finish_rowsum(rp.out[RS].ptr, m, R, p.num_n, p.rs_out, p.rs_scale, p.rs_cnt, flag);
+    }
+  }
+
+};
+#undef YCE
+
 // X3 (3xTF32, the compensated mode): a stage also holds the LOW parts of both tiles,
 // lo = x - tf32(x) (planner-made Float32 shadows, see launch_split_tf32), and every k-step
 // issues three MMAs into the same TMEM accumulator: hi*hi + hi*lo + lo*hi.  What is dropped is
@@ -183,10 +345,14 @@ struct Smem {
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;  // + barriers + slack for 1 KiB alignment
 };
 
-template <int TN, bool A_MN, bool B_MN, int EB, bool X3>
+// EPI >= 0 (skinny outputs of an unrolled recurrence, C4: 1024 x 128 per step): the consumer region's
+// chain runs on the accumulator like in the 2-CTA kernel -- h = tanh.(zx .+ Wh*h .+ b) forward,
+// dz = (Wh'*dz) .* (1 .- h.^2) backward -- stores only (no row-sum sinks, no shadows).
+template <int TN, bool A_MN, bool B_MN, int EB, bool X3, int EPI, int ZIN>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const __grid_constant__ CUtensorMap map_al, const __grid_constant__ CUtensorMap map_bl, const Params p) {
+               const __grid_constant__ CUtensorMap map_al, const __grid_constant__ CUtensorMap map_bl, const Params p,
+               const __grid_constant__ RegionParams rp) {
   static_assert(!X3 || EB == 4, "the compensated mode splits Float32 operands");
   using S = Smem<TN, X3>;
   using E = El<EB>;
@@ -360,6 +526,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       // so its adds arrive in chunk order -- deterministic)
       const bool red = X3 && (p.accumulate || kb0 > 0);
       const bool add_old = !X3 && p.accumulate;
+      using EP = Epilogue<(EPI >= 0 ? EPI : 0), ZIN>;
+      float ebase[EP::NS], eaccs[EP::NO];
+      if constexpr (EPI >= 0) EP::begin_tile(rp, m, n0, p.M, ebase, eaccs, false);
       mbar_wait(&tfull[acc], acc_phase);
       tcgen05_fence_after();
       float* crow = p.C + m + n0 * p.ldc;
@@ -369,7 +538,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // C += ...: the 32 old values are requested before the accumulator read, all in flight at
         // once (left inside the store loop they serialise: load -> add -> store per element)
         float old[32];
-        if (add_old) {
+        if (EPI < 0 && add_old) {
           const float* cp0 = crow + (long long)(c * 32) * p.ldc;
 #pragma unroll
           for (int j = 0; j < 32; j++) old[j] = __ldcg(cp0 + j * p.ldc);
@@ -387,7 +556,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         float* cp = crow + (long long)(c * 32) * p.ldc;
-        if (X3 && red) {
+        if constexpr (EPI >= 0) {
+          EP::chunk32(rp, v, m, n0 + c * 32, p.M, ebase, eaccs, nullptr, 0, -1, nullptr, nullptr, -1);
+        } else if (X3 && red) {
 #pragma unroll
           for (int j = 0; j < 32; j++) atomicAdd(cp + j * p.ldc, __uint_as_float(v[j]));
           if (p.pace_ns) __nanosleep(p.pace_ns);
@@ -478,10 +649,10 @@ struct Maps {
   CUtensorMap a, b, al, bl;  // al / bl: the lo shadows of the compensated mode (copies of a / b otherwise)
 };
 
-template <int TN, bool A_MN, bool B_MN, int EB, bool X3 = false>
-static int launch(const GemmArgs& g, const Maps& mp, int sm_count, cudaStream_t s) {
+template <int TN, bool A_MN, bool B_MN, int EB, bool X3 = false, int EPI = -1, int ZIN = 0>
+static int launch(const GemmArgs& g, const Maps& mp, int sm_count, cudaStream_t s, const RegionParams* rp = nullptr) {
   static bool attr = false;
-  auto kern = gemm_tc_kernel<TN, A_MN, B_MN, EB, X3>;
+  auto kern = gemm_tc_kernel<TN, A_MN, B_MN, EB, X3, EPI, ZIN>;
   if (!attr) {
     YOTA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<TN, X3>::TOTAL));
     attr = true;
@@ -508,7 +679,8 @@ static int launch(const GemmArgs& g, const Maps& mp, int sm_count, cudaStream_t 
   p.num_n = (int)(g.N / TN);
   const int tiles = p.num_m * p.num_n;
   const int grid = tiles < sm_count ? tiles : sm_count;
-  kern<<<grid, THREADS, Smem<TN, X3>::TOTAL, s>>>(mp.a, mp.b, mp.al, mp.bl, p);
+  static const RegionParams no_rp{};
+  kern<<<grid, THREADS, Smem<TN, X3>::TOTAL, s>>>(mp.a, mp.b, mp.al, mp.bl, p, rp ? *rp : no_rp);
   YOTA_CUDA(cudaGetLastError());
   return YOTA_OK;
 }
@@ -612,167 +784,6 @@ __device__ __forceinline__ void umma_2sm(uint32_t d_tmem, uint64_t a_desc, uint6
 }
 
 
-// ---- fused epilogues -------------------------------------------------------------------------
-// The consumer region of a GEMM output (bias [+ tanh] after W*h; tanh'(h) * delta + db after
-// W'*dz) runs on the accumulator tile instead of as a separate pass: the SAME ahead-of-time
-// micro-program (ChainOf<ID>) the region kernel would execute, with the accumulator element
-// standing in for the region's FULL operand `z_in`.  The epilogue's thread mapping (thread =
-// row m, walking the tile's columns) is the region kernel's mapping, so ROWVEC operands (bias)
-// are loaded once per tile and row sums (db) accumulate per thread in column order and leave
-// as partial[tile_n][m] for the same fixed-order finisher.
-// Out of line on purpose: the epilogue's hot loop keeps its register allocation (inlined, this tail
-// pushed the tanh'/db epilogue kernel from 208 registers to 255 with spills and from 360 to 427 us).
-// threadFenceReduction: publish this CTA's partials, count the arrival; the last of the num_n CTAs
-// covering these 128 rows sums all partials in rowsum_finish_kernel's fixed order.
-__device__ __noinline__ void finish_rowsum(const float* part, long long m, long long R, int num_n, float* out, float scale,
-                                           unsigned* cnt, unsigned* flag) {
-  __threadfence();
-  asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
-  const int et = (threadIdx.x - EPI_WARP0 * 32);
-  if (et == 0) *flag = atomicAdd(cnt + (m >> 7), 1u) == (unsigned)(num_n - 1) ? 1u : 0u;
-  asm volatile("bar.sync 1, 128;" ::: "memory");
-  if (*flag) {
-    __threadfence();
-    float sj[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-      float acc = 0.f;
-      for (int q = j; q < num_n; q += 8) acc = __fadd_rn(acc, __ldcg(part + (long long)q * R + m));
-      sj[j] = acc;
-    }
-    float t = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; j++) t = __fadd_rn(t, sj[j]);
-    out[m] = scale == 1.f ? t : __fmul_rn(t, scale);
-    if (et == 0) cnt[m >> 7] = 0u;  // ready for the next run
-  }
-  asm volatile("bar.sync 1, 128;" ::: "memory");  // the flag word is reused by the next tile
-}
-__device__ __noinline__ void prefetch_tile_l2(const float* line0, long long R, int lane) {
-#pragma unroll
-  for (int i = 0; i < 8; i++) asm volatile("prefetch.global.L2 [%0];" ::"l"(line0 + (long long)(lane + 32 * i) * R));
-}
-
-#define YCE(field, i) (ChainOf<ID>::value.field[decltype(i)::value])
-template <int ID, int Z_IN>
-struct Epilogue {
-  static constexpr int N_IN = ChainOf<ID>::value.n_in, N_OPS = ChainOf<ID>::value.n_ops, N_OUT = ChainOf<ID>::value.n_out;
-  static constexpr int NS = ChainOf<ID>::value.n_slots > 0 ? ChainOf<ID>::value.n_slots : 1;
-  static constexpr int NO = N_OUT > 0 ? N_OUT : 1;
-  static constexpr int first_rowsum() {
-    for (int k = 0; k < N_OUT; k++)
-      if (ChainOf<ID>::value.out_kind[k] == OUT_ROWSUM) return k;
-    return -1;
-  }
-  static constexpr int RS_OUT = first_rowsum();  // the sink whose partials the kernel finishes itself
-
-  __device__ __forceinline__ static void begin_tile(const RegionParams& rp, long long m, long long n0, long long R,
-                                                    float (&base)[NS], float (&accs)[NO], bool prefetch) {
-    // With ONE tile per CTA (small batches per GPU) nothing hides the latency of the epilogue's
-    // operand loads -- beside an all-reduce that latency triples -- so the tile's other FULL
-    // operands (h of the tanh' epilogue) are pulled into L2 while the mainloop runs.  With several
-    // tiles per CTA the next mainloop hides the epilogue and a prefetch would only be evicted by
-    // the operand stream before it is used (measured: +180 MB of DRAM reads, 360 -> 426 us).
-    static_for<N_IN>([&](auto k) {
-      constexpr int K = decltype(k)::value, cls = YCE(in_cls, k);
-      if constexpr (cls == CLS_FULL && K != Z_IN) if (prefetch) {
-        const int lane = threadIdx.x & 31;
-        prefetch_tile_l2(rp.in[K].ptr + n0 * R + (m - lane), R, lane);
-      }
-    });
-    static_for<NS>([&](auto s) { base[decltype(s)::value] = 0.f; });
-    static_for<NO>([&](auto k) { accs[decltype(k)::value] = 0.f; });
-    static_for<N_IN>([&](auto k) {
-      constexpr int cls = YCE(in_cls, k), slot = YCE(in_slot, k);
-      if constexpr (cls == CLS_ROWVEC) base[slot] = __ldg(rp.in[decltype(k)::value].ptr + m);
-      if constexpr (cls == CLS_SCALAR) base[slot] = __ldg(rp.in[decltype(k)::value].ptr);
-    });
-  }
-  // one chunk of 32 consecutive columns: accumulator values z[j] at (m, n0 + j).  The other FULL
-  // operands of the chunk are loaded up front (32 independent loads in flight per operand) --
-  // left per element, each load sits between the previous element's store and its own use and
-  // the epilogue runs at one DRAM latency per element.
-  __device__ __forceinline__ static void chunk32(const RegionParams& rp, const uint32_t (&z)[32], long long m,
-                                                 long long n0, long long R, const float (&base)[NS], float (&accs)[NO],
-                                                 float* tsh, long long tsh_ld, int tsh_out, float4* stage,
-                                                 __nv_bfloat16* bsh, int bsh_out) {
-    const int lane = threadIdx.x & 31;
-    float tv[4];
-    constexpr int NI = N_IN > 0 ? N_IN : 1;
-    float pre[NI][32];
-    static_for<N_IN>([&](auto k) {
-      constexpr int K = decltype(k)::value, cls = YCE(in_cls, k);
-      if constexpr (cls == CLS_FULL && K != Z_IN) {
-        const float* src = rp.in[K].ptr + n0 * R + m;
-#pragma unroll
-        for (int j = 0; j < 32; j++) pre[K][j] = __ldg(src + (long long)j * R);
-      }
-      if constexpr (cls == CLS_COLVEC) {
-        // lanes read consecutive entries once and broadcast them with shuffles
-        const float mine = __ldg(rp.in[K].ptr + n0 + (threadIdx.x & 31));
-#pragma unroll
-        for (int j = 0; j < 32; j++) pre[K][j] = __shfl_sync(0xffffffffu, mine, j);
-      }
-    });
-#pragma unroll
-    for (int j = 0; j < 32; j++) {
-      float v[NS];
-      static_for<NS>([&](auto s) { v[decltype(s)::value] = base[decltype(s)::value]; });
-      const long long off = (n0 + j) * R + m;
-      static_for<N_IN>([&](auto k) {
-        constexpr int K = decltype(k)::value, cls = YCE(in_cls, k), slot = YCE(in_slot, k);
-        if constexpr (cls == CLS_FULL) v[slot] = (K == Z_IN) ? __uint_as_float(z[j]) : pre[K][j];
-        if constexpr (cls == CLS_COLVEC) v[slot] = pre[K][j];
-      });
-      float acc = 0.f;
-      static_for<N_OPS>([&](auto i) {
-        constexpr int OP = YCE(op, i), D = YCE(dst, i), A = YCE(a, i), B = YCE(b, i);
-        float a, b;
-        if constexpr (A == RG_ACC) a = acc; else a = v[A];
-        if constexpr (B == RG_ACC) b = acc; else b = v[B];
-        acc = ew_v<OP>(a, b, rp.ops[decltype(i)::value].imm);
-        if constexpr (D != RG_NONE) v[D] = acc;
-      });
-      static_for<N_OUT>([&](auto k) {
-        constexpr int kind = YCE(out_kind, k), src = YCE(out_src, k);
-        if constexpr (kind == OUT_STORE) {
-          rp.out[decltype(k)::value].ptr[off] = v[src];
-          if (decltype(k)::value == tsh_out) tv[j & 3] = v[src];
-          if (bsh && decltype(k)::value == bsh_out) bsh[off] = __float2bfloat16_rn(v[src]);
-        } else
-          accs[decltype(k)::value] = __fadd_rn(accs[decltype(k)::value], v[src]);
-      });
-      // this thread's 32 columns of row m are one 128-byte line of the transposed copy: staged in
-      // shared memory (16-byte pieces XOR-swizzled by row: conflict-free both ways) ...
-      if ((j & 3) == 3 && tsh) stage[lane * 8 + ((j >> 2) ^ (lane & 7))] = make_float4(tv[0], tv[1], tv[2], tv[3]);
-    }
-    if (tsh) {
-      // ... and written out 4 whole lines per warp instruction (8 lanes x 16 bytes each) instead of
-      // 32 quarter-sector stores to 32 different lines
-      __syncwarp();
-      float* base_row = tsh + (m - lane) * tsh_ld + n0;
-#pragma unroll
-      for (int i = 0; i < 8; i++) {
-        const int rr = 4 * i + (lane >> 3), piece = lane & 7;
-        reinterpret_cast<float4*>(base_row + (long long)rr * tsh_ld)[piece] = stage[rr * 8 + (piece ^ (rr & 7))];
-      }
-      __syncwarp();
-    }
-  }
-  __device__ __forceinline__ static void end_tile(const RegionParams& rp, long long m, long long tile_n, long long R,
-                                                  const float (&accs)[NO], const Params& p, unsigned* flag) {
-    static_for<N_OUT>([&](auto k) {
-      constexpr int kind = YCE(out_kind, k);
-      if constexpr (kind == OUT_ROWSUM) rp.out[decltype(k)::value].ptr[tile_n * R + m] = accs[decltype(k)::value];
-    });
-    constexpr int RS = RS_OUT;
-    if constexpr (RS >= 0) {
-      if (p.rs_cnt) finish_rowsum(rp.out[RS].ptr, m, R, p.num_n, p.rs_out, p.rs_scale, p.rs_cnt, flag);
-    }
-  }
-
-};
-#undef YCE
 
 // MC = 2: clusters of FOUR CTAs -- two pairs computing the tiles (m, 2j) and (m, 2j + 1), which
 // read the same 256 rows of A.  Each CTA fetches only half of its 128-row A box and TMA-multicasts
@@ -1233,13 +1244,67 @@ static int launch_epi(const GemmArgs& g, int sm_count, cudaStream_t s, const Reg
 }
 }  // namespace tc
 
+// tile width the 1-CTA kernel uses: the widest that still gives half the SMs a CTA; skinny outputs
+// go down to 128 x 32 (64 for BF16 operands, whose MN-major boxes are 64 elements wide)
+static int pick_tn(const GemmArgs& g, int sm_count) {
+  const int eb = g.mode == 2 ? 2 : 4;
+  const int widths[4] = {256, 128, 64, 32};
+  for (int w : widths)
+    if (w >= (eb == 4 ? 32 : 64) && g.N % w == 0 && (g.M / tc::TM) * (g.N / w) >= sm_count / 2) return w;
+  return eb == 4 ? 32 : 64;
+}
+
+// store-only chains that also exist as epilogues of the 1-CTA kernel (TF32, 128 x 32 tiles)
+template <int ID>
+static constexpr bool epi1_chain_stores_only() {
+  for (int k = 0; k < ChainOf<ID>::value.n_out; k++)
+    if (ChainOf<ID>::value.out_kind[k] != OUT_STORE) return false;
+  return true;
+}
+bool gemm_epilogue1_chain_ok(const GemmArgs& g, int sm_count, int static_id, int z_in) {
+  if (g.mode != 1 || !gemm_tc_eligible(g) || gemm_tc2_eligible(g, sm_count) || g.transB || g.accumulate) return false;
+  if (pick_tn(g, sm_count) != 32) return false;
+  switch (static_id) {
+#define X(ID) \
+  case ID:    \
+    return epi_z_ok<ID>(z_in) && epi1_chain_stores_only<ID>();
+    YOTA_EPI1_CHAIN_LIST(X)
+#undef X
+  }
+  return false;
+}
+
+namespace tc {
+template <int ID, int ZIN>
+static int launch_epi1(const GemmArgs& g, const Maps& mp, int sm_count, cudaStream_t s, const RegionParams& rp, bool A_MN) {
+  if constexpr (epi_z_ok<ID>(ZIN) && epi1_chain_stores_only<ID>()) {
+    if (A_MN) return launch<32, true, false, 4, false, ID, ZIN>(g, mp, sm_count, s, &rp);
+    return launch<32, false, false, 4, false, ID, ZIN>(g, mp, sm_count, s, &rp);
+  } else {
+    YOTA_FAIL(YOTA_E_ARG, "internal: chain %d cannot run as a 1-CTA epilogue", ID);
+  }
+}
+}  // namespace tc
+
 // GEMM whose output tile goes straight through the consumer region's micro-program
 int launch_gemm_tc_epilogue(yota_ctx* ctx, const GemmArgs& g, int static_id, const RegionParams& rp, int z_in,
                             cudaStream_t s) {
+  const bool A_MN = !g.transA;
+  if (gemm_epilogue1_chain_ok(g, ctx->sm_count, static_id, z_in)) {  // skinny output: 1-CTA kernel, 128 x 32 tiles
+    tc::Maps mp;
+    YOTA_TRY(tc::make_maps(&mp, g, A_MN, false, 32));
+    switch (static_id) {
+#define X(ID)                                                                        \
+  case ID:                                                                           \
+    return z_in == 0 ? tc::launch_epi1<ID, 0>(g, mp, grid_sms(ctx), s, rp, A_MN)    \
+                     : tc::launch_epi1<ID, 1>(g, mp, grid_sms(ctx), s, rp, A_MN);
+      YOTA_EPI1_CHAIN_LIST(X)
+#undef X
+    }
+  }
   if (!gemm_tc2_eligible(g, ctx->sm_count) || g.accumulate ||
       !gemm_epilogue_chain_ok(static_id, g.transA, g.transB, z_in))
     YOTA_FAIL(YOTA_E_ARG, "internal: GEMM epilogue fusion planned for an ineligible GEMM");
-  const bool A_MN = !g.transA;
   switch (static_id) {
 #define X(ID)                                                                       \
   case ID:                                                                          \
@@ -1273,15 +1338,7 @@ int launch_gemm_tc(yota_ctx* ctx, const GemmArgs& g, cudaStream_t s) {
     GO2(false, false);
 #undef GO2
   }
-  // widest tile that still gives half the SMs a CTA; skinny outputs go down to 128 x 32 (64 for
-  // BF16 operands, whose MN-major boxes are 64 elements wide)
-  const int widths[4] = {256, 128, 64, 32};
-  int TN = eb == 4 ? 32 : 64;
-  for (int w : widths)
-    if (w >= (eb == 4 ? 32 : 64) && g.N % w == 0 && (g.M / tc::TM) * (g.N / w) >= ctx->sm_count / 2) {
-      TN = w;
-      break;
-    }
+  const int TN = pick_tn(g, ctx->sm_count);
   YOTA_TRY(tc::make_maps(&mp, g, A_MN, B_MN, TN));
 #define GO(TNv, a, b)                                                                          \
   return g.mode == 3   ? tc::launch<TNv, a, b, 4, true>(g, mp, grid_sms(ctx), s)               \

@@ -1754,7 +1754,8 @@ static int plan_gemm_epilogues(yota_program& P) {
     g.transA = (int)o.iattr[0];
     g.transB = (int)o.iattr[1];
     gemm_dims(P, o, &g.M, &g.N, &g.K, &g.lda, &g.ldb);
-    if (!gemm_tc2_eligible(g, P.ctx->sm_count)) continue;
+    const bool two_cta = gemm_tc2_eligible(g, P.ctx->sm_count);
+    if (!two_cta && !(mode == 1 && gemm_tc_eligible(g))) continue;
     // every needed consumer of z is an elementwise op of one region
     int ri = -1;
     bool ok = true;
@@ -1782,7 +1783,10 @@ static int plan_gemm_epilogues(yota_program& P) {
       }
     }
     if (!ok || z_in < 0) continue;
-    if (!gemm_epilogue_chain_ok(r.L.static_id, g.transA, g.transB, z_in)) continue;
+    if (two_cta ? !gemm_epilogue_chain_ok(r.L.static_id, g.transA, g.transB, z_in)
+                : !(r.sums.empty() && !getenv("YOTA_NO_EPILOGUE1") &&
+                    gemm_epilogue1_chain_ok(g, P.ctx->sm_count, r.L.static_id, z_in)))
+      continue;
     // absorb
     gs.epi_region = ri;
     gs.epi_z_in = z_in;
