@@ -213,7 +213,8 @@ def test_recurrence_epilogues_of_the_1cta_kernel(monkeypatch):
     d = [Y.cu(a) for a in args]
     gf = Y.CompiledGrad(Y.gradtape(f, *d), flags=ffi.FLAG_GEMM_TF32)
     desc = gf.describe()
-    assert desc.count("epilogue{region[add,add,tanh]}") == T - 1 and desc.count("epilogue{region[square,rsubc,mul]}") >= T - 2, desc
+    # (the last forward step's region also carries the loss and the start of the pullback: not an epilogue)
+    assert desc.count("epilogue{region[add,add,tanh]}") == T - 2 and desc.count("epilogue{region[square,rsubc,mul]}") == T - 1, desc
     v1, g1 = gf.run(d)
     g1 = [x.to_host() for x in g1]
     monkeypatch.setenv("YOTA_NO_EPILOGUE1", "1")

@@ -87,6 +87,61 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// ---- cluster-scope helpers (2-CTA pairs, multicast clusters, split-K clusters) ----------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same smem offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
+// release at cluster scope: the data this thread wrote into the target CTA's shared memory is
+// visible to whoever acquires the barrier there
+__device__ __forceinline__ void mbar_arrive_remote_release(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait_acquire_cluster(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAITC_LOOP:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAITC_DONE;\n\t"
+      "bra WAITC_LOOP;\n\t"
+      "WAITC_DONE:\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(const void* p, uint32_t cta) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(p)), "r"(cta));
+  return ra;
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -348,7 +403,12 @@ struct Smem {
 // EPI >= 0 (skinny outputs of an unrolled recurrence, C4: 1024 x 128 per step): the consumer region's
 // chain runs on the accumulator like in the 2-CTA kernel -- h = tanh.(zx .+ Wh*h .+ b) forward,
 // dz = (Wh'*dz) .* (1 .- h.^2) backward -- stores only (no row-sum sinks, no shadows).
-template <int TN, bool A_MN, bool B_MN, int EB, bool X3, int EPI, int ZIN>
+// KS > 1 (skinny outputs with a long K: the per-step GEMMs of a recurrence, 1024 x 128 x 1024):
+// a cluster of KS CTAs shares one output tile, each streaming 1/KS of K -- a CTA that streams all
+// of its A panel alone is bound by what one SM can pull from L2 (640 KB in ~7 us), four of them
+// need a quarter of that.  The non-leader CTAs write their accumulators into the leader's shared
+// memory (DSMEM), the leader adds them in rank order (deterministic) and runs the epilogue.
+template <int TN, bool A_MN, bool B_MN, int EB, bool X3, int EPI, int ZIN, int KS>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_al, const __grid_constant__ CUtensorMap map_bl, const Params p,
@@ -364,10 +424,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* tfull = empty + S::NSTAGE;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  static_assert(!(KS > 1) || (!X3 && S::NSTAGE * 16 + 2 * 16 + 8 <= 176), "split-K: plain TF32/BF16, barriers fit");
+  uint64_t* pfull = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF + 176);   // leader: partial tiles of the other CTAs landed
+  uint64_t* pempty = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF + 184);  // non-leaders: the leader has consumed them
+  float* part = reinterpret_cast<float*>(smem + S::BAR_OFF + 256);          // leader: [KS - 1][TN][128] partial sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = p.num_m * p.num_n;
-  const int nkb = (int)(p.K / (128 / EB));
+  const uint32_t kr = KS > 1 ? cluster_ctarank() : 0u;  // which K-slice of the tile this CTA computes
+  const int tile0 = (int)blockIdx.x / KS, tile_step = (int)gridDim.x / KS;
+  const int nkb = (int)(p.K / (128 / EB)) / KS;   // k-blocks of this CTA ...
+  const int kbeg = (int)kr * nkb;                 // ... starting here
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S::NSTAGE; s++) {
@@ -377,6 +444,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     for (int a = 0; a < 2; a++) {
       mbar_init(&tfull[a], 1);
       mbar_init(&tempty[a], 128);
+    }
+    if (KS > 1) {
+      mbar_init(pfull, (KS - 1) * 128);
+      mbar_init(pempty, 128);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -392,6 +463,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
   tcgen05_fence_before();
   __syncthreads();
+  if constexpr (KS > 1) cluster_sync_all();  // every CTA's barriers exist before anyone arrives remotely
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -405,7 +477,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     static_assert((X3 ? 2 : 1) * (NA + NB) <= 32, "one lane per TMA box");
     int stage = 0;
     uint32_t phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (int t = tile0; t < num_tiles; t += tile_step) {
       const int m0 = (t % p.num_m) * TM, n0 = (t / p.num_m) * TN;
       for (int kb = 0; kb < nkb; kb++) {
         if (lane == 0) {  // one poller per warp; the other lanes are released by the warp barrier
@@ -413,7 +485,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           mbar_expect_tx(&full[stage], S::STAGE_BYTES);
         }
         __syncwarp();
-        const int k0 = kb * TK;
+        const int k0 = (kbeg + kb) * TK;
 #pragma unroll
         for (int part = 0; part < (X3 ? 2 : 1); part++) {  // part 1: the lo tiles of the compensated mode
           unsigned char* sa = smem + stage * S::STAGE_BYTES + part * S::HALF;
@@ -465,7 +537,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int acc = 0;
       uint32_t acc_phase = 0;
       const int kc = X3 ? p.kchunk : nkb;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x)
+      for (int t = tile0; t < num_tiles; t += tile_step)
        for (int ch = 0; ch < (X3 ? (nkb + kc - 1) / kc : 1); ch++) {  // one accumulator per chunk of k-blocks (X3) / per tile
         const int kb0 = X3 ? ch * kc : 0;
         mbar_wait(&tempty[acc], acc_phase ^ 1);
@@ -515,8 +587,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t pphase = 0;  // split-K: phase of the partial-sum hand-over barriers
     const int kc = X3 ? p.kchunk : nkb;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x)
+    for (int t = tile0; t < num_tiles; t += tile_step)
      for (int ch = 0; ch < (X3 ? (nkb + kc - 1) / kc : 1); ch++) {
       const int kb0 = X3 ? ch * kc : 0;
       const long long m = (long long)(t % p.num_m) * TM + q * 32 + lane;
@@ -526,10 +599,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       // so its adds arrive in chunk order -- deterministic)
       const bool red = X3 && (p.accumulate || kb0 > 0);
       const bool add_old = !X3 && p.accumulate;
+      if constexpr (KS > 1) {
+        if (kr != 0) {
+          // partial sums of this CTA's K-slice -> the leader's shared memory, [slice][column][row]
+          mbar_wait(pempty, pphase ^ 1);  // the leader is done with the previous tile's partials
+          mbar_wait(&tfull[acc], acc_phase);
+          tcgen05_fence_after();
+          const uint32_t dst0 = map_to_cta(part, 0) + (uint32_t)((((kr - 1) * TN) * 128 + (q * 32 + lane)) * 4);
+#pragma unroll 1
+          for (int c = 0; c < TN / 32; c++) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem_base + (uint32_t)(acc * TN + c * 32) + ((uint32_t)(q * 32) << 16);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; j++) st_cluster_f32(dst0 + (uint32_t)((c * 32 + j) * 128 * 4), __uint_as_float(v[j]));
+          }
+          tcgen05_fence_before();
+          mbar_arrive(&tempty[acc]);
+          mbar_arrive_remote_release(pfull, 0);
+          pphase ^= 1;
+          if (++acc == 2) {
+            acc = 0;
+            acc_phase ^= 1;
+          }
+          continue;
+        }
+      }
       using EP = Epilogue<(EPI >= 0 ? EPI : 0), ZIN>;
       float ebase[EP::NS], eaccs[EP::NO];
       if constexpr (EPI >= 0) EP::begin_tile(rp, m, n0, p.M, ebase, eaccs, false);
       mbar_wait(&tfull[acc], acc_phase);
+      if constexpr (KS > 1) {
+        mbar_wait_acquire_cluster(pfull, pphase);  // the other K-slices' partial sums have landed
+        pphase ^= 1;
+      }
       tcgen05_fence_after();
       float* crow = p.C + m + n0 * p.ldc;
 #pragma unroll 1
@@ -555,6 +668,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             : "r"(taddr)
             : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if constexpr (KS > 1) {  // + the other K-slices, in rank order
+#pragma unroll
+          for (int r = 1; r < KS; r++) {
+            const float* pr = part + ((r - 1) * TN + c * 32) * 128 + (q * 32 + lane);
+#pragma unroll
+            for (int j = 0; j < 32; j++) v[j] = __float_as_uint(__fadd_rn(__uint_as_float(v[j]), pr[j * 128]));
+          }
+        }
         float* cp = crow + (long long)(c * 32) * p.ldc;
         if constexpr (EPI >= 0) {
           EP::chunk32(rp, v, m, n0 + c * 32, p.M, ebase, eaccs, nullptr, 0, -1, nullptr, nullptr, -1);
@@ -572,6 +693,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
       tcgen05_fence_before();
       mbar_arrive(&tempty[acc]);
+      if constexpr (KS > 1) {  // the partial-sum buffer may be overwritten for the next tile
+#pragma unroll
+        for (int r = 1; r < KS; r++) mbar_arrive_remote(pempty, (uint32_t)r);
+      }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
@@ -580,6 +705,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
   tcgen05_fence_before();
   __syncthreads();
+  if constexpr (KS > 1) cluster_sync_all();  // the leader's shared memory outlives the others' DSMEM stores
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * TN) : "memory");
@@ -649,12 +775,14 @@ struct Maps {
   CUtensorMap a, b, al, bl;  // al / bl: the lo shadows of the compensated mode (copies of a / b otherwise)
 };
 
-template <int TN, bool A_MN, bool B_MN, int EB, bool X3 = false, int EPI = -1, int ZIN = 0>
+template <int TN, bool A_MN, bool B_MN, int EB, bool X3 = false, int EPI = -1, int ZIN = 0, int KS = 1>
 static int launch(const GemmArgs& g, const Maps& mp, int sm_count, cudaStream_t s, const RegionParams* rp = nullptr) {
   static bool attr = false;
-  auto kern = gemm_tc_kernel<TN, A_MN, B_MN, EB, X3, EPI, ZIN>;
+  auto kern = gemm_tc_kernel<TN, A_MN, B_MN, EB, X3, EPI, ZIN, KS>;
+  constexpr int SMEM = Smem<TN, X3>::TOTAL + (KS > 1 ? (KS - 1) * TN * 128 * 4 : 0);
+  static_assert(SMEM <= 227 * 1024, "split-K partial sums must fit beside the ring");
   if (!attr) {
-    YOTA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<TN, X3>::TOTAL));
+    YOTA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr = true;
   }
   Params p;
@@ -678,10 +806,27 @@ static int launch(const GemmArgs& g, const Maps& mp, int sm_count, cudaStream_t 
   p.num_m = (int)(g.M / TM);
   p.num_n = (int)(g.N / TN);
   const int tiles = p.num_m * p.num_n;
-  const int grid = tiles < sm_count ? tiles : sm_count;
   static const RegionParams no_rp{};
-  kern<<<grid, THREADS, Smem<TN, X3>::TOTAL, s>>>(mp.a, mp.b, mp.al, mp.bl, p, rp ? *rp : no_rp);
-  YOTA_CUDA(cudaGetLastError());
+  if constexpr (KS == 1) {
+    const int grid = tiles < sm_count ? tiles : sm_count;
+    kern<<<grid, THREADS, SMEM, s>>>(mp.a, mp.b, mp.al, mp.bl, p, rp ? *rp : no_rp);
+    YOTA_CUDA(cudaGetLastError());
+  } else {
+    const int clusters = tiles < sm_count / KS ? tiles : sm_count / KS;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(KS * (clusters < 1 ? 1 : clusters));
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = SMEM;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = KS;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    YOTA_CUDA(cudaLaunchKernelEx(&cfg, kern, mp.a, mp.b, mp.al, mp.bl, p, rp ? *rp : no_rp));
+  }
   return YOTA_OK;
 }
 
@@ -713,26 +858,6 @@ struct Smem2T {
   static constexpr int TOTAL = TSH_OFF + 4 * 4096 + 1024;  // + slack for 1 KiB alignment
 };
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// arrive on the barrier at the same smem offset in CTA `cta` of the cluster
-__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
-  asm volatile(
-      "{\n\t"
-      ".reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(cta)
-      : "memory");
-}
 // TMA load whose completion is signalled on the LEADER CTA's mbarrier (peer bit cleared)
 __device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile(
@@ -1274,10 +1399,21 @@ bool gemm_epilogue1_chain_ok(const GemmArgs& g, int sm_count, int static_id, int
   return false;
 }
 
+// skinny output with a long K: a cluster of 4 CTAs per tile, each streaming a quarter of K
+static bool use_splitk4(const GemmArgs& g, int sm_count) {
+  if (g.mode != 1 || g.transB || getenv("YOTA_GEMM_NO_SPLITK")) return false;
+  const long long tiles = (g.M / tc::TM) * (g.N / 32), nkb = g.K / 32;
+  return pick_tn(g, sm_count) == 32 && tiles <= sm_count / 4 && nkb % 4 == 0 && nkb >= 8;
+}
+
 namespace tc {
 template <int ID, int ZIN>
 static int launch_epi1(const GemmArgs& g, const Maps& mp, int sm_count, cudaStream_t s, const RegionParams& rp, bool A_MN) {
   if constexpr (epi_z_ok<ID>(ZIN) && epi1_chain_stores_only<ID>()) {
+    if (use_splitk4(g, sm_count)) {
+      if (A_MN) return launch<32, true, false, 4, false, ID, ZIN, 4>(g, mp, sm_count, s, &rp);
+      return launch<32, false, false, 4, false, ID, ZIN, 4>(g, mp, sm_count, s, &rp);
+    }
     if (A_MN) return launch<32, true, false, 4, false, ID, ZIN>(g, mp, sm_count, s, &rp);
     return launch<32, false, false, 4, false, ID, ZIN>(g, mp, sm_count, s, &rp);
   } else {
@@ -1355,6 +1491,10 @@ int launch_gemm_tc(yota_ctx* ctx, const GemmArgs& g, cudaStream_t s) {
   if (TN == 128) GOALL(128);
   if (TN == 64) GOALL(64);
   if (eb == 4) {
+    if (use_splitk4(g, ctx->sm_count)) {  // (B K-major: the forward and dh products of a recurrence)
+      if (A_MN) return tc::launch<32, true, false, 4, false, -1, 0, 4>(g, mp, grid_sms(ctx), s);
+      return tc::launch<32, false, false, 4, false, -1, 0, 4>(g, mp, grid_sms(ctx), s);
+    }
 #define GO32(a, b)                                                                      \
   return g.mode == 3 ? tc::launch<32, a, b, 4, true>(g, mp, grid_sms(ctx), s)           \
                      : tc::launch<32, a, b, 4>(g, mp, grid_sms(ctx), s)
