@@ -1,9 +1,10 @@
 #!/bin/bash
-# round 2, first call: smoke, the whole GPU suite (no -x: every failure is wanted), default bench
+# round 2: smoke, the whole GPU suite (no -x: every failure is wanted), default bench + reference arm
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,memory.total --format=csv,noheader; nproc; free -g | head -2
+nvidia-smi --query-gpu=name,memory.total --format=csv,noheader; nproc
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/smoke.log
-timeout 1500 python -m pytest tests -m gpu -q --timeout 900 --durations=10 -s > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
-grep -E "passed|failed|FAILED|ERROR|C3 full size|Error" gpurun_out/pytest_gpu.log | tail -40
-timeout 600 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo "bench default rc=$?"
-tail -c 6000 gpurun_out/bench_default.json; tail -5 gpurun_out/bench_default.err
+timeout 1500 python -m pytest tests -m gpu -q --timeout 900 --durations=10 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
+grep -E "passed|failed|FAILED|ERROR" gpurun_out/pytest_gpu.log | tail -20
+timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo "bench default rc=$?"
+tail -c 5500 gpurun_out/bench_default.json; tail -5 gpurun_out/bench_default.err
+timeout 400 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "bench reference rc=$?"; cut -c1-700 gpurun_out/bench_reference.json
