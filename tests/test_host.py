@@ -166,6 +166,8 @@ def test_planner_c5_gathers_in_the_region_and_scales_in_the_fold(built):
     assert "(gathered inside step" in desc and " gather " in desc and regions == 1, desc
     assert "region[mul,copy,mul]+sum" in desc  # dG = seed .* V is gone from the region
     assert ws < 128 << 20, ws  # was 2 x 4 GiB of temporaries
+    # the index vector is a program input: its sort leaves the step and runs beside the forward pass
+    assert desc.count("index sort on the side stream") == 1, desc
     unf, (_s, _l, ws_u, *_r) = _plan(cases.c5_embed, *av, flags=ffi.FLAG_NO_FUSE)
     assert ": getindex ->" in unf and ws_u > 8 << 30
 

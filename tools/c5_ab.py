@@ -1,0 +1,31 @@
+#!/usr/bin/env python
+"""C5 evals/s in the graph-replayed loop (the product path): python tools/c5_ab.py [steps]
+Used for A/B runs through environment switches (YOTA_NO_PRESORT, YOTA_PRESORT_REGION_PER_SM)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import bench  # noqa: E402
+import yota_b200 as Y  # noqa: E402
+from yota_b200 import ffi  # noqa: E402
+
+steps = int(sys.argv[1]) if len(sys.argv) > 1 else 50
+name = sys.argv[2] if len(sys.argv) > 2 else "c5"
+ctx = Y.context(0)
+wl = bench.workload(name, 0, 1)
+dargs = [Y.cu(x) for x in wl["args"]]
+gf = Y.CompiledGrad(Y.gradtape(wl["f"], *dargs), ctx, 0)
+outs = [Y.B200Array(gf._out_dims[s], "f32", ctx) for s in range(gf.n_out)]
+for _ in range(5):
+    gf.run(dargs, out=outs)
+best = 1e9
+for _ in range(3):
+    tm = bench.Timer(ctx, ffi.lib(), ffi)
+    tm.start()
+    for _ in range(steps):
+        gf.run(dargs, out=outs)
+    best = min(best, tm.stop() / steps)
+tag = " ".join(f"{k}={v}" for k, v in os.environ.items() if k.startswith("YOTA_"))
+print(f"{name}: {best:.4f} ms/eval  {1e3 / best:.1f} evals/s  [{tag or 'default'}]")

@@ -42,6 +42,7 @@ int ctx_ensure_device(yota_ctx* ctx) {
   YOTA_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   YOTA_CUDA(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
   YOTA_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  YOTA_CUDA(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
   YOTA_CUDA(cudaEventCreateWithFlags(&ctx->fence_event, cudaEventDisableTiming));
   YOTA_CUDA(cudaEventCreateWithFlags(&ctx->free_event, cudaEventDisableTiming));
   YOTA_CUDA(cudaHostAlloc((void**)&ctx->err_host, 4 * sizeof(long long), cudaHostAllocMapped));
@@ -159,6 +160,7 @@ int yota_shutdown(yota_ctx* ctx) {
     cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->comm_stream);
     cudaStreamDestroy(ctx->copy_stream);
+    cudaStreamDestroy(ctx->side_stream);
     cudaEventDestroy(ctx->fence_event);
     if (ctx->free_event) cudaEventDestroy(ctx->free_event);
     for (auto& e : ctx->pending_ar) cudaEventDestroy(e.ev);

@@ -49,6 +49,7 @@ struct yota_ctx {
   bool device_ready = false;  // lazily initialised so that plan-only use works without a GPU
   cudaStream_t stream = nullptr;
   cudaStream_t comm_stream = nullptr;
+  cudaStream_t side_stream = nullptr;  // work of a run that depends on its inputs only (index sorts)
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t fence_event = nullptr;
   // size-bucketed free lists (caller-owned buffers come and go every grad() call)
@@ -165,7 +166,7 @@ struct RegionLaunch {
 };
 
 // geometry from (R, C, V): fills TRG, TCC, rowblocks, colchunks, cols_per_chunk, grid
-void region_geometry(RegionLaunch& L, int sm_count);
+void region_geometry(RegionLaunch& L, int sm_count, int ctas_per_sm = 8);
 int launch_region(const RegionLaunch& L, cudaStream_t s);
 // out[r] = scale * sum_p partial[p*R + r], p ascending (deterministic)
 int launch_rowsum_finish(float* out, const float* partial, long long R, int P, float scale, cudaStream_t s);
@@ -250,8 +251,12 @@ struct IndexSpec {
 int launch_getindex(const IndexSpec& sp, float* y, const float* x, long long n_out, cudaStream_t s,
                     long long* err = nullptr);
 size_t ungetindex_workspace_bytes(const IndexSpec& sp);
+// A scatter-add is a sort of the index vector (needs nothing else) followed by the ordered fold of
+// dy: UNGET_SORT / UNGET_FOLD run the halves separately on the same workspace, UNGET_ALL both.
+enum { UNGET_ALL = 0, UNGET_SORT = 1, UNGET_FOLD = 2 };
 int launch_ungetindex(const IndexSpec& sp, float* dx, const float* dy, void* workspace, size_t ws_bytes,
-                      int sm_count, cudaStream_t s, const float* scale = nullptr, long long* err = nullptr);
+                      int sm_count, cudaStream_t s, const float* scale = nullptr, long long* err = nullptr,
+                      int phase = UNGET_ALL);
 // acc[I...] = acc[I...] + (0.0f + dy) over the selection (no index vectors); other elements untouched
 int launch_slice_accum(const IndexSpec& sp, float* acc, const float* dy, bool scalar_dy, cudaStream_t s);
 size_t scatter_cols_workspace_bytes(long long n_dst, long long n_src);
@@ -260,7 +265,7 @@ size_t scatter_cols_workspace_bytes(long long n_dst, long long n_src);
 int launch_scatter_add_cols(float* dx, long long rows, long long n_dst, const float* dy, const int64_t* idx,
                             long long n_src, void* workspace, size_t ws_bytes, cudaStream_t s,
                             const float* scale = nullptr, long long* err = nullptr, long long dst_lo = 0,
-                            long long n_total = -1);
+                            long long n_total = -1, int phase = UNGET_ALL);
 int launch_gather_cols(float* y, const float* x, long long rows, long long n_dst, const int64_t* idx,
                        long long n_src, cudaStream_t s, long long* err = nullptr);
 

@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(RG_THREADS) region_interp_kernel(const __grid_
 
 namespace yota {
 
-void region_geometry(RegionLaunch& L, int sm_count) {
+void region_geometry(RegionLaunch& L, int sm_count, int ctas_per_sm) {
   RegionParams& p = L.p;
   const long long RG = p.R / L.V;
   if (RG >= RG_THREADS) {
@@ -174,7 +174,7 @@ void region_geometry(RegionLaunch& L, int sm_count) {
     p.rowblocks = 1;
   }
   L.smem = (size_t)p.n_slots * RG_THREADS * sizeof(float) * L.V;
-  int per_sm = 8;
+  int per_sm = ctas_per_sm;
   if (L.smem > 0) {
     int fit = (int)((200 * 1024) / L.smem);
     if (fit < per_sm) per_sm = fit < 1 ? 1 : fit;

@@ -312,9 +312,11 @@ __global__ void __launch_bounds__(RS_T) radix_hist_kernel(const unsigned* __rest
 }
 
 // Each warp owns a contiguous 512-key segment of the CTA's tile and walks it in order, 32
-// keys at a time; match-any gives the rank among equal digits inside a round.  Position =
-// global digit base (scan of hist) + earlier warps' count + this warp's running count + rank
-// => a stable split.
+// keys at a time; ballots give the rank among equal digits inside a round.  Rank inside the
+// CTA = digit's start in the tile + earlier warps' count + this warp's running count + rank in
+// the round => a stable split.  The tile is first split in shared memory and then copied out
+// digit run by digit run: consecutive threads write consecutive addresses (a direct scatter of
+// 4-byte items costs a 32-byte sector each, which made this kernel L2-write bound at 60 us).
 template <int BITS, bool FROM_IDX>
 __global__ void __launch_bounds__(RS_T) radix_scatter_kernel(const unsigned* __restrict__ keys_in,
                                                              const unsigned* __restrict__ vals_in,
@@ -323,15 +325,21 @@ __global__ void __launch_bounds__(RS_T) radix_scatter_kernel(const unsigned* __r
                                                              unsigned* __restrict__ vals_out, long long n, int shift,
                                                              const unsigned* __restrict__ hist, int nblocks) {
   constexpr int ND = 1 << BITS;
-  __shared__ unsigned sh[RS_WARPS * ND];  // [warp][digit] counts, then running offsets
+  static_assert(ND <= RS_T, "one thread per digit in the table pass");
+  constexpr int SEG = RS_TILE / RS_WARPS, LD = 4;  // keys per warp; key loads kept in flight
+  __shared__ unsigned sh[RS_WARPS * ND];  // [warp][digit] counts, then running tile-local offsets
+  __shared__ unsigned gbase[ND];          // global position of tile-local position 0 of each digit run
+  __shared__ unsigned xk[RS_TILE], xv[RS_TILE];
+  __shared__ unsigned scan_sm[8];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   unsigned* mine = sh + w * ND;
   for (int i = threadIdx.x; i < RS_WARPS * ND; i += RS_T) sh[i] = 0;
   __syncthreads();
-  const long long wbase = (long long)blockIdx.x * RS_TILE + (long long)w * (RS_TILE / RS_WARPS);
+  const long long tbase = (long long)blockIdx.x * RS_TILE;
+  const long long wbase = tbase + (long long)w * SEG;
   const unsigned lt = (1u << lane) - 1u;
   // Lanes holding the same digit, from BITS ballots (MATCH.ANY is microcoded and ~50x slower
-  // than VOTE on this part: it made this kernel 5x slower than the data movement).
+  // than VOTE on this part).
   auto peers_of = [&](unsigned d, unsigned act) {
     unsigned peers = act;
 #pragma unroll
@@ -342,48 +350,84 @@ __global__ void __launch_bounds__(RS_T) radix_scatter_kernel(const unsigned* __r
     }
     return peers;
   };
+  auto load_key = [&](long long i) {
+    return i < n ? (FROM_IDX ? key_of_idx(idx, i, n_dst) : keys_in[i]) : 0xffffffffu;
+  };
   // pass 1: per-warp digit counts (keys are re-read in pass 2: 16 MB from L2 is cheaper than
   // 16 live registers per thread)
-#pragma unroll 4
-  for (int r = 0; r < RS_ROUNDS; r++) {
-    const long long i = wbase + r * 32 + lane;
-    const bool ok = i < n;
-    const unsigned key = ok ? (FROM_IDX ? key_of_idx(idx, i, n_dst) : keys_in[i]) : 0xffffffffu;
-    const unsigned d = (key >> shift) & (ND - 1);
-    const unsigned act = __ballot_sync(0xffffffffu, ok);
-    const unsigned peers = peers_of(d, act);
-    if (ok && (peers & lt) == 0) mine[d] += __popc(peers);  // lowest lane of each digit group
-    __syncwarp();
-  }
-  __syncthreads();
-  // exclusive prefix over warps per digit, plus the global base of this (digit, block)
-  for (int d = threadIdx.x; d < ND; d += RS_T) {
-    unsigned run = hist[(long long)d * nblocks + blockIdx.x];
+  for (int r0 = 0; r0 < RS_ROUNDS; r0 += LD) {
+    unsigned k[LD];
 #pragma unroll
-    for (int ww = 0; ww < RS_WARPS; ww++) {
-      const unsigned c = sh[ww * ND + d];
-      sh[ww * ND + d] = run;
-      run += c;
+    for (int q = 0; q < LD; q++) k[q] = load_key(wbase + (r0 + q) * 32 + lane);
+#pragma unroll
+    for (int q = 0; q < LD; q++) {
+      const bool ok = wbase + (r0 + q) * 32 + lane < n;
+      const unsigned d = (k[q] >> shift) & (ND - 1);
+      const unsigned act = __ballot_sync(0xffffffffu, ok);
+      const unsigned peers = peers_of(d, act);
+      if (ok && (peers & lt) == 0) mine[d] += __popc(peers);  // lowest lane of each digit group
+      __syncwarp();
     }
   }
   __syncthreads();
-  // pass 2: stable scatter
-#pragma unroll 2
-  for (int r = 0; r < RS_ROUNDS; r++) {
-    const long long i = wbase + r * 32 + lane;
-    const bool ok = i < n;
-    const unsigned key = ok ? (FROM_IDX ? key_of_idx(idx, i, n_dst) : keys_in[i]) : 0xffffffffu;
-    const unsigned d = (key >> shift) & (ND - 1);
-    const unsigned act = __ballot_sync(0xffffffffu, ok);
-    const unsigned peers = peers_of(d, act);
-    const unsigned pos = mine[d] + __popc(peers & lt);
-    if (ok) {
-      keys_out[pos] = key;
-      vals_out[pos] = FROM_IDX ? (unsigned)i : vals_in[i];
+  // per digit: start of its run in the tile (scan over digits of the tile totals), exclusive
+  // prefix over warps, and where the run goes in the output (scan of hist)
+  {
+    const int d = threadIdx.x;
+    unsigned tot = 0;
+    if (d < ND) {
+#pragma unroll
+      for (int ww = 0; ww < RS_WARPS; ww++) tot += sh[ww * ND + d];
     }
-    __syncwarp();
-    if (ok && (peers & lt) == 0) mine[d] += __popc(peers);
-    __syncwarp();
+    unsigned all;
+    const unsigned lstart = block_excl_scan_u32(tot, &all, scan_sm);
+    if (d < ND) {
+      unsigned run = lstart;
+#pragma unroll
+      for (int ww = 0; ww < RS_WARPS; ww++) {
+        const unsigned c = sh[ww * ND + d];
+        sh[ww * ND + d] = run;
+        run += c;
+      }
+      gbase[d] = hist[(long long)d * nblocks + blockIdx.x] - lstart;  // mod 2^32: added back below
+    }
+  }
+  __syncthreads();
+  // pass 2: stable split of the tile in shared memory
+  for (int r0 = 0; r0 < RS_ROUNDS; r0 += LD) {
+    unsigned k[LD], v[LD];
+#pragma unroll
+    for (int q = 0; q < LD; q++) {
+      const long long i = wbase + (r0 + q) * 32 + lane;
+      k[q] = load_key(i);
+      v[q] = FROM_IDX ? (unsigned)i : (i < n ? vals_in[i] : 0u);
+    }
+#pragma unroll
+    for (int q = 0; q < LD; q++) {
+      const bool ok = wbase + (r0 + q) * 32 + lane < n;
+      const unsigned d = (k[q] >> shift) & (ND - 1);
+      const unsigned act = __ballot_sync(0xffffffffu, ok);
+      const unsigned peers = peers_of(d, act);
+      const unsigned pos = mine[d] + __popc(peers & lt);
+      if (ok) {
+        xk[pos] = k[q];
+        xv[pos] = v[q];
+      }
+      __syncwarp();
+      if (ok && (peers & lt) == 0) mine[d] += __popc(peers);
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // copy out: tile-local position j of digit d goes to gbase[d] + j
+  const long long left = n - tbase;
+  const int nvalid = left < RS_TILE ? (int)left : RS_TILE;
+#pragma unroll 4
+  for (int j = threadIdx.x; j < nvalid; j += RS_T) {
+    const unsigned key = xk[j];
+    const unsigned pos = gbase[(key >> shift) & (ND - 1)] + (unsigned)j;
+    keys_out[pos] = key;
+    vals_out[pos] = xv[j];
   }
 }
 
@@ -445,8 +489,17 @@ static int radix_pass(const unsigned* kin, const unsigned* vin, const int64_t* i
   return YOTA_OK;
 }
 
-// Sort (idx -> dest key, position) and build segment starts.  Results: *perm (source
-// positions grouped by destination, ascending inside a group), *seg (n_dst + 1 starts).
+// Where a finished sort left its results in the workspace: *perm (source positions grouped by
+// destination, ascending inside a group) and *seg (n_dst + 1 starts).
+static void sort_results(const SortPlan& sp, void* ws, const unsigned** perm, const unsigned** seg) {
+  char* base = static_cast<char*>(ws);
+  const int cur = (sp.passes - 1) & 1;  // pass 0 writes buffer 0, every later pass flips
+  *perm = reinterpret_cast<const unsigned*>(base + sp.off_vals[cur]);
+  *seg = reinterpret_cast<const unsigned*>(base + sp.off_seg);
+}
+
+// Sort (idx -> dest key, position) and build segment starts.  Depends on the index vector
+// only: a program may run it on a side stream long before the tangent it permutes exists.
 static int sort_by_destination(const int64_t* idx, long long n_src, long long n_dst, void* ws, const unsigned** perm,
                                const unsigned** seg, cudaStream_t s, long long* err, long long dst_lo = 0,
                                long long n_total = -1) {
@@ -482,8 +535,7 @@ static int sort_by_destination(const int64_t* idx, long long n_src, long long n_
   }
   seg_start_kernel<<<grid_for(n_src + 1, 256), 256, 0, s>>>(keys[cur], n_src, segp, n_dst);
   YOTA_CUDA(cudaGetLastError());
-  *perm = vals[cur];
-  *seg = segp;
+  sort_results(sp, ws, perm, seg);
   return YOTA_OK;
 }
 
@@ -551,13 +603,17 @@ __global__ void __launch_bounds__(256) scatter_fold_cols_kernel(typename FV<V>::
 
 int launch_scatter_add_cols(float* dx, long long rows, long long n_dst, const float* dy, const int64_t* idx,
                             long long n_src, void* workspace, size_t ws_bytes, cudaStream_t s, const float* scale,
-                            long long* err, long long dst_lo, long long n_total) {
+                            long long* err, long long dst_lo, long long n_total, int phase) {
   if (rows * n_dst == 0) return YOTA_OK;
   if (n_src >= (1ll << 32) - 1 || n_dst >= (1ll << 32) - 2)
     YOTA_FAIL(YOTA_E_SHAPE, "scatter-add: more than 2^32 sources/destinations are not supported");
   if (ws_bytes < scatter_cols_workspace_bytes(n_dst, n_src)) YOTA_FAIL(YOTA_E_ARG, "scatter-add: workspace too small");
   const unsigned *perm, *seg;
-  YOTA_TRY(sort_by_destination(idx, n_src, n_dst, workspace, &perm, &seg, s, err, dst_lo, n_total));
+  if (phase == UNGET_FOLD)
+    sort_results(sort_plan(n_dst, n_src), workspace, &perm, &seg);
+  else
+    YOTA_TRY(sort_by_destination(idx, n_src, n_dst, workspace, &perm, &seg, s, err, dst_lo, n_total));
+  if (phase == UNGET_SORT) return YOTA_OK;
   const bool v4 = (rows % 4 == 0) && ((reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(dy)) % 16 == 0);
   if (v4) {
     const int RV = (int)(rows / 4);
@@ -639,7 +695,7 @@ size_t ungetindex_workspace_bytes(const IndexSpec& sp) {
 }
 
 int launch_ungetindex(const IndexSpec& sp, float* dx, const float* dy, void* workspace, size_t ws_bytes, int sm_count,
-                      cudaStream_t s, const float* scale, long long* err) {
+                      cudaStream_t s, const float* scale, long long* err, int phase) {
   (void)sm_count;
   long long n_x = 1;
   for (int d = 0; d < sp.n; d++) n_x *= sp.xdims[d];
@@ -654,7 +710,7 @@ int launch_ungetindex(const IndexSpec& sp, float* dx, const float* dy, void* wor
   // fast path: dx[:, idx] += dy on a matrix
   if (sp.n == 2 && sp.kind[0] == YOTA_IDX_COLON && vec_dim == 1)
     return launch_scatter_add_cols(dx, sp.xdims[0], sp.xdims[1], dy, sp.vec[1], sp.vlen[1], workspace, ws_bytes, s,
-                                   scale, err);
+                                   scale, err, 0, -1, phase);
   if (scale) YOTA_FAIL(YOTA_E_ARG, "internal: scaled source planned for a general ungetindex");
   UngetParams p{};
   p.nd = sp.n;
@@ -683,9 +739,13 @@ int launch_ungetindex(const IndexSpec& sp, float* dx, const float* dy, void* wor
   }
   if (vec_dim >= 0) {
     if (ws_bytes < ungetindex_workspace_bytes(sp)) YOTA_FAIL(YOTA_E_ARG, "ungetindex: workspace too small");
-    YOTA_TRY(sort_by_destination(sp.vec[vec_dim], sp.vlen[vec_dim], sp.xdims[vec_dim], workspace, &p.perm, &p.seg, s,
-                                 err));
+    if (phase == UNGET_FOLD)
+      sort_results(sort_plan(sp.xdims[vec_dim], sp.vlen[vec_dim]), workspace, &p.perm, &p.seg);
+    else
+      YOTA_TRY(sort_by_destination(sp.vec[vec_dim], sp.vlen[vec_dim], sp.xdims[vec_dim], workspace, &p.perm, &p.seg,
+                                   s, err));
   }
+  if (phase == UNGET_SORT) return YOTA_OK;
   ungetindex_generic_kernel<<<grid_for(n_x, 256), 256, 0, s>>>(p, dx, dy, n_x);
   YOTA_CUDA(cudaGetLastError());
   return YOTA_OK;

@@ -110,6 +110,8 @@ struct Step {
   bool fused_away = false;  // finisher: performed by the last CTA of the kernel that wrote the partials
   int bsh_make = -1;      // fused-epilogue GEMM (BF16 mode): BF16 shadow it writes itself ...
   int bsh_make_out = -1;  // ... of this store output of the chain
+  int presort = -1;       // scatter-add whose index vector is an input/constant: its sort runs on the side
+                          // stream from the start of the run (index into presort_join), the step only folds
 };
 
 }  // namespace yota
@@ -158,6 +160,10 @@ struct yota_program {
   std::vector<Shadow> tshadows;  // transposed Float32 copies written by GEMM epilogues (TF32 mode)
   std::vector<int> allreduce_slots;
   std::vector<cudaEvent_t> ar_events;
+  int n_presort = 0;
+  int region_per_sm = 8;  // CTAs per SM the elementwise regions are sized for (fewer beside side-stream sorts)
+  cudaEvent_t presort_fork = nullptr;
+  std::vector<cudaEvent_t> presort_join;
   // where the caller-owned output buffers are touched, and which reductions follow which step
   // (plan_comm; rebuilt after yota_program_set_allreduce)
   struct CommPlan {
@@ -928,7 +934,7 @@ static int codegen_region(yota_program& P, int ri) {
   }
   p.n_slots = n_slots;
   if (n_slots > RG_MAX_SLOTS) YOTA_FAIL(YOTA_E_ARG, "internal: region %d needs %d slots", ri, n_slots);
-  region_geometry(r.L, P.ctx->sm_count);
+  region_geometry(r.L, P.ctx->sm_count, P.region_per_sm);
   r.sig = region_signature(p, r.L.V);
   if (!(P.flags & YOTA_FLAG_NO_STATIC)) r.L.static_id = static_chain_lookup(p, r.L.V);
   if (r.L.static_id >= 0) P.n_static++;
@@ -1196,6 +1202,13 @@ static int plan_memory(yota_program& P) {
   fl.end = P.const_bytes;
   // workspaces: allocated at their owner step, released after the finisher / same step
   std::vector<std::vector<std::pair<size_t, size_t>>> ws_frees(ns);
+  for (int s = 0; s < ns; s++) {  // sorted on the side stream from the start of the run: live from step 0
+    Step& st = P.steps[s];
+    if (st.kind == STEP_UNGETINDEX && st.ws_bytes > 0 && st.presort >= 0) {
+      st.ws_off = (long long)fl.alloc(st.ws_bytes);
+      ws_frees[s].push_back({(size_t)st.ws_off, st.ws_bytes});
+    }
+  }
   for (int s = 0; s < ns; s++) {
     Step& st = P.steps[s];
     for (auto& sh : P.shadows)
@@ -1212,7 +1225,7 @@ static int plan_memory(yota_program& P) {
         r.ws_off[n_store + q] = fs.ws_off;
         ws_frees[r.finish_steps[q]].push_back({(size_t)fs.ws_off, fs.ws_bytes});
       }
-    } else if (st.kind == STEP_UNGETINDEX && st.ws_bytes > 0) {
+    } else if (st.kind == STEP_UNGETINDEX && st.ws_bytes > 0 && st.presort < 0) {
       st.ws_off = (long long)fl.alloc(st.ws_bytes);
       ws_frees[s].push_back({(size_t)st.ws_off, st.ws_bytes});
     }
@@ -1831,6 +1844,19 @@ static int plan_gemm_epilogues(yota_program& P) {
   return YOTA_OK;
 }
 
+// The index vectors of this op exist before the first step (program inputs or constants), so the
+// sort of a scatter-add over them can start with the run.  YOTA_NO_PRESORT=1: keep it in the step.
+static bool index_vectors_early(const yota_program& P, const yota_op_desc& o, const IndexSpec& sp) {
+  static const bool off = getenv("YOTA_NO_PRESORT") != nullptr;
+  if (off) return false;
+  for (int d = 0; d < sp.n; d++)
+    if (sp.kind[d] == YOTA_IDX_VEC) {
+      const int k = P.T[o.in[1 + (int)sp.a[d]]].d.kind;
+      if (k != YOTA_T_INPUT && k != YOTA_T_CONST) return false;
+    }
+  return true;
+}
+
 static int finish_steps(yota_program& P) {
   for (size_t s = 0; s < P.steps.size(); s++) {
     Step& st = P.steps[s];
@@ -1846,12 +1872,16 @@ static int finish_steps(yota_program& P) {
       const TInfo& sel = st.kind == STEP_GETINDEX ? P.T[o.out] : P.T[o.in[0]];
       if (sel.numel != nsel && !(st.kind != STEP_GETINDEX && sel.numel == 1))
         YOTA_FAIL(YOTA_E_SHAPE, "%s: selection has %lld elements, tensor has %lld", opname(o.opcode), nsel, sel.numel);
-      if (st.kind == STEP_UNGETINDEX) st.ws_bytes = ungetindex_workspace_bytes(sp);
+      if (st.kind == STEP_UNGETINDEX) {
+        st.ws_bytes = ungetindex_workspace_bytes(sp);
+        if (st.ws_bytes > 0 && index_vectors_early(P, o, sp)) st.presort = P.n_presort++;
+      }
     }
     char buf[128];
     const TInfo& ot = P.T[o.out];
     snprintf(buf, sizeof(buf), " -> %%%d[%lld,%lld,%lld,%lld]", o.out, ot.dims[0], ot.dims[1], ot.dims[2], ot.dims[3]);
     st.label += buf;
+    if (st.presort >= 0) st.label += " (index sort on the side stream from the start of the run)";
   }
   return YOTA_OK;
 }
@@ -1946,6 +1976,24 @@ extern "C" int yota_program_build(yota_ctx* ctx, const yota_op_desc* ops, int64_
       set_error("an OUTPUT tensor has no producer");
       return fail(YOTA_E_ARG);
     }
+  // A scatter-add whose sort runs beside the forward sweep competes with the (persistent,
+  // slot-filling) elementwise regions for CTA slots.  Measured on C5: regions sized for 8 / 7 / 6
+  // CTAs per SM give 2.88 / 2.96 / 3.13 ms per eval (2.99 with the sort inside the step): the
+  // gather needs all its threads to cover HBM latency, so the default stays 8; the knob is for A/B.
+  for (size_t i = 0; i < P.ops.size(); i++) {
+    const yota_op_desc& o = P.ops[i];
+    if (!P.op_needed[i] || o.opcode != YOTA_OP_UNGETINDEX) continue;
+    IndexSpec sp;
+    long long nsel;
+    if (index_spec_of(P, o, P.T[o.out], sp, &nsel) != YOTA_OK) continue;  // reported by finish_steps
+    bool vec = false;
+    for (int d = 0; d < sp.n; d++) vec |= sp.kind[d] == YOTA_IDX_VEC;
+    if (vec && index_vectors_early(P, o, sp)) {
+      const char* e = getenv("YOTA_PRESORT_REGION_PER_SM");
+      P.region_per_sm = e && atoi(e) >= 1 && atoi(e) <= 8 ? atoi(e) : 8;
+      break;
+    }
+  }
   if ((st = plan_fusion(P))) return fail(st);
   for (size_t r = 0; r < P.regions.size(); r++)
     if ((st = codegen_region(P, (int)r))) return fail(st);
@@ -2047,6 +2095,8 @@ extern "C" int yota_program_destroy(yota_program* p) {
   for (auto& g : p->graphs)
     if (g.exec) cudaGraphExecDestroy(g.exec);
   for (auto e : p->ar_events) cudaEventDestroy(e);
+  if (p->presort_fork) cudaEventDestroy(p->presort_fork);
+  for (auto e : p->presort_join) cudaEventDestroy(e);
   free_adam_state(p);
   if (p->arena) cudaFree(p->arena);
   delete p;
@@ -2153,7 +2203,7 @@ static int run_gemm_epilogue(yota_program& P, Step& st, const GemmArgs& g_in, cu
   return launch_gemm_tc_epilogue(P.ctx, g, L.static_id, L.p, st.epi_z_in, s);
 }
 
-static int run_step(yota_program& P, Step& st, cudaStream_t s) {
+static int run_step(yota_program& P, Step& st, cudaStream_t s, int unget_phase = UNGET_ALL) {
   switch (st.kind) {
     case STEP_REGION: {
       Region& r = P.regions[st.region];
@@ -2276,7 +2326,7 @@ static int run_step(yota_program& P, Step& st, cudaStream_t s) {
       const float* scale =
           P.op_scale[st.op] >= 0 ? static_cast<const float*>(tensor_ptr(P, P.op_scale[st.op])) : nullptr;
       return launch_ungetindex(sp, out, in0, st.ws_off >= 0 ? P.arena + st.ws_off : nullptr, st.ws_bytes,
-                               P.ctx->sm_count, s, scale, P.ctx->err_dev);
+                               P.ctx->sm_count, s, scale, P.ctx->err_dev, unget_phase);
     }
     case STEP_LOGSOFTMAX: {
       const TInfo& x = P.T[o.in[0]];
@@ -2432,6 +2482,25 @@ static int run_all_steps(yota_program& P, cudaStream_t s, bool with_comm, Timeli
   const bool inherited = !ctx->pending_ar.empty();
   if (inherited)
     for (int i = 0; i < P.n_in; i++) YOTA_TRY(ctx_wait_pending(ctx, P.bound_in[i], (size_t)C.in_bytes[i], s));
+  // Sorts that need the index vectors only start now, beside the forward sweep (fork / join by
+  // events: inside a stream capture this becomes a parallel branch of the graph).
+  if (P.n_presort > 0) {
+    if (!P.presort_fork) YOTA_CUDA(cudaEventCreateWithFlags(&P.presort_fork, cudaEventDisableTiming));
+    while ((int)P.presort_join.size() < P.n_presort) {
+      cudaEvent_t e;
+      YOTA_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      P.presort_join.push_back(e);
+    }
+    YOTA_CUDA(cudaEventRecord(P.presort_fork, s));
+    YOTA_CUDA(cudaStreamWaitEvent(ctx->side_stream, P.presort_fork, 0));
+    for (Step& st : P.steps)
+      if (st.presort >= 0) {
+        if (tl) YOTA_TRY(tl->open("index sort for " + st.label, ctx->side_stream));
+        YOTA_TRY(run_step(P, st, ctx->side_stream, UNGET_SORT));
+        if (tl) YOTA_TRY(tl->close(ctx->side_stream));
+        YOTA_CUDA(cudaEventRecord(P.presort_join[st.presort], ctx->side_stream));
+      }
+  }
   int head_gemms = inherited && with_comm ? env_int_p("YOTA_AR_HEAD_RESERVE", 3) : 0;
   const int reserve = with_comm ? comm_reserved_sms(ctx) : 0;
   bool in_flight = false;
@@ -2454,7 +2523,8 @@ static int run_all_steps(yota_program& P, cudaStream_t s, bool with_comm, Timeli
     }
     const bool launches = st.kind != STEP_NOP && !st.fused_away;
     if (tl && launches) YOTA_TRY(tl->open(st.label, s));
-    YOTA_TRY(run_step(P, st, s));
+    if (st.presort >= 0) YOTA_CUDA(cudaStreamWaitEvent(s, P.presort_join[st.presort], 0));
+    YOTA_TRY(run_step(P, st, s, st.presort >= 0 ? UNGET_FOLD : UNGET_ALL));
     if (tl && launches) YOTA_TRY(tl->close(s));
     if (with_comm && !C.ar_at[q].empty()) {
       for (int slot : C.ar_at[q]) {
