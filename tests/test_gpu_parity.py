@@ -169,6 +169,30 @@ def test_c5_embedding_bit_exact():
         assert abs(val - ref) <= 1e-5 * abs(ref) + 1e-3
 
 
+@pytest.mark.parametrize("flags", [0, ffi.FLAG_NO_GRAPH])
+def test_index_sort_on_the_side_stream_follows_the_bound_indices(flags):
+    """The sort of a scatter-add runs beside the forward pass (side stream / parallel branch of the
+    graph).  Replaying ONE compiled program on new index vectors and tangents -- same buffers, new
+    contents, and other buffers -- must re-sort every run and stay bit-exact."""
+    rows, nt, ni = 64, 700, 9000
+    E, idx, V = cases.c5_args(rows, nt, ni)
+    dE_, dI_, dV_ = Y.cu(E), Y.cu(idx), Y.cu(V)
+    gf = Y.CompiledGrad(Y.gradtape(cases.c5_embed, dE_, dI_, dV_), Y.context(), flags)
+    assert "index sort on the side stream" in gf.describe()
+    r = cases.rng(33)
+    for it in range(6):
+        if it % 2:  # other buffers: the graph is re-bound
+            dI_, dV_ = Y.cu(idx), Y.cu(V)
+        else:  # same buffers, new contents
+            dI_.copy_from_host(idx)
+            dV_.copy_from_host(V)
+        val, g = gf(cases.c5_embed, dE_, dI_, dV_)
+        assert np.array_equal(U.bits(g[1].to_host()), U.bits(c_oracle.scatter_add_cols(V, idx, nt))), it
+        assert np.array_equal(U.bits(g[3].to_host()), U.bits(c_oracle.gather_cols(E, idx))), it
+        idx = r.integers(1, nt + 1, size=ni).astype(np.int64) if it != 3 else np.full(ni, 5, np.int64)
+        V = np.asfortranarray(r.standard_normal((rows, ni), dtype=F32))
+
+
 def test_scatter_negative_zero_and_empty_destinations():
     ctx = Y.context()
     dy = np.asfortranarray(np.array([[-0.0, 1.0, -0.0], [-0.0, -1.0, 2.0]], F32))
