@@ -13,7 +13,7 @@ import cases
 import gpu_util as U
 import yota_b200 as Y
 from oracle import yota_oracle as O
-from yota_b200 import ffi
+from yota_b200 import ffi, jl
 
 pytestmark = pytest.mark.gpu
 F32 = np.float32
@@ -228,3 +228,46 @@ def test_recurrence_epilogues_of_the_1cta_kernel(monkeypatch):
     v64, g64 = O.grad(f, *U.to_f64(list(args)), dtype=np.float64)
     for a, b in zip(g1, g64[1:]):
         assert np.max(np.abs(a - b)) <= 5e-3 * np.max(np.abs(b))
+
+
+@pytest.mark.parametrize("transposed", [False, True])
+def test_k_split_of_the_2cta_kernel(transposed, monkeypatch):
+    """Few 256 x 256 output tiles, long K (the batched dW of an unrolled recurrence): the planner
+    cuts K into slices that the 2-CTA kernel schedules like tiles; the partial tiles are summed in
+    slice order by a second launch.  Checked against the un-split plan (same operands, FP32 sums of
+    TF32 partial products either way), against the Float64 oracle at the TF32 gate, and for
+    run-to-run bit equality (fixed summation order)."""
+    r = cases.rng(77)
+    M, N, K = 512, 256, 8192
+    Cw = r.standard_normal((M, N)).astype(np.float32)
+    if transposed:  # dW = dZ * X' of the matmul rrule: both operands MN-major, K = the batch
+        W = r.standard_normal((M, N)).astype(np.float32) / 16
+        X = r.standard_normal((N, K)).astype(np.float32)
+        f = lambda W, X: jl.sum(jl.tanh(W @ X))
+        args = [W, X]
+    else:
+        A = r.standard_normal((M, K)).astype(np.float32) / 8
+        B = r.standard_normal((K, N)).astype(np.float32) / 8
+        f = lambda A, B, Cw: jl.sum((A @ B) * Cw)
+        args = [A, B, Cw]
+    d = [Y.cu(np.asfortranarray(a)) for a in args]
+    gf = Y.CompiledGrad(Y.gradtape(f, *d), flags=ffi.FLAG_GEMM_TF32)
+    assert "[K split in 4]" in gf.describe(), gf.describe()
+    v1, g1 = gf.run(d)
+    g1 = [x.to_host() for x in g1]
+    v1b, g1b = gf.run(d)
+    for a, b in zip(g1, g1b):
+        assert np.array_equal(U.bits(a), U.bits(b.to_host()))
+    monkeypatch.setenv("YOTA_GEMM_NO_KSPLIT", "1")
+    gu = Y.CompiledGrad(Y.gradtape(f, *d), flags=ffi.FLAG_GEMM_TF32)
+    assert "K split" not in gu.describe()
+    v2, g2 = gu.run(d)
+    assert abs(float(v1.to_host()) - float(v2.to_host())) <= 1e-5 * abs(float(v2.to_host())) + 1e-3
+    v64, g64 = O.grad(f, *U.to_f64(list(args)), dtype=np.float64)
+    assert abs(float(v1.to_host()) - v64) <= 5e-3 * np.sqrt(M * N) * 4
+    for a, b, b64 in zip(g1, g2, g64[1:]):
+        b = b.to_host()
+        # (not 1e-5: the tensor core's accumulator truncates, a bias that grows with the number of
+        # accumulations per slice -- 1.7e-4 of max|g| at K = 8192 x 3 products, see DESIGN.md 4.2)
+        assert np.max(np.abs(a - b)) <= 3e-4 * np.max(np.abs(b))
+        assert np.max(np.abs(a - b64)) <= 5e-3 * np.max(np.abs(b64))

@@ -177,6 +177,10 @@ def test_planner_c4_slices_are_views_and_accumulation_is_in_place(built, monkeyp
     desc, (steps, *_r) = _plan(cases.make_c4(16), *av)
     assert ": getindex ->" not in desc, "x[:, :, t] must be a view, not a copy"
     assert "unrolled loops: 5 " in desc and steps <= 4 * 16 + 8, desc  # batched: 2 GEMMs + 2 regions per step remain
+    # full size: the two batched dW contractions (1024 x 1024 x 16384: 16 tiles for 74 CTA pairs) are cut along K
+    av_full = [A((1024, 1024)), A((1024, 1024)), A((1024,)), A((1024, 128, 128))]
+    desc_full, _ = _plan(cases.make_c4(128), *av_full, flags=ffi.FLAG_GEMM_TF32)
+    assert desc_full.count("[K split in 4]") == 2, [l for l in desc_full.splitlines() if "K split" in l]
     # BF16 / 3xTF32 keep whole-array operand shadows: the loop stays unrolled there and the tape's
     # accumulation is done in place (GEMM C += ..., slice +=) -- also the plan with the pass disabled
     for flags, env in ((ffi.FLAG_GEMM_BF16, None), (0, "1")):

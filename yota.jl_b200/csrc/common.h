@@ -225,7 +225,20 @@ struct GemmArgs {
   // mode 3: Float32 shadows  x - tf32(x)  of both operands (same dims / leading dimensions)
   const void* A_lo = nullptr;
   const void* B_lo = nullptr;
+  // 1-CTA tcgen05 kernel: launch with programmatic stream serialisation (the grid is scheduled
+  // while the kernel before it in the stream drains; it waits for that kernel before it reads B,
+  // the epilogue operands or writes anything).  early_a: A is not written by that kernel, so its
+  // first tiles may be requested before the wait.
+  int pdl = 0;
+  int early_a = 0;
+  // few output tiles, long K (the batched dW of an unrolled recurrence): the 2-CTA kernel cuts K
+  // into `ksplit` slices (gemm_tc2_ksplit) whose partial tiles go to splitk_ws (ksplit * M * N
+  // floats) and are summed in slice order by a second launch.  0 / nullptr: no split.
+  int ksplit = 0;
+  void* splitk_ws = nullptr;
 };
+// K slices the 2-CTA kernel would use for this GEMM (0: no split); sizes the workspace at plan time
+int gemm_tc2_ksplit(const GemmArgs& g, int sm_count);
 int launch_gemm_ffma(const GemmArgs& g, cudaStream_t s);
 int launch_gemm_tc(yota_ctx* ctx, const GemmArgs& g, cudaStream_t s);  // returns YOTA_E_UNSUPPORTED_OP if shape not eligible
 bool gemm_tc_eligible(const GemmArgs& g);

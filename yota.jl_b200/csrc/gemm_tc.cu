@@ -144,6 +144,15 @@ __device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
 
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// Programmatic dependent launch: a kernel launched with programmatic stream serialisation may start
+// while its predecessor in the stream still runs.  griddep_wait() returns once the predecessor has
+// completed and its writes are visible (at once when there is no such dependency); nothing the
+// predecessor may have written is read, and nothing is written to global memory, before it.
+// griddep_launch() lets the NEXT kernel be scheduled early; it is only issued after this kernel's
+// own wait, so that a successor's pre-wait work can never overlap anything older than this kernel.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // 32 consecutive accumulator columns of this thread's TMEM lane (row) into registers
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -221,6 +230,14 @@ struct Params {
   float* rs_out;
   float rs_scale;
   unsigned* rs_cnt;
+  // 1-CTA kernel: operand A is not written by the kernel launched just before this one, so the A
+  // tiles of the first ring pass may be requested before the grid dependency resolves
+  int early_a;
+  // 2-CTA kernel, plain stores only: the K range is cut into `ksplit` slices that are scheduled like
+  // extra tiles (a 1024 x 1024 x 16384 contraction has 16 output tiles for 74 CTA pairs); slice i
+  // stores its partial tile into part + i * M * N and splitk_reduce_kernel adds the slices in order.
+  int ksplit;
+  float* part;
   // fused epilogue: store output `tsh_out` of the chain a second time, transposed (element (m, n)
   // at tsh[n + m * tsh_ld]): the K-major operand of the dW GEMM that would otherwise read this
   // tensor MN-major (see plan_transposed_shadows in program.cu)
@@ -489,43 +506,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     constexpr int NA = A_MN ? TM / E::CHUNK : 1;
     constexpr int NB = B_MN ? TN / E::CHUNK : 1;
     static_assert((X3 ? 2 : 1) * (NA + NB) <= 32, "one lane per TMA box");
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int t = tile0; t < num_tiles; t += tile_step) {
-      const int m0 = (t % p.num_m) * TM, n0 = (t / p.num_m) * TN;
-      for (int kb = 0; kb < nkb; kb++) {
-        if (lane == 0) {  // one poller per warp; the other lanes are released by the warp barrier
-          mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], S::STAGE_BYTES);
-        }
-        __syncwarp();
-        const int k0 = (kbeg + kb) * TK;
+    // issue the TMA boxes of operand A and / or B for k-block k0 into `stage`
+    auto issue = [&](int stage, int m0, int n0, int k0, bool do_a, bool do_b) {
 #pragma unroll
-        for (int part = 0; part < (X3 ? 2 : 1); part++) {  // part 1: the lo tiles of the compensated mode
-          unsigned char* sa = smem + stage * S::STAGE_BYTES + part * S::HALF;
-          unsigned char* sb = sa + S::A_BYTES;
-          const CUtensorMap* ma = part ? &map_al : &map_a;
-          const CUtensorMap* mb = part ? &map_bl : &map_b;
-          const int l0 = part * (NA + NB);
-          if (!p.spread) {
-            if (lane == 0) {
+      for (int part = 0; part < (X3 ? 2 : 1); part++) {  // part 1: the lo tiles of the compensated mode
+        unsigned char* sa = smem + stage * S::STAGE_BYTES + part * S::HALF;
+        unsigned char* sb = sa + S::A_BYTES;
+        const CUtensorMap* ma = part ? &map_al : &map_a;
+        const CUtensorMap* mb = part ? &map_bl : &map_b;
+        const int l0 = part * (NA + NB);
+        if (!p.spread) {
+          if (lane == 0) {
+            if (do_a) {
               if (A_MN) {
 #pragma unroll
                 for (int c = 0; c < NA; c++) tma_load_2d(sa + c * E::CHUNK_BYTES, ma, &full[stage], m0 + E::CHUNK * c, k0);
               } else
                 tma_load_2d(sa, ma, &full[stage], k0, m0);
+            }
+            if (do_b) {
               if (B_MN) {
 #pragma unroll
                 for (int c = 0; c < NB; c++) tma_load_2d(sb + c * E::CHUNK_BYTES, mb, &full[stage], n0 + E::CHUNK * c, k0);
               } else
                 tma_load_2d(sb, mb, &full[stage], k0, n0);
             }
-          } else if (lane >= l0 && lane < l0 + NA) {
+          }
+        } else if (lane >= l0 && lane < l0 + NA) {
+          if (do_a) {
             if (A_MN)
               tma_load_2d(sa + (lane - l0) * E::CHUNK_BYTES, ma, &full[stage], m0 + E::CHUNK * (lane - l0), k0);
             else
               tma_load_2d(sa, ma, &full[stage], k0, m0);
-          } else if (lane >= l0 + NA && lane < l0 + NA + NB) {
+          }
+        } else if (lane >= l0 + NA && lane < l0 + NA + NB) {
+          if (do_b) {
             const int c = lane - l0 - NA;
             if (B_MN)
               tma_load_2d(sb + c * E::CHUNK_BYTES, mb, &full[stage], n0 + E::CHUNK * c, k0);
@@ -533,6 +548,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               tma_load_2d(sb, mb, &full[stage], k0, n0);
           }
         }
+      }
+    };
+    // Before the grid dependency resolves: the A tiles of the first ring pass (the ring is empty,
+    // nothing to wait for), when A cannot have been written by the kernel still running.
+    int pre = 0;
+    if (p.early_a && tile0 < num_tiles) {
+      pre = nkb < S::NSTAGE ? nkb : S::NSTAGE;
+      const int m0 = (tile0 % p.num_m) * TM;
+      for (int kb = 0; kb < pre; kb++) {
+        if (lane == 0) mbar_expect_tx(&full[kb], S::STAGE_BYTES);
+        __syncwarp();
+        issue(kb, m0, 0, (kbeg + kb) * TK, true, false);
+      }
+    }
+    griddep_wait();
+    griddep_launch();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = tile0; t < num_tiles; t += tile_step) {
+      const int m0 = (t % p.num_m) * TM, n0 = (t / p.num_m) * TN;
+      for (int kb = 0; kb < nkb; kb++) {
+        const bool half = t == tile0 && kb < pre;  // A is already in flight, the barrier already armed
+        if (!half) {
+          if (lane == 0) {  // one poller per warp; the other lanes are released by the warp barrier
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_expect_tx(&full[stage], S::STAGE_BYTES);
+          }
+          __syncwarp();
+        }
+        issue(stage, m0, n0, (kbeg + kb) * TK, !half, true);
         if (++stage == S::NSTAGE) {
           stage = 0;
           phase ^= 1;
@@ -541,6 +586,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one elected lane) =====================
+    griddep_wait();
+    griddep_launch();
     if (lane == 0) {
       // instruction descriptor: D = F32, A = B = TF32 (2) or BF16 (1), majors, N >> 3, M >> 4
       constexpr uint32_t FMT = EB == 4 ? 2u : 1u;
@@ -598,6 +645,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else {
     // ===================== epilogue warps: TMEM -> registers -> global =====================
+    griddep_wait();  // epilogue operands and C itself may come from the kernel before this one
+    griddep_launch();
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -797,30 +846,36 @@ static int launch(const GemmArgs& g, const Maps& mp, int sm_count, cudaStream_t 
   p.rs_out = nullptr;
   p.rs_scale = 1.f;
   p.rs_cnt = nullptr;
+  p.early_a = g.pdl && g.early_a;
+  p.ksplit = 1;
+  p.part = nullptr;
   p.num_m = (int)(g.M / TM);
   p.num_n = (int)(g.N / TN);
   const int tiles = p.num_m * p.num_n;
   static const RegionParams no_rp{};
-  if constexpr (KS == 1) {
-    const int grid = tiles < sm_count ? tiles : sm_count;
-    kern<<<grid, THREADS, SMEM, s>>>(mp.a, mp.b, mp.al, mp.bl, p, rp ? *rp : no_rp);
-    YOTA_CUDA(cudaGetLastError());
-  } else {
-    const int clusters = tiles < sm_count / KS ? tiles : sm_count / KS;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(KS * (clusters < 1 ? 1 : clusters));
-    cfg.blockDim = dim3(THREADS);
-    cfg.dynamicSmemBytes = SMEM;
-    cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = KS;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    YOTA_CUDA(cudaLaunchKernelEx(&cfg, kern, mp.a, mp.b, mp.al, mp.bl, p, rp ? *rp : no_rp));
+  const int clusters = tiles < sm_count / KS ? tiles : sm_count / KS;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = KS == 1 ? dim3(tiles < sm_count ? tiles : sm_count) : dim3(KS * (clusters < 1 ? 1 : clusters));
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = SMEM;
+  cfg.stream = s;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  if (KS > 1) {
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = KS;
+    at[na].val.clusterDim.y = 1;
+    at[na].val.clusterDim.z = 1;
+    na++;
   }
+  if (g.pdl) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    na++;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = na;
+  YOTA_CUDA(cudaLaunchKernelEx(&cfg, kern, mp.a, mp.b, mp.al, mp.bl, p, rp ? *rp : no_rp));
   return YOTA_OK;
 }
 
@@ -946,8 +1001,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   const uint32_t lead = crank & ~1u;              // cluster rank of this pair's leader
   const bool leader = rank == 0;
   const int pair = blockIdx.x / (2 * MC), num_pairs = gridDim.x / (2 * MC);  // work units: MC tiles adjacent along N
-  const int num_tiles = p.num_m * (p.num_n / MC);
-  const int nkb = (int)(p.K / TK);
+  const int ksplit = (EPI < 0 && !X3) ? p.ksplit : 1;
+  const int base_tiles = p.num_m * (p.num_n / MC);
+  const int num_tiles = base_tiles * ksplit;  // K slices are scheduled like extra tiles
+  const int nkb = (int)(p.K / TK) / ksplit;
   const uint16_t mask_pair = (uint16_t)(3u << (2 * cpp)), mask_all = (uint16_t)((1u << (2 * mc)) - 1u);
   const uint16_t mask_same_rows = (uint16_t)((1u << rank) | (1u << (2 + rank)));  // MC = 2: this CTA and its twin
 
@@ -985,7 +1042,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     int stage = 0;
     uint32_t phase = 0;
     constexpr int NAI = NA / MC > 0 ? NA / MC : 1;  // A boxes this CTA issues itself (MN-major A: half the chunks)
-    for (int t = pair; t < num_tiles; t += num_pairs) {
+    for (int tk = pair; tk < num_tiles; tk += num_pairs) {
+      const int ks = tk / base_tiles, t = tk - ks * base_tiles;
       const int m0 = (t % p.num_m) * (2 * TM) + (int)rank * TM;
       const int n0 = ((t / p.num_m) * MC + (int)pp) * TN2 + (int)rank * TNH;
       for (int kb = 0; kb < nkb; kb++) {
@@ -997,7 +1055,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             mbar_arrive_remote(&full[stage], lead);
         }
         __syncwarp();
-        const int k0 = kb * TK;
+        const int k0 = (ks * nkb + kb) * TK;
 #pragma unroll
         for (int part = 0; part < (X3 ? 2 : 1); part++) {  // part 1: the lo tiles of the compensated mode
           unsigned char* sa = smem + stage * S::STAGE_BYTES + part * S::HALF;
@@ -1115,11 +1173,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     int acc = 0;
     uint32_t acc_phase = 0;
     const int kc = X3 ? p.kchunk : nkb;
-    for (int t = pair; t < num_tiles; t += num_pairs) {
+    for (int tk = pair; tk < num_tiles; tk += num_pairs) {
+      const int ks = tk / base_tiles, t = tk - ks * base_tiles;
       const long long m = (long long)(t % p.num_m) * (2 * TM) + (long long)rank * TM + q * 32 + lane;
       const long long tile_n = (long long)(t / p.num_m) * MC + pp;
       const long long n0 = tile_n * TN2;
-      float* crow = p.C + m + n0 * p.ldc;
+      const long long ldc = ksplit > 1 ? p.M : p.ldc;
+      float* crow = (ksplit > 1 ? p.part + (long long)ks * p.M * p.N : p.C) + m + n0 * ldc;
       using EP = Epilogue<(EPI >= 0 ? EPI : 0), ZIN>;
       float ebase[EP::NS], eaccs[EP::NO];
       if constexpr (EPI >= 0) EP::begin_tile(rp, m, n0, p.M, ebase, eaccs, num_tiles <= num_pairs);
@@ -1127,7 +1187,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const int kb0 = X3 ? ch * kc : 0;
       // X3: the tile arrives in chunks of k-blocks; every chunk but the first is added to the
       // partial sums in C, the fused chain runs on the complete sum (C + last chunk)
-      bool add_old = EPI < 0 && p.accumulate;
+      bool add_old = EPI < 0 && p.accumulate && ksplit == 1;
       bool last = true, red = false;
       if constexpr (X3) {
         last = kb0 + kc >= nkb;
@@ -1143,9 +1203,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         uint32_t v[32];
         float old[32];
         if (add_old) {  // see gemm_tc_kernel: old values of C in flight before the accumulator read
-          const float* cp0 = crow + (long long)(c * 32) * p.ldc;
+          const float* cp0 = crow + (long long)(c * 32) * ldc;
 #pragma unroll
-          for (int j = 0; j < 32; j++) old[j] = __ldcg(cp0 + j * p.ldc);
+          for (int j = 0; j < 32; j++) old[j] = __ldcg(cp0 + j * ldc);
         }
         const uint32_t taddr = tmem_base + (uint32_t)(acc * TN2 + c * 32) + ((uint32_t)(q * 32) << 16);
         tmem_ld32(taddr, v);
@@ -1159,17 +1219,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         reinterpret_cast<float4*>(smem + S::TSH_OFF) + q * 256, p.bsh, p.bsh_out);
           }
         } else {
-          float* cp = crow + (long long)(c * 32) * p.ldc;
+          float* cp = crow + (long long)(c * 32) * ldc;
           if (X3 && red) {
 #pragma unroll
-            for (int j = 0; j < 32; j++) atomicAdd(cp + j * p.ldc, __uint_as_float(v[j]));
+            for (int j = 0; j < 32; j++) atomicAdd(cp + j * ldc, __uint_as_float(v[j]));
             if (p.pace_ns) __nanosleep(p.pace_ns);
           } else if (add_old) {
 #pragma unroll
-            for (int j = 0; j < 32; j++) cp[j * p.ldc] = __uint_as_float(v[j]) + old[j];
+            for (int j = 0; j < 32; j++) cp[j * ldc] = __uint_as_float(v[j]) + old[j];
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; j++) cp[j * p.ldc] = __uint_as_float(v[j]);
+            for (int j = 0; j < 32; j++) cp[j * ldc] = __uint_as_float(v[j]);
           }
         }
       }
@@ -1247,9 +1307,12 @@ static int launch2_mc(const GemmArgs& g, const Maps& mp, int sm_count, cudaStrea
   p.rs_out = g.rs_out;
   p.rs_scale = g.rs_scale;
   p.rs_cnt = g.rs_cnt;
+  p.early_a = 0;
+  p.ksplit = (EPI < 0 && !X3 && g.ksplit > 1) ? g.ksplit : 1;
+  p.part = static_cast<float*>(g.splitk_ws);
   p.num_m = (int)(g.M / (2 * TM));
   p.num_n = (int)(g.N / TN2);
-  const int units = p.num_m * (p.num_n / MC);  // one unit = MC tiles adjacent along N = one cluster's work item
+  const int units = p.num_m * (p.num_n / MC) * p.ksplit;  // one unit = MC tiles adjacent along N = one cluster's work item
   int clusters = sm_count / (2 * MC);
   if (max_clusters > 0 && clusters > max_clusters) clusters = max_clusters;
   if (units < clusters) clusters = units;
@@ -1315,6 +1378,35 @@ bool gemm_tc2_eligible(const GemmArgs& g, int sm_count) {
   if (g.M % 256 || g.N % 256) return false;
   const long long tiles = (g.M / 256) * (g.N / 256);
   return getenv("YOTA_GEMM_FORCE_2CTA") ? tiles >= 1 : tiles >= sm_count / 4;
+}
+
+// Few 256 x 256 output tiles and a long K: cut K so that about 64 CTA pairs have work.  The
+// slices are summed in slice order afterwards -- deterministic, one more 4-byte pass over
+// ksplit + 1 copies of C, nothing next to the operand streams of such a contraction.
+int gemm_tc2_ksplit(const GemmArgs& g, int sm_count) {
+  if (g.mode != 1 || getenv("YOTA_GEMM_1CTA") || getenv("YOTA_GEMM_NO_KSPLIT")) return 0;
+  if (!gemm_tc_eligible(g) || g.M % 256 || g.N % 256 || g.ldc != g.M) return 0;
+  const long long tiles = (g.M / 256) * (g.N / 256);
+  if (tiles >= sm_count / 4) return 0;  // enough tiles for the plain 2-CTA schedule
+  int ks = 0;
+  for (int c = 2; c <= 8; c *= 2)
+    if (tiles * c <= sm_count / 2 && (g.K / 32) % c == 0 && g.K / c >= 2048) ks = c;
+  return ks;
+}
+
+__global__ void splitk_reduce_kernel(float4* __restrict__ C, const float4* __restrict__ part, long long n4, int ks,
+                                     int accumulate) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 a = accumulate ? C[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < ks; k++) {  // slice order: the same sum on every run
+      const float4 v = __ldcs(part + (long long)k * n4 + i);
+      a.x = __fadd_rn(a.x, v.x);
+      a.y = __fadd_rn(a.y, v.y);
+      a.z = __fadd_rn(a.z, v.z);
+      a.w = __fadd_rn(a.w, v.w);
+    }
+    C[i] = a;
+  }
 }
 
 // the accumulator may stand in for input 0 or 1 of the chain, if that input is a FULL operand
@@ -1445,6 +1537,22 @@ int launch_gemm_tc(yota_ctx* ctx, const GemmArgs& g, cudaStream_t s) {
   const bool B_MN = g.transB != 0;  // B stored N x K column-major: N contiguous
   const int eb = g.mode == 2 ? 2 : 4;
   tc::Maps mp;
+  if (g.splitk_ws && g.ksplit > 1 && g.ksplit == gemm_tc2_ksplit(g, ctx->sm_count)) {
+    int st;
+    if (A_MN && B_MN) st = tc::launch2<true, true, 4>(g, grid_sms(ctx), s);
+    else if (A_MN) st = tc::launch2<true, false, 4>(g, grid_sms(ctx), s);
+    else if (B_MN) st = tc::launch2<false, true, 4>(g, grid_sms(ctx), s);
+    else st = tc::launch2<false, false, 4>(g, grid_sms(ctx), s);
+    YOTA_TRY(st);
+    const long long n4 = g.M * g.N / 4;
+    long long blocks = (n4 + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<float4*>(g.C),
+                                                          static_cast<const float4*>(g.splitk_ws), n4, g.ksplit,
+                                                          g.accumulate);
+    YOTA_CUDA(cudaGetLastError());
+    return YOTA_OK;
+  }
   const bool two_cta = gemm_tc2_eligible(g, ctx->sm_count);
   if (two_cta) {
     // each CTA of a pair loads a 128-row box of A and a 128-column box of B

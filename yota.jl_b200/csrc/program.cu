@@ -110,6 +110,9 @@ struct Step {
   bool fused_away = false;  // finisher: performed by the last CTA of the kernel that wrote the partials
   int bsh_make = -1;      // fused-epilogue GEMM (BF16 mode): BF16 shadow it writes itself ...
   int bsh_make_out = -1;  // ... of this store output of the chain
+  int ksplit = 0;         // GEMM cut along K inside the 2-CTA kernel; partial tiles in the step's workspace
+  bool pdl = false;       // tcgen05 GEMM: launched with programmatic stream serialisation (plan_dependent_launch)
+  bool early_a = false;   // ... and operand A is not written by the launch before it
   int presort = -1;       // scatter-add whose index vector is an input/constant: its sort runs on the side
                           // stream from the start of the run (index into presort_join), the step only folds
 };
@@ -1160,6 +1163,57 @@ static int plan_transposed_shadows(yota_program& P) {
   return YOTA_OK;
 }
 
+// Back-to-back skinny GEMMs (the per-step products of an unrolled recurrence: 1024 x 128 x 1024,
+// ~9 us each, most of it launch latency, prologue and the first TMA round trip) are launched
+// with programmatic stream serialisation: the next grid is scheduled while this one drains, and
+// waits (griddepcontrol.wait) before it reads B, epilogue operands or writes anything.  Where the
+// launch just before does not write this GEMM's A operand (the recurrence weights), the first A
+// tiles are requested before that wait.  Only the 1-CTA kernel looks at these flags; every other
+// kernel is launched and ordered as before.  YOTA_NO_PDL=1 turns it off.
+// Contractions with few output tiles and a long K (the batched dW = dZ_all * H_all' of an unrolled
+// recurrence: 1024 x 1024 x 16384) are cut along K inside the 2-CTA kernel; the partial tiles need a
+// workspace for the duration of the step.
+static int plan_split_k(yota_program& P) {
+  if (gemm_mode_of(P.flags) != 1) return YOTA_OK;
+  for (Step& st : P.steps) {
+    if (st.kind != STEP_GEMM || st.epi_region >= 0) continue;
+    const yota_op_desc& o = P.ops[st.op];
+    GemmArgs g{};
+    g.mode = 1;
+    g.transA = (int)o.iattr[0];
+    g.transB = (int)o.iattr[1];
+    gemm_dims(P, o, &g.M, &g.N, &g.K, &g.lda, &g.ldb);
+    g.ldc = g.M;
+    if (st.tsh_use[0] >= 0) g.lda = g.K;  // (read from a K-major copy: does not change eligibility)
+    if (st.tsh_use[1] >= 0) g.ldb = g.K;
+    const int ks = gemm_tc2_ksplit(g, P.ctx->sm_count);
+    if (ks > 1) {
+      st.ksplit = ks;
+      st.ws_bytes = (size_t)ks * (size_t)g.M * (size_t)g.N * sizeof(float);
+      st.label += " [K split in " + std::to_string(ks) + "]";
+    }
+  }
+  return YOTA_OK;
+}
+
+static int plan_dependent_launch(yota_program& P) {
+  if (getenv("YOTA_NO_PDL") || gemm_mode_of(P.flags) != 1) return YOTA_OK;
+  int prev = -1;
+  for (size_t s = 0; s < P.steps.size(); s++) {
+    Step& st = P.steps[s];
+    if (st.kind == STEP_NOP || st.fused_away) continue;
+    if (st.kind == STEP_GEMM && prev >= 0) {
+      st.pdl = true;
+      const int a_root = root_of(P, P.ops[st.op].in[0]);
+      bool clean = st.tsh_use[0] < 0 || P.tshadows[st.tsh_use[0]].first_step != prev;
+      for (int t : P.steps[prev].writes) clean = clean && root_of(P, t) != a_root;
+      st.early_a = clean;
+    }
+    prev = (int)s;
+  }
+  return YOTA_OK;
+}
+
 static int plan_memory(yota_program& P) {
   const int ns = (int)P.steps.size();
   // constants first
@@ -1225,7 +1279,7 @@ static int plan_memory(yota_program& P) {
         r.ws_off[n_store + q] = fs.ws_off;
         ws_frees[r.finish_steps[q]].push_back({(size_t)fs.ws_off, fs.ws_bytes});
       }
-    } else if (st.kind == STEP_UNGETINDEX && st.ws_bytes > 0 && st.presort < 0) {
+    } else if ((st.kind == STEP_UNGETINDEX || st.kind == STEP_GEMM) && st.ws_bytes > 0 && st.presort < 0) {
       st.ws_off = (long long)fl.alloc(st.ws_bytes);
       ws_frees[s].push_back({(size_t)st.ws_off, st.ws_bytes});
     }
@@ -2002,10 +2056,12 @@ extern "C" int yota_program_build(yota_ctx* ctx, const yota_op_desc* ops, int64_
   if ((st = finish_steps(P))) return fail(st);
   if ((st = plan_bf16_shadows(P))) return fail(st);
   if ((st = plan_transposed_shadows(P))) return fail(st);
+  if ((st = plan_split_k(P))) return fail(st);
+  if ((st = plan_dependent_launch(P))) return fail(st);
   if ((st = plan_memory(P))) return fail(st);
   P.n_launches = 0;
   for (auto& s : P.steps)  // absorbed regions launch nothing; BF16 operand casts are launches of their GEMM step
-    P.n_launches += (s.kind == STEP_NOP || s.fused_away) ? 0 : (s.kind == STEP_UNGETINDEX ? 8 : 1) + (s.cast[0] ? 1 : 0) + (s.cast[1] ? 1 : 0);
+    P.n_launches += (s.kind == STEP_NOP || s.fused_away) ? 0 : (s.kind == STEP_UNGETINDEX ? 8 : 1) + (s.ksplit > 1 ? 1 : 0) + (s.cast[0] ? 1 : 0) + (s.cast[1] ? 1 : 0);
   *out = Pp;
   return YOTA_OK;
 }
@@ -2265,6 +2321,12 @@ static int run_step(yota_program& P, Step& st, cudaStream_t s, int unget_phase =
       g.ldc = g.M;
       g.accumulate = st.acc_tensor >= 0 ? 1 : 0;
       g.mode = gemm_mode_of(P.flags);
+      g.pdl = st.pdl;
+      g.early_a = st.early_a;
+      if (st.ksplit > 1 && st.ws_off >= 0) {
+        g.ksplit = st.ksplit;
+        g.splitk_ws = P.arena + st.ws_off;
+      }
       if ((g.mode == 2 || g.mode == 3) && st.shadow[0] >= 0) {
         void* sh[2];
         for (int j = 0; j < 2; j++) {
