@@ -271,3 +271,32 @@ def test_k_split_of_the_2cta_kernel(transposed, monkeypatch):
         # accumulations per slice -- 1.7e-4 of max|g| at K = 8192 x 3 products)
         assert np.max(np.abs(a - b)) <= 3e-4 * np.max(np.abs(b))
         assert np.max(np.abs(a - b64)) <= 5e-3 * np.max(np.abs(b64))
+
+
+@pytest.mark.parametrize("T,H,B", [(6, 256, 128), (9, 512, 128)])
+def test_recurrence_as_one_persistent_launch(T, H, B, monkeypatch):
+    """The per-step GEMM + epilogue launches of an unrolled recurrence run as ONE persistent kernel
+    (weights resident in shared memory, steps ordered by per-tile flags).  Same arithmetic on the
+    same accumulators as the step-by-step launches: bit-identical results, and fewer launches."""
+    f, args = cases.make_c4(T), cases.c4_args(H, B, T)
+    d = [Y.cu(a) for a in args]
+    gf = Y.CompiledGrad(Y.gradtape(f, *d), flags=ffi.FLAG_GEMM_TF32)
+    desc = gf.describe()
+    assert desc.count("one persistent launch]") == 2, desc
+    v1, g1 = gf.run(d)
+    g1 = [x.to_host() for x in g1]
+    n1 = gf.stats()["launches"]
+    v1b, g1b = gf.run(d)  # replay: the flags are reset inside the run
+    for a, b in zip(g1, g1b):
+        assert np.array_equal(U.bits(a), U.bits(b.to_host()))
+    monkeypatch.setenv("YOTA_NO_CHAIN", "1")
+    gu = Y.CompiledGrad(Y.gradtape(f, *d), flags=ffi.FLAG_GEMM_TF32)
+    assert "persistent launch" not in gu.describe()
+    v2, g2 = gu.run(d)
+    assert gu.stats()["launches"] >= n1 + (T - 3) + (T - 2) - 2, (n1, gu.stats())
+    assert U.bits(np.float32(v1.to_host())) == U.bits(np.float32(v2.to_host()))
+    for a, b in zip(g1, g2):
+        assert np.array_equal(U.bits(a), U.bits(b.to_host()))
+    v64, g64 = O.grad(f, *U.to_f64(list(args)), dtype=np.float64)
+    for a, b in zip(g1, g64[1:]):
+        assert np.max(np.abs(a - b)) <= 5e-3 * np.max(np.abs(b))

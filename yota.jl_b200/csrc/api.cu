@@ -104,7 +104,13 @@ int ctx_add_pending(yota_ctx* ctx, const std::vector<std::pair<const char*, cons
 }
 
 int ctx_check_index_errors(yota_ctx* ctx) {
-  if (!ctx->err_host || !*(volatile long long*)ctx->err_host) return YOTA_OK;
+  if (!ctx->err_host) return YOTA_OK;
+  if (*(volatile long long*)(ctx->err_host + 3)) {
+    memset(ctx->err_host, 0, 4 * sizeof(long long));
+    YOTA_FAIL(YOTA_E_CUDA, "internal: a persistent recurrence kernel gave up waiting for a tile of its previous step "
+                           "(the results of that run are invalid; YOTA_NO_CHAIN=1 launches the steps one by one)");
+  }
+  if (!*(volatile long long*)ctx->err_host) return YOTA_OK;
   const long long j = ctx->err_host[1], n = ctx->err_host[2];
   memset(ctx->err_host, 0, 4 * sizeof(long long));
   YOTA_FAIL(YOTA_E_SHAPE,

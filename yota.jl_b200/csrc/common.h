@@ -237,6 +237,10 @@ struct GemmArgs {
   int ksplit = 0;
   void* splitk_ws = nullptr;
 };
+// a whole recurrence of skinny GEMM + epilogue steps as one persistent launch (gemm_tc.cu); returns 1
+// when the steps have to be launched one by one
+int launch_gemm_chain(yota_ctx* ctx, const GemmArgs& g0, int static_id, const RegionParams& rp0, int z_in, int nsteps,
+                      long long b_delta, long long e_dcol, unsigned* flags, cudaStream_t s);
 // K slices the 2-CTA kernel would use for this GEMM (0: no split); sizes the workspace at plan time
 int gemm_tc2_ksplit(const GemmArgs& g, int sm_count);
 int launch_gemm_ffma(const GemmArgs& g, cudaStream_t s);

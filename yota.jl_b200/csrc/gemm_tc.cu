@@ -330,14 +330,19 @@ struct Epilogue {
   // operands of the chunk are loaded up front (32 independent loads in flight per operand) --
   // left per element, each load sits between the previous element's store and its own use and
   // the epilogue runs at one DRAM latency per element.
+  static constexpr int NI = N_IN > 0 ? N_IN : 1;
   __device__ __forceinline__ static void chunk32(const RegionParams& rp, const uint32_t (&z)[32], long long m,
                                                  long long n0, long long R, const float (&base)[NS], float (&accs)[NO],
                                                  float* tsh, long long tsh_ld, int tsh_out, float4* stage,
                                                  __nv_bfloat16* bsh, int bsh_out) {
-    const int lane = threadIdx.x & 31;
-    float tv[4];
-    constexpr int NI = N_IN > 0 ? N_IN : 1;
     float pre[NI][32];
+    load_operands(rp, m, n0, R, pre);
+    chunk32_with(rp, z, pre, m, n0, R, base, accs, tsh, tsh_ld, tsh_out, stage, bsh, bsh_out);
+  }
+  // the chunk's other operands (everything but the accumulator): independent of the GEMM, so a caller
+  // may request them before it waits for the accumulator (the persistent recurrence kernel does)
+  __device__ __forceinline__ static void load_operands(const RegionParams& rp, long long m, long long n0, long long R,
+                                                       float (&pre)[NI][32]) {
     static_for<N_IN>([&](auto k) {
       constexpr int K = decltype(k)::value, cls = YCE(in_cls, k);
       if constexpr (cls == CLS_FULL && K != Z_IN) {
@@ -352,6 +357,14 @@ struct Epilogue {
         for (int j = 0; j < 32; j++) pre[K][j] = __shfl_sync(0xffffffffu, mine, j);
       }
     });
+  }
+  __device__ __forceinline__ static void chunk32_with(const RegionParams& rp, const uint32_t (&z)[32],
+                                                      const float (&pre)[NI][32], long long m, long long n0, long long R,
+                                                      const float (&base)[NS], float (&accs)[NO], float* tsh,
+                                                      long long tsh_ld, int tsh_out, float4* stage, __nv_bfloat16* bsh,
+                                                      int bsh_out) {
+    const int lane = threadIdx.x & 31;
+    float tv[4];
 #pragma unroll
     for (int j = 0; j < 32; j++) {
       float v[NS];
@@ -749,6 +762,218 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   tcgen05_fence_before();
   __syncthreads();
   if constexpr (KS > 1) cluster_sync_all();  // the leader's shared memory outlives the others' DSMEM stores
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * TN) : "memory");
+  }
+}
+
+// =============================================================================================
+// Persistent recurrence: h_i = chain(A * h_{i-1}, operands_i) for i = 0 .. nsteps-1 in ONE launch.
+// The per-step products of an unrolled RNN (1024 x 128 x 1024, ~8 us per launch of the split-K
+// kernel above, most of it prologue, the A stream and the launch hand-over) repeat the same A
+// (the recurrence weights) on the previous step's output.  Here a cluster of KS = 4 CTAs owns
+// one 128 x 32 output tile for the whole recurrence: its K-slice of A is loaded into the smem
+// ring ONCE and stays there (K / KS <= 8 k-blocks), per step only the 32 KiB B slice moves.
+// Steps are ordered through global step counters, one per output tile: the leader publishes
+// flag[tile] = i + 1 (release) after its epilogue stored h_i; a producer whose K-slice covers rows
+// [r0, r1) of h_i polls the flags of the tiles holding those rows (acquire), then crosses into the
+// async proxy (fence.proxy.async) before the TMA loads.  All clusters are co-resident (the host
+// checks), nothing else on the device waits for this kernel while it spins.
+// Operands advance per step by whole columns: B tile column b_col0 + i * b_dcol of one tensor map
+// over the container of all h_i; the chain's FULL operands and stores by e_dcol columns (folded
+// into the column argument of the epilogue -- ROWVEC / SCALAR operands do not move).
+struct ChainParams {
+  int nsteps;
+  int b_col0, b_dcol;
+  long long e_dcol;
+  unsigned* flags;
+  long long* err;  // err[3] = 1: a flag did not arrive (reported by the next synchronising call)
+};
+
+// false: gave up (~1 s).  The results are garbage then, but nothing hangs: the caller stops waiting
+// for the rest of the recurrence and the next synchronising call reports the failure.
+__device__ __forceinline__ bool wait_step_flag(const unsigned* f, unsigned want, long long* err) {
+  for (int spin = 0; spin < (1 << 20); spin++) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+    if (v >= want) return true;
+    __nanosleep(20);
+  }
+  if (err) *(volatile long long*)(err + 3) = 1;
+  return false;
+}
+
+template <bool A_MN, int EPI, int ZIN>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_chain_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p,
+                  const ChainParams cp, const __grid_constant__ RegionParams rp) {
+  constexpr int TN = 32, KS = 4, EB = 4;
+  using S = Smem<TN, false>;
+  using E = El<EB>;
+  constexpr int TK = E::TK;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+  uint64_t* empty = full + S::NSTAGE;
+  uint64_t* tfull = empty + S::NSTAGE;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  static_assert(S::NSTAGE * 16 + 2 * 16 + 8 <= 176, "barriers fit");
+  uint64_t* pfull = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF + 176);
+  uint64_t* pempty = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF + 184);
+  float* part = reinterpret_cast<float*>(smem + S::BAR_OFF + 256);  // leader: [KS - 1][TN][128] partial sums
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t kr = cluster_ctarank();
+  const int tile = (int)blockIdx.x / KS;  // one tile per cluster for the whole recurrence
+  const int tm = tile % p.num_m, tn = tile / p.num_m;
+  const int nkb = (int)(p.K / TK) / KS;  // <= NSTAGE: k-block kb of this CTA lives in stage kb
+  const int kbeg = (int)kr * nkb;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S::NSTAGE; s++) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; a++) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 128);
+    }
+    mbar_init(pfull, (KS - 1) * 128);
+    mbar_init(pempty, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(2 * TN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      constexpr int NA = A_MN ? TM / E::CHUNK : 1;
+      const int m0 = tm * TM, n0 = tn * TN;
+      // output tiles of the previous step that hold rows [kbeg * TK, (kbeg + nkb) * TK) of B
+      const int t_lo = (kbeg * TK) / TM, t_hi = ((kbeg + nkb) * TK - 1) / TM;
+      bool alive = true;
+      for (int i = 0; i < cp.nsteps; i++) {
+        if (i > 0) {
+          for (int t = t_lo; t <= t_hi; t++)
+            if (alive) alive = wait_step_flag(cp.flags + tn * p.num_m + t, (unsigned)i, cp.err);
+          asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy stores of other SMs -> TMA reads
+        }
+        const int nb = cp.b_col0 + i * cp.b_dcol + n0;
+        for (int kb = 0; kb < nkb; kb++) {
+          mbar_wait(&empty[kb], (uint32_t)((i & 1) ^ 1));
+          unsigned char* sa = smem + kb * S::STAGE_BYTES;
+          const int k0 = (kbeg + kb) * TK;
+          if (i == 0) {  // A: once, resident for all steps
+            mbar_expect_tx(&full[kb], S::STAGE_BYTES);
+            if (A_MN) {
+#pragma unroll
+              for (int c = 0; c < NA; c++) tma_load_2d(sa + c * E::CHUNK_BYTES, &map_a, &full[kb], m0 + E::CHUNK * c, k0);
+            } else
+              tma_load_2d(sa, &map_a, &full[kb], k0, m0);
+          } else
+            mbar_expect_tx(&full[kb], S::B_BYTES);
+          tma_load_2d(sa + S::A_BYTES, &map_b, &full[kb], k0, nb);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((uint32_t)(TN >> 3) << 17) |
+                             ((uint32_t)(TM >> 4) << 24);
+      for (int i = 0; i < cp.nsteps; i++) {
+        const int acc = i & 1;
+        mbar_wait(&tempty[acc], (uint32_t)(((i >> 1) & 1) ^ 1));
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * TN;
+        for (int kb = 0; kb < nkb; kb++) {
+          mbar_wait(&full[kb], (uint32_t)(i & 1));
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + kb * S::STAGE_BYTES);
+          const uint32_t sb = sa + S::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const uint64_t da = A_MN ? make_desc(sa + k * E::MN_KSTEP, E::CHUNK_BYTES, E::MN_SBO, E::MN_LAYOUT)
+                                     : make_desc(sa + k * 32, 16, 1024, 2);
+            const uint64_t db = make_desc(sb + k * 32, 16, 1024, 2);
+            umma_tf32(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[kb]);  // B of this stage may be overwritten by the next step
+        }
+        umma_commit(&tfull[acc]);
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int q = warp & 3;
+    const long long m = (long long)tm * TM + q * 32 + lane;
+    for (int i = 0; i < cp.nsteps; i++) {
+      const int acc = i & 1;
+      const uint32_t acc_par = (uint32_t)((i >> 1) & 1), ppar = (uint32_t)(i & 1);
+      if (kr != 0) {
+        mbar_wait(pempty, ppar ^ 1);
+        mbar_wait(&tfull[acc], acc_par);
+        tcgen05_fence_after();
+        const uint32_t dst0 = map_to_cta(part, 0) + (uint32_t)((((kr - 1) * TN) * 128 + (q * 32 + lane)) * 4);
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + (uint32_t)(acc * TN) + ((uint32_t)(q * 32) << 16);
+        tmem_ld32(taddr, v);
+#pragma unroll
+        for (int j = 0; j < 32; j++) st_cluster_f32(dst0 + (uint32_t)(j * 128 * 4), __uint_as_float(v[j]));
+        tcgen05_fence_before();
+        mbar_arrive(&tempty[acc]);
+        mbar_arrive_remote_release(pfull, 0);
+        continue;
+      }
+      using EP = Epilogue<EPI, ZIN>;
+      float ebase[EP::NS], eaccs[EP::NO];
+      const long long n0 = (long long)tn * TN + (long long)i * cp.e_dcol;  // this step's columns of the containers
+      EP::begin_tile(rp, m, n0, p.M, ebase, eaccs, false);
+      float pre[EP::NI][32];
+      EP::load_operands(rp, m, n0, p.M, pre);  // in flight while this step's products are still being computed
+      mbar_wait(&tfull[acc], acc_par);
+      mbar_wait_acquire_cluster(pfull, ppar);
+      tcgen05_fence_after();
+      uint32_t v[32];
+      const uint32_t taddr = tmem_base + (uint32_t)(acc * TN) + ((uint32_t)(q * 32) << 16);
+      tmem_ld32(taddr, v);
+#pragma unroll
+      for (int r = 1; r < KS; r++) {  // + the other K-slices, in rank order
+        const float* pr = part + ((r - 1) * TN) * 128 + (q * 32 + lane);
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] = __float_as_uint(__fadd_rn(__uint_as_float(v[j]), pr[j * 128]));
+      }
+      tcgen05_fence_before();
+      mbar_arrive(&tempty[acc]);  // the accumulator and the partial sums are in registers
+#pragma unroll
+      for (int r = 1; r < KS; r++) mbar_arrive_remote(pempty, (uint32_t)r);
+      EP::chunk32_with(rp, v, pre, m, n0, p.M, ebase, eaccs, nullptr, 0, -1, nullptr, nullptr, -1);
+      // publish h_i: every thread's stores are ordered before the flag at device scope
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == EPI_WARP0 * 32)
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(cp.flags + tn * p.num_m + tm), "r"((unsigned)(i + 1)) : "memory");
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * TN) : "memory");
@@ -1497,6 +1722,98 @@ static int launch_epi1(const GemmArgs& g, const Maps& mp, int sm_count, cudaStre
   }
 }
 }  // namespace tc
+
+namespace tc {
+template <bool A_MN, int ID, int ZIN>
+static int launch_chain_t(const GemmArgs& g, const CUtensorMap& ma, const CUtensorMap& mb, const ChainParams& cp,
+                          const RegionParams& rp, cudaStream_t s) {
+  if constexpr (epi_z_ok<ID>(ZIN) && epi1_chain_stores_only<ID>()) {
+    static bool attr = false;
+    static int max_clusters = 0;
+    auto kern = gemm_chain_kernel<A_MN, ID, ZIN>;
+    constexpr int SMEM = Smem<32, false>::TOTAL + 3 * 32 * 128 * 4;
+    const int tiles = (int)((g.M / TM) * (g.N / 32));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(4 * tiles);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = SMEM;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 4;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    if (!attr) {
+      YOTA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess) max_clusters = n;
+      (void)cudaGetLastError();
+      attr = true;
+    }
+    if (tiles > max_clusters) return 1;  // the clusters spin on each other's flags: all must be resident
+    Params p{};
+    p.M = g.M;
+    p.N = g.N;
+    p.K = g.K;
+    p.C = g.C;
+    p.ldc = g.ldc;
+    p.kchunk = 1;
+    p.tsh_out = -1;
+    p.bsh_out = -1;
+    p.rs_scale = 1.f;
+    p.ksplit = 1;
+    p.num_m = (int)(g.M / TM);
+    p.num_n = (int)(g.N / 32);
+    YOTA_CUDA(cudaMemsetAsync(cp.flags, 0, (size_t)tiles * sizeof(unsigned), s));
+    YOTA_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, p, cp, rp));
+    return YOTA_OK;
+  } else {
+    return 1;
+  }
+}
+}  // namespace tc
+
+// The whole recurrence  out_i = chain(A * B_i, operands_i),  B_{i+1} = out_i,  i < nsteps, as one
+// persistent launch (tc::gemm_chain_kernel).  g0 / rp0: arguments of step 0; b_delta: floats from
+// B_i to B_{i+1}; e_dcol: columns from the chain's FULL operands / stores of step i to those of step
+// i + 1; flags: >= tiles zero-initialisable unsigneds owned by this chain.  Returns YOTA_OK when the
+// recurrence was launched, 1 when it cannot run this way (the caller launches the steps one by
+// one), a negative status on errors.
+int launch_gemm_chain(yota_ctx* ctx, const GemmArgs& g0, int static_id, const RegionParams& rp0, int z_in, int nsteps,
+                      long long b_delta, long long e_dcol, unsigned* flags, cudaStream_t s) {
+  if (getenv("YOTA_NO_CHAIN") || nsteps < 2 || g0.mode != 1 || g0.accumulate || g0.transB || g0.M != g0.K) return 1;
+  if (!gemm_epilogue1_chain_ok(g0, ctx->sm_count, static_id, z_in) || !use_splitk4(g0, ctx->sm_count)) return 1;
+  const long long nkb = g0.K / 32 / 4;
+  if (nkb > tc::Smem<32, false>::NSTAGE) return 1;  // the CTA's K-slice of A stays in the ring
+  if (b_delta % g0.ldb) return 1;
+  const long long b_dcol = b_delta / g0.ldb, span = (nsteps - 1) * (b_dcol < 0 ? -b_dcol : b_dcol);
+  if (g0.N + span > 0x7fffffff || e_dcol * (nsteps - 1) > 0x7fffffff || e_dcol * (nsteps - 1) < -0x7fffffff) return 1;
+  const float* b_base = static_cast<const float*>(g0.B) + (b_delta < 0 ? (nsteps - 1) * b_delta : 0);
+  if (reinterpret_cast<uintptr_t>(b_base) & 15) return 1;
+  const bool A_MN = !g0.transA;
+  CUtensorMap ma, mb;
+  YOTA_TRY(tc::make_map(&ma, g0.A, g0.M, g0.K, g0.lda, A_MN, tc::TM, 4));
+  YOTA_TRY(tc::make_map(&mb, b_base, g0.N + span, g0.K, g0.ldb, false, 32, 4));
+  tc::ChainParams cp{};
+  cp.nsteps = nsteps;
+  cp.b_col0 = (int)(b_delta < 0 ? span : 0);
+  cp.b_dcol = (int)b_dcol;
+  cp.e_dcol = e_dcol;
+  cp.flags = flags;
+  cp.err = ctx->err_dev;
+  switch (static_id) {
+#define X(ID)                                                                                           \
+  case ID:                                                                                              \
+    if (z_in == 0)                                                                                      \
+      return A_MN ? tc::launch_chain_t<true, ID, 0>(g0, ma, mb, cp, rp0, s) : tc::launch_chain_t<false, ID, 0>(g0, ma, mb, cp, rp0, s); \
+    return A_MN ? tc::launch_chain_t<true, ID, 1>(g0, ma, mb, cp, rp0, s) : tc::launch_chain_t<false, ID, 1>(g0, ma, mb, cp, rp0, s);
+    YOTA_EPI1_CHAIN_LIST(X)
+#undef X
+  }
+  return 1;
+}
 
 // GEMM whose output tile goes straight through the consumer region's micro-program
 int launch_gemm_tc_epilogue(yota_ctx* ctx, const GemmArgs& g, int static_id, const RegionParams& rp, int z_in,

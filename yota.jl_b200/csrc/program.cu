@@ -110,6 +110,9 @@ struct Step {
   bool fused_away = false;  // finisher: performed by the last CTA of the kernel that wrote the partials
   int bsh_make = -1;      // fused-epilogue GEMM (BF16 mode): BF16 shadow it writes itself ...
   int bsh_make_out = -1;  // ... of this store output of the chain
+  int chain_len = 0;      // head of a recurrence (plan_recurrence_chains): this many GEMM + epilogue steps
+  int chain_head = -1;    // member of a recurrence (the head too): index of its head step
+  int chain_id = -1;      // head: which slice of the flag area is this recurrence's
   int ksplit = 0;         // GEMM cut along K inside the 2-CTA kernel; partial tiles in the step's workspace
   bool pdl = false;       // tcgen05 GEMM: launched with programmatic stream serialisation (plan_dependent_launch)
   bool early_a = false;   // ... and operand A is not written by the launch before it
@@ -137,6 +140,10 @@ struct yota_program {
   std::vector<int> op_scale;  // UNGETINDEX ops: scalar tensor multiplied into the source on load (-1: none)
   int n_in = 0, n_out = 0;
   size_t arena_bytes = 0, const_bytes = 0;
+  size_t chain_flags_off = 0;  // step counters of the persistent recurrence launches: 256 bytes per recurrence
+  int n_chains = 0;
+  std::vector<int> chain_lens;    // steps of recurrence i ...
+  std::vector<char> chain_taken;  // ... and whether the last run launched it persistently (before any run: assumed)
   size_t counter_off = 0, counter_bytes = 0;  // arrival counters of in-kernel reduction finishers (zeroed once)
   std::vector<int> const_tensors;  // CONST / SEED tensors, in const-buffer order
   int n_launches = 0, n_static = 0;
@@ -1170,6 +1177,64 @@ static int plan_transposed_shadows(yota_program& P) {
 // launch just before does not write this GEMM's A operand (the recurrence weights), the first A
 // tiles are requested before that wait.  Only the 1-CTA kernel looks at these flags; every other
 // kernel is launched and ordered as before.  YOTA_NO_PDL=1 turns it off.
+// An unrolled recurrence  h_i = chain(W * h_{i-1}, ...)  shows up as a run of consecutive skinny
+// GEMM + epilogue steps of one shape and one chain whose B operand is the previous step's stored
+// output.  Such a run is marked here; at run time (try_run_chain) the bound addresses are checked
+// for constant strides and the whole run becomes ONE persistent launch (tc::gemm_chain_kernel:
+// weights resident in shared memory, steps ordered through per-tile flags) -- or, if anything
+// does not fit, the steps are launched one by one as before.  YOTA_NO_CHAIN=1 turns it off.
+static int plan_recurrence_chains(yota_program& P) {
+  if (getenv("YOTA_NO_CHAIN") || gemm_mode_of(P.flags) != 1) return YOTA_OK;
+  std::vector<int> L;
+  for (size_t s = 0; s < P.steps.size(); s++)
+    if (P.steps[s].kind != STEP_NOP && !P.steps[s].fused_away) L.push_back((int)s);
+  auto cand = [&](int s) {
+    const Step& st = P.steps[s];
+    return st.kind == STEP_GEMM && st.epi_region >= 0 && st.tsh_make < 0 && st.bsh_make < 0 && st.rs_finish < 0 &&
+           st.acc_tensor < 0 && st.shadow[0] < 0 && st.tsh_use[0] < 0 && st.tsh_use[1] < 0 &&
+           P.regions[st.epi_region].sums.empty() && P.regions[st.epi_region].L.static_id >= 0;
+  };
+  auto same = [&](int a, int b) {
+    const yota_op_desc &oa = P.ops[P.steps[a].op], &ob = P.ops[P.steps[b].op];
+    long long da[5], db[5];
+    gemm_dims(P, oa, &da[0], &da[1], &da[2], &da[3], &da[4]);
+    gemm_dims(P, ob, &db[0], &db[1], &db[2], &db[3], &db[4]);
+    for (int q = 0; q < 5; q++)
+      if (da[q] != db[q]) return false;
+    return oa.iattr[0] == ob.iattr[0] && oa.iattr[1] == ob.iattr[1] && P.steps[a].epi_z_in == P.steps[b].epi_z_in &&
+           P.regions[P.steps[a].epi_region].L.static_id == P.regions[P.steps[b].epi_region].L.static_id &&
+           root_of(P, oa.in[0]) == root_of(P, ob.in[0]) && alias_offset(P, oa.in[0]) == alias_offset(P, ob.in[0]);
+  };
+  auto feeds = [&](int a, int b) {  // B of step b is a stored output of step a's epilogue
+    const int bt = P.ops[P.steps[b].op].in[1];
+    for (int t : P.regions[P.steps[a].epi_region].out_tensors)
+      if (t == bt || (root_of(P, t) == root_of(P, bt) && alias_offset(P, t) == alias_offset(P, bt) &&
+                      P.T[t].numel == P.T[bt].numel))
+        return true;
+    return false;
+  };
+  for (size_t i = 0; i < L.size();) {
+    if (!cand(L[i])) {
+      i++;
+      continue;
+    }
+    size_t j = i + 1;
+    while (j < L.size() && cand(L[j]) && same(L[i], L[j]) && feeds(L[j - 1], L[j])) j++;
+    const int n = (int)(j - i);
+    if (n >= 4) {
+      Step& head = P.steps[L[i]];
+      head.chain_len = n;
+      head.chain_id = P.n_chains++;
+      P.chain_lens.push_back(n);
+      P.chain_taken.push_back(1);
+      head.label += " [recurrence of " + std::to_string(n) + " steps: one persistent launch]";
+      for (size_t q = i; q < j; q++) P.steps[L[q]].chain_head = L[i];
+    }
+    i = j;
+  }
+  return YOTA_OK;
+}
+
 // Contractions with few output tiles and a long K (the batched dW = dZ_all * H_all' of an unrolled
 // recurrence: 1024 x 1024 x 16384) are cut along K inside the 2-CTA kernel; the partial tiles need a
 // workspace for the duration of the step.
@@ -1226,6 +1291,8 @@ static int plan_memory(yota_program& P) {
     }
   P.counter_off = coff;
   coff += (P.counter_bytes + 255) & ~(size_t)255;
+  P.chain_flags_off = coff;
+  coff += (size_t)P.n_chains * 256;
   P.const_bytes = coff;
   // last use per root tensor
   for (int s = 0; s < ns; s++) {
@@ -2056,6 +2123,7 @@ extern "C" int yota_program_build(yota_ctx* ctx, const yota_op_desc* ops, int64_
   if ((st = finish_steps(P))) return fail(st);
   if ((st = plan_bf16_shadows(P))) return fail(st);
   if ((st = plan_transposed_shadows(P))) return fail(st);
+  if ((st = plan_recurrence_chains(P))) return fail(st);
   if ((st = plan_split_k(P))) return fail(st);
   if ((st = plan_dependent_launch(P))) return fail(st);
   if ((st = plan_memory(P))) return fail(st);
@@ -2129,7 +2197,11 @@ extern "C" int yota_program_stats(yota_program* p, int64_t* n_steps, int64_t* n_
                                   int64_t* n_fused_regions, int64_t* n_static_kernels) {
   if (!p) YOTA_FAIL(YOTA_E_ARG, "null program");
   if (n_steps) *n_steps = (int64_t)p->steps.size();
-  if (n_launches) *n_launches = p->n_launches;
+  if (n_launches) {
+    *n_launches = p->n_launches;
+    for (size_t c = 0; c < p->chain_lens.size(); c++)  // a recurrence launched persistently is one kernel
+      if (p->chain_taken[c]) *n_launches -= p->chain_lens[c] - 1;
+  }
   if (workspace_bytes) *workspace_bytes = (int64_t)p->arena_bytes;
   if (n_fused_regions) *n_fused_regions = (int64_t)p->regions.size();
   if (n_static_kernels) *n_static_kernels = p->n_static;
@@ -2257,6 +2329,98 @@ static int run_gemm_epilogue(yota_program& P, Step& st, const GemmArgs& g_in, cu
     L.p.out[q].ptr = q < n_store ? static_cast<float*>(tensor_ptr(P, r.out_tensors[q]))
                                  : reinterpret_cast<float*>(P.arena + r.ws_off[q]);
   return launch_gemm_tc_epilogue(P.ctx, g, L.static_id, L.p, st.epi_z_in, s);
+}
+
+// GemmArgs and bound region parameters of a GEMM + epilogue step in plain TF32 mode (no shadows)
+static void bind_epilogue_step(yota_program& P, const Step& st, GemmArgs& g, RegionLaunch& L) {
+  const yota_op_desc& o = P.ops[st.op];
+  g = GemmArgs{};
+  g.transA = (int)o.iattr[0];
+  g.transB = (int)o.iattr[1];
+  gemm_dims(P, o, &g.M, &g.N, &g.K, &g.lda, &g.ldb);
+  g.A = tensor_ptr(P, o.in[0]);
+  g.B = tensor_ptr(P, o.in[1]);
+  g.C = static_cast<float*>(tensor_ptr(P, o.out));
+  g.ldc = g.M;
+  g.mode = 1;
+  Region& r = P.regions[st.epi_region];
+  L = r.L;
+  L.p.in[st.epi_z_in].ptr = nullptr;
+  for (int q = 0; q < L.p.n_in; q++)
+    if (q != st.epi_z_in) L.p.in[q].ptr = static_cast<const float*>(tensor_ptr(P, r.in_tensors[q]));
+  for (int q = 0; q < L.p.n_out; q++) L.p.out[q].ptr = static_cast<float*>(tensor_ptr(P, r.out_tensors[q]));
+}
+
+// Head of a marked recurrence: verify on the bound addresses that the steps are one arithmetic
+// progression (A fixed; B, the chain's FULL operands and its stores advancing by constant strides;
+// B of step i + 1 = a store of step i; nothing a later step reads is written inside the run except
+// through B) and launch them as one persistent kernel.  Returns YOTA_OK (launched), 1 (launch the
+// steps one by one) or an error.
+static int try_run_chain(yota_program& P, int head, cudaStream_t s) {
+  const Step& hs = P.steps[head];
+  std::vector<int> mem;
+  for (size_t q = head; q < P.steps.size() && (int)mem.size() < hs.chain_len; q++)
+    if (P.steps[q].chain_head == head) mem.push_back((int)q);
+  const int n = (int)mem.size();
+  if (n != hs.chain_len || n < 2) return 1;
+  std::vector<GemmArgs> G(n);
+  std::vector<RegionLaunch> R(n);
+  for (int i = 0; i < n; i++) bind_epilogue_step(P, P.steps[mem[i]], G[i], R[i]);
+  const GemmArgs& g0 = G[0];
+  const RegionParams& r0 = R[0].p;
+  const int z = hs.epi_z_in;
+  const long long b_delta = static_cast<const float*>(G[1].B) - static_cast<const float*>(g0.B);
+  long long e_delta = 0;
+  bool have_e = false;
+  auto full_ptr_delta = [&](int i, long long d) {  // every moving operand moves by the same stride
+    if (!have_e) {
+      e_delta = d / (i > 0 ? i : 1);
+      have_e = true;
+    }
+    return d == e_delta * i;
+  };
+  for (int i = 1; i < n; i++) {
+    const GemmArgs& g = G[i];
+    const RegionParams& r = R[i].p;
+    if (g.A != g0.A || g.lda != g0.lda || g.ldb != g0.ldb || g.M != g0.M || g.N != g0.N || g.K != g0.K) return 1;
+    if (static_cast<const float*>(g.B) - static_cast<const float*>(g0.B) != b_delta * i) return 1;
+    if (r.n_in != r0.n_in || r.n_out != r0.n_out || r.n_ops != r0.n_ops) return 1;
+    for (int q = 0; q < r.n_ops; q++)
+      if (memcmp(&r.ops[q], &r0.ops[q], sizeof(MicroOp)) != 0) return 1;
+    for (int q = 0; q < r.n_in; q++) {
+      if (q == z) continue;
+      if (r.in[q].cls != r0.in[q].cls) return 1;
+      if (r.in[q].cls == CLS_FULL) {
+        if (!full_ptr_delta(i, r.in[q].ptr - r0.in[q].ptr)) return 1;
+      } else if (r.in[q].ptr != r0.in[q].ptr)
+        return 1;
+    }
+    for (int q = 0; q < r.n_out; q++)
+      if (!full_ptr_delta(i, r.out[q].ptr - r0.out[q].ptr)) return 1;
+    bool fed = false;  // B of this step is what the previous step stored
+    for (int q = 0; q < r.n_out; q++) fed = fed || R[i - 1].p.out[q].ptr == static_cast<const float*>(g.B);
+    if (!fed) return 1;
+  }
+  if (!have_e || e_delta % g0.M) return 1;
+  // the chain's other operands are read without waiting for anything: none of them may live in
+  // memory the run itself writes
+  const long long tile = g0.M * g0.N, span = e_delta * (n - 1);
+  for (int qo = 0; qo < r0.n_out; qo++) {
+    const float* o_lo = r0.out[qo].ptr + (span < 0 ? span : 0);
+    const float* o_hi = r0.out[qo].ptr + (span > 0 ? span : 0) + tile;
+    for (int q = 0; q < r0.n_in; q++) {
+      if (q == z) continue;
+      const bool moves = r0.in[q].cls == CLS_FULL;
+      const float* i_lo = r0.in[q].ptr + (moves && span < 0 ? span : 0);
+      const float* i_hi = r0.in[q].ptr + (moves && span > 0 ? span : 0) + (moves ? tile : g0.M);
+      if (i_lo < o_hi && o_lo < i_hi) return 1;
+    }
+    const float* a_lo = static_cast<const float*>(g0.A);
+    if (a_lo < o_hi && o_lo < a_lo + g0.M * g0.K) return 1;
+  }
+  unsigned* flags = reinterpret_cast<unsigned*>(P.arena + P.chain_flags_off + (size_t)hs.chain_id * 256);
+  if ((g0.M / 128) * (g0.N / 32) > 64) return 1;  // 256 bytes of flags per recurrence
+  return launch_gemm_chain(P.ctx, g0, R[0].static_id, r0, z, n, b_delta, e_delta / g0.M, flags, s);
 }
 
 static int run_step(yota_program& P, Step& st, cudaStream_t s, int unget_phase = UNGET_ALL) {
@@ -2566,6 +2730,7 @@ static int run_all_steps(yota_program& P, cudaStream_t s, bool with_comm, Timeli
   int head_gemms = inherited && with_comm ? env_int_p("YOTA_AR_HEAD_RESERVE", 3) : 0;
   const int reserve = with_comm ? comm_reserved_sms(ctx) : 0;
   bool in_flight = false;
+  int chain_done_until = -1;  // steps of a recurrence up to here were executed by their head's persistent launch
   size_t ev = 0;
   // Buckets: outputs finished by a step wait until at least kBucketBytes are pending (a
   // layer's 16 KiB bias gradient rides with the next weight gradient instead of paying a
@@ -2586,7 +2751,24 @@ static int run_all_steps(yota_program& P, cudaStream_t s, bool with_comm, Timeli
     const bool launches = st.kind != STEP_NOP && !st.fused_away;
     if (tl && launches) YOTA_TRY(tl->open(st.label, s));
     if (st.presort >= 0) YOTA_CUDA(cudaStreamWaitEvent(s, P.presort_join[st.presort], 0));
-    YOTA_TRY(run_step(P, st, s, st.presort >= 0 ? UNGET_FOLD : UNGET_ALL));
+    if (st.chain_len > 0) {  // head of a recurrence: one persistent launch for all its steps, if they line up
+      // (not when a member is where a bound output is first touched or all-reduced: those waits and
+      // launches are tied to the member's own place in the sweep)
+      bool plain = true;
+      int last = -1, seen = 0;
+      for (size_t e = q; e < P.steps.size() && seen < st.chain_len; e++)
+        if (P.steps[e].chain_head == (int)q) {
+          seen++;
+          last = (int)e;
+          plain = plain && C.first_touch_at[e].empty() && C.ar_at[e].empty();
+        }
+      const int taken = plain ? try_run_chain(P, (int)q, s) : 1;
+      if (taken < 0) return taken;
+      chain_done_until = taken == YOTA_OK ? last : -1;
+      P.chain_taken[st.chain_id] = taken == YOTA_OK;
+    }
+    if (!(st.chain_head >= 0 && (int)q <= chain_done_until))
+      YOTA_TRY(run_step(P, st, s, st.presort >= 0 ? UNGET_FOLD : UNGET_ALL));
     if (tl && launches) YOTA_TRY(tl->close(s));
     if (with_comm && !C.ar_at[q].empty()) {
       for (int slot : C.ar_at[q]) {
