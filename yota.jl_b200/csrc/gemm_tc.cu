@@ -775,9 +775,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // (the recurrence weights) on the previous step's output.  Here a cluster of KS = 4 CTAs owns
 // one 128 x 32 output tile for the whole recurrence: its K-slice of A is loaded into the smem
 // ring ONCE and stays there (K / KS <= 8 k-blocks), per step only the 32 KiB B slice moves.
-// Steps are ordered through global step counters, one per output tile: the leader publishes
-// flag[tile] = i + 1 (release) after its epilogue stored h_i; a producer whose K-slice covers rows
-// [r0, r1) of h_i polls the flags of the tiles holding those rows (acquire), then crosses into the
+// Steps are ordered through global counters, one per output tile: each of the leader's 128 epilogue
+// threads adds 1 (release) after it stored its part of h_i; a producer whose K-slice covers rows
+// [r0, r1) of h_i polls the counters of the tiles holding those rows (acquire) until they show
+// 128 (i + 1), then crosses into the
 // async proxy (fence.proxy.async) before the TMA loads.  All clusters are co-resident (the host
 // checks), nothing else on the device waits for this kernel while it spins.
 // Operands advance per step by whole columns: B tile column b_col0 + i * b_dcol of one tensor map
@@ -789,7 +790,18 @@ struct ChainParams {
   long long e_dcol;
   unsigned* flags;
   long long* err;  // err[3] = 1: a flag did not arrive (reported by the next synchronising call)
+  // diagnostics (YOTA_CHAIN_TRACE=1, tools/chain_trace.py): %globaltimer stamps of the cluster of tile 0,
+  // [step][8]: 0 flags seen, 1 B requested, 2 products done (leader), 3 products done (rank 1),
+  // 4 partial sums sent (rank 1), 5 partial sums in (leader), 6 stored, 7 published
+  unsigned long long* trace;
 };
+__device__ __forceinline__ void chain_stamp(const ChainParams& cp, int tile, int i, int what) {
+  if (cp.trace && tile == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    cp.trace[i * 8 + what] = t;
+  }
+}
 
 // false: gave up (~1 s).  The results are garbage then, but nothing hangs: the caller stops waiting
 // for the rest of the recurrence and the next synchronising call reports the failure.
@@ -861,36 +873,40 @@ gemm_chain_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      constexpr int NA = A_MN ? TM / E::CHUNK : 1;
-      const int m0 = tm * TM, n0 = tn * TN;
-      // output tiles of the previous step that hold rows [kbeg * TK, (kbeg + nkb) * TK) of B
-      const int t_lo = (kbeg * TK) / TM, t_hi = ((kbeg + nkb) * TK - 1) / TM;
-      bool alive = true;
-      for (int i = 0; i < cp.nsteps; i++) {
-        if (i > 0) {
-          for (int t = t_lo; t <= t_hi; t++)
-            if (alive) alive = wait_step_flag(cp.flags + tn * p.num_m + t, (unsigned)i, cp.err);
-          asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy stores of other SMs -> TMA reads
-        }
-        const int nb = cp.b_col0 + i * cp.b_dcol + n0;
-        for (int kb = 0; kb < nkb; kb++) {
-          mbar_wait(&empty[kb], (uint32_t)((i & 1) ^ 1));
-          unsigned char* sa = smem + kb * S::STAGE_BYTES;
-          const int k0 = (kbeg + kb) * TK;
-          if (i == 0) {  // A: once, resident for all steps
-            mbar_expect_tx(&full[kb], S::STAGE_BYTES);
-            if (A_MN) {
-#pragma unroll
-              for (int c = 0; c < NA; c++) tma_load_2d(sa + c * E::CHUNK_BYTES, &map_a, &full[kb], m0 + E::CHUNK * c, k0);
-            } else
-              tma_load_2d(sa, &map_a, &full[kb], k0, m0);
-          } else
-            mbar_expect_tx(&full[kb], S::B_BYTES);
-          tma_load_2d(sa + S::A_BYTES, &map_b, &full[kb], k0, nb);
-        }
+    // ===================== TMA producer: lane kb owns k-block kb =====================
+    // (one lane issuing all eight loads of a step took 0.77 us of the 7.4 us step; the two flags of
+    // a step are polled by two lanes at once)
+    constexpr int NA = A_MN ? TM / E::CHUNK : 1;
+    const int m0 = tm * TM, n0 = tn * TN;
+    // output tiles of the previous step that hold rows [kbeg * TK, (kbeg + nkb) * TK) of B
+    const int t_lo = (kbeg * TK) / TM, t_hi = ((kbeg + nkb) * TK - 1) / TM;
+    bool alive = true;
+    for (int i = 0; i < cp.nsteps; i++) {
+      if (i > 0) {
+        for (int t = t_lo + lane; t <= t_hi; t += 32)
+          if (alive) alive = wait_step_flag(cp.flags + tn * p.num_m + t, (unsigned)i * 128u, cp.err);
+        __syncwarp();
+        asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy stores of other SMs -> TMA reads
       }
+      if (kr == 0 && lane == 0) chain_stamp(cp, tile, i, 0);
+      const int nb = cp.b_col0 + i * cp.b_dcol + n0;
+      if (lane < nkb) {
+        const int kb = lane;
+        mbar_wait(&empty[kb], (uint32_t)((i & 1) ^ 1));
+        unsigned char* sa = smem + kb * S::STAGE_BYTES;
+        const int k0 = (kbeg + kb) * TK;
+        if (i == 0) {  // A: once, resident for all steps
+          mbar_expect_tx(&full[kb], S::STAGE_BYTES);
+          if (A_MN) {
+#pragma unroll
+            for (int c = 0; c < NA; c++) tma_load_2d(sa + c * E::CHUNK_BYTES, &map_a, &full[kb], m0 + E::CHUNK * c, k0);
+          } else
+            tma_load_2d(sa, &map_a, &full[kb], k0, m0);
+        } else
+          mbar_expect_tx(&full[kb], S::B_BYTES);
+        tma_load_2d(sa + S::A_BYTES, &map_b, &full[kb], k0, nb);
+      }
+      if (kr == 0 && lane == 0) chain_stamp(cp, tile, i, 1);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -930,6 +946,7 @@ gemm_chain_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         mbar_wait(pempty, ppar ^ 1);
         mbar_wait(&tfull[acc], acc_par);
         tcgen05_fence_after();
+        if (kr == 1 && threadIdx.x == EPI_WARP0 * 32) chain_stamp(cp, tile, i, 3);
         const uint32_t dst0 = map_to_cta(part, 0) + (uint32_t)((((kr - 1) * TN) * 128 + (q * 32 + lane)) * 4);
         uint32_t v[32];
         const uint32_t taddr = tmem_base + (uint32_t)(acc * TN) + ((uint32_t)(q * 32) << 16);
@@ -939,6 +956,7 @@ gemm_chain_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         tcgen05_fence_before();
         mbar_arrive(&tempty[acc]);
         mbar_arrive_remote_release(pfull, 0);
+        if (kr == 1 && threadIdx.x == EPI_WARP0 * 32) chain_stamp(cp, tile, i, 4);
         continue;
       }
       using EP = Epilogue<EPI, ZIN>;
@@ -948,8 +966,10 @@ gemm_chain_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       float pre[EP::NI][32];
       EP::load_operands(rp, m, n0, p.M, pre);  // in flight while this step's products are still being computed
       mbar_wait(&tfull[acc], acc_par);
+      if (threadIdx.x == EPI_WARP0 * 32) chain_stamp(cp, tile, i, 2);
       mbar_wait_acquire_cluster(pfull, ppar);
       tcgen05_fence_after();
+      if (threadIdx.x == EPI_WARP0 * 32) chain_stamp(cp, tile, i, 5);
       uint32_t v[32];
       const uint32_t taddr = tmem_base + (uint32_t)(acc * TN) + ((uint32_t)(q * 32) << 16);
       tmem_ld32(taddr, v);
@@ -964,11 +984,11 @@ gemm_chain_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
       for (int r = 1; r < KS; r++) mbar_arrive_remote(pempty, (uint32_t)r);
       EP::chunk32_with(rp, v, pre, m, n0, p.M, ebase, eaccs, nullptr, 0, -1, nullptr, nullptr, -1);
-      // publish h_i: every thread's stores are ordered before the flag at device scope
-      __threadfence();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (threadIdx.x == EPI_WARP0 * 32)
-        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(cp.flags + tn * p.num_m + tm), "r"((unsigned)(i + 1)) : "memory");
+      // publish h_i: each of the 128 threads counts itself in once ITS stores are visible at device
+      // scope (release) -- no fence + barrier + single store in series; step i is complete at 128 (i + 1)
+      if (threadIdx.x == EPI_WARP0 * 32) chain_stamp(cp, tile, i, 6);
+      asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(cp.flags + tn * p.num_m + tm), "r"(1u) : "memory");
+      if (threadIdx.x == EPI_WARP0 * 32) chain_stamp(cp, tile, i, 7);
     }
   }
   tcgen05_fence_before();
@@ -1775,6 +1795,23 @@ static int launch_chain_t(const GemmArgs& g, const CUtensorMap& ma, const CUtens
 }
 }  // namespace tc
 
+// YOTA_CHAIN_TRACE=1: device buffer for the time stamps of the last persistent recurrence launched
+static unsigned long long* g_chain_trace = nullptr;
+static int g_chain_trace_steps = 0;
+static unsigned long long* chain_trace_buffer(int nsteps) {
+  if (!getenv("YOTA_CHAIN_TRACE") || nsteps > 4096) return nullptr;
+  if (!g_chain_trace && cudaMalloc(&g_chain_trace, 4096 * 8 * sizeof(unsigned long long)) != cudaSuccess) return nullptr;
+  g_chain_trace_steps = nsteps;
+  return g_chain_trace;
+}
+// diagnostic export (not part of include/yota_cuda.h): copies the stamps of the last traced recurrence
+extern "C" int yota_debug_chain_trace(unsigned long long* out, int cap_steps) {
+  if (!g_chain_trace) return 0;
+  const int n = g_chain_trace_steps < cap_steps ? g_chain_trace_steps : cap_steps;
+  if (cudaMemcpy(out, g_chain_trace, (size_t)n * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return n;
+}
+
 // The whole recurrence  out_i = chain(A * B_i, operands_i),  B_{i+1} = out_i,  i < nsteps, as one
 // persistent launch (tc::gemm_chain_kernel).  g0 / rp0: arguments of step 0; b_delta: floats from
 // B_i to B_{i+1}; e_dcol: columns from the chain's FULL operands / stores of step i to those of step
@@ -1803,6 +1840,7 @@ int launch_gemm_chain(yota_ctx* ctx, const GemmArgs& g0, int static_id, const Re
   cp.e_dcol = e_dcol;
   cp.flags = flags;
   cp.err = ctx->err_dev;
+  cp.trace = chain_trace_buffer(nsteps);
   switch (static_id) {
 #define X(ID)                                                                                           \
   case ID:                                                                                              \
