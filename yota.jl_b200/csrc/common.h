@@ -268,6 +268,7 @@ struct IndexSpec {
 int launch_getindex(const IndexSpec& sp, float* y, const float* x, long long n_out, cudaStream_t s,
                     long long* err = nullptr);
 size_t ungetindex_workspace_bytes(const IndexSpec& sp);
+int ungetindex_launch_count(const IndexSpec& sp);
 // A scatter-add is a sort of the index vector (needs nothing else) followed by the ordered fold of
 // dy: UNGET_SORT / UNGET_FOLD run the halves separately on the same workspace, UNGET_ALL both.
 enum { UNGET_ALL = 0, UNGET_SORT = 1, UNGET_FOLD = 2 };

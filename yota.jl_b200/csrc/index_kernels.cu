@@ -688,6 +688,27 @@ __global__ void ungetindex_generic_kernel(UngetParams p, float* __restrict__ dx,
   }
 }
 
+// kernels one ungetindex launches (the program's launch count is part of what the bench reports)
+int ungetindex_launch_count(const IndexSpec& sp) {
+  for (int d = 0; d < sp.n; d++)
+    if (sp.kind[d] == YOTA_IDX_VEC) {
+      const SortPlan pl = sort_plan(sp.xdims[d], sp.vlen[d]);
+      long long n = ((long long)1 << pl.bits) * pl.nblocks;
+      int scan = 0;  // exclusive_scan_u32: one kernel for a single tile, else tile + recursion + add
+      for (;;) {
+        const long long nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+        if (nb == 1) {
+          scan += 1;
+          break;
+        }
+        scan += 2;
+        n = nb;
+      }
+      return pl.passes * (2 + scan) + 2;  // per pass: histogram, scan, split; then segment starts and the fold
+    }
+  return 1;
+}
+
 size_t ungetindex_workspace_bytes(const IndexSpec& sp) {
   for (int d = 0; d < sp.n; d++)
     if (sp.kind[d] == YOTA_IDX_VEC) return scatter_cols_workspace_bytes(sp.xdims[d], sp.vlen[d]);

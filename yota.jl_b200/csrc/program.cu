@@ -110,6 +110,7 @@ struct Step {
   bool fused_away = false;  // finisher: performed by the last CTA of the kernel that wrote the partials
   int bsh_make = -1;      // fused-epilogue GEMM (BF16 mode): BF16 shadow it writes itself ...
   int bsh_make_out = -1;  // ... of this store output of the chain
+  int unget_launches = 1; // kernels of an ungetindex step (sort passes + fold)
   int chain_len = 0;      // head of a recurrence (plan_recurrence_chains): this many GEMM + epilogue steps
   int chain_head = -1;    // member of a recurrence (the head too): index of its head step
   int chain_id = -1;      // head: which slice of the flag area is this recurrence's
@@ -1995,6 +1996,7 @@ static int finish_steps(yota_program& P) {
         YOTA_FAIL(YOTA_E_SHAPE, "%s: selection has %lld elements, tensor has %lld", opname(o.opcode), nsel, sel.numel);
       if (st.kind == STEP_UNGETINDEX) {
         st.ws_bytes = ungetindex_workspace_bytes(sp);
+        st.unget_launches = ungetindex_launch_count(sp);
         if (st.ws_bytes > 0 && index_vectors_early(P, o, sp)) st.presort = P.n_presort++;
       }
     }
@@ -2129,7 +2131,7 @@ extern "C" int yota_program_build(yota_ctx* ctx, const yota_op_desc* ops, int64_
   if ((st = plan_memory(P))) return fail(st);
   P.n_launches = 0;
   for (auto& s : P.steps)  // absorbed regions launch nothing; BF16 operand casts are launches of their GEMM step
-    P.n_launches += (s.kind == STEP_NOP || s.fused_away) ? 0 : (s.kind == STEP_UNGETINDEX ? 8 : 1) + (s.ksplit > 1 ? 1 : 0) + (s.cast[0] ? 1 : 0) + (s.cast[1] ? 1 : 0);
+    P.n_launches += (s.kind == STEP_NOP || s.fused_away) ? 0 : (s.kind == STEP_UNGETINDEX ? s.unget_launches : 1) + (s.ksplit > 1 ? 1 : 0) + (s.cast[0] ? 1 : 0) + (s.cast[1] ? 1 : 0);
   *out = Pp;
   return YOTA_OK;
 }
