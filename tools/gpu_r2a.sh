@@ -8,3 +8,8 @@ grep -E "passed|failed|FAILED|ERROR" gpurun_out/pytest_gpu.log | tail -20
 timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo "bench default rc=$?"
 tail -c 5500 gpurun_out/bench_default.json; tail -5 gpurun_out/bench_default.err
 timeout 400 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "bench reference rc=$?"; cut -c1-700 gpurun_out/bench_reference.json
+for w in c4 c1; do
+  timeout 300 python bench.py --workload $w --steps 30 --warmup 5 --no-other-modes --no-cpu-baseline --no-secondary > gpurun_out/bench_$w.json 2> gpurun_out/bench_$w.err; echo "bench $w rc=$?"
+  python -c "
+import json;d=json.loads(open('gpurun_out/bench_$w.json').read().strip().splitlines()[-1]);print(d['value'],d['ms_per_step'],d['e2e']['value'],d['gpu_launches'],d.get('roofline',{}).get('frac'))"
+done
