@@ -425,7 +425,8 @@ def main():
     for i in bidx:
         p = C.c_void_p()
         ffi.check(lib.yota_host_alloc(ctx.h, hargs[i].nbytes, C.byref(p)))
-        C.memmove(p, np.asfortranarray(hargs[i]).ctypes.data, hargs[i].nbytes)
+        hcol = np.asfortranarray(hargs[i])  # (named: a temporary would be freed before memmove reads it)
+        C.memmove(p, hcol.ctypes.data, hcol.nbytes)
         pinned.append((i, p, hargs[i].nbytes))
         h2d += hargs[i].nbytes
     # the loss of every step is read back into pinned host memory by an asynchronous copy ordered

@@ -167,6 +167,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// ... 16 columns (the compensated mode's drain keeps 128 running sums per thread: a 32-column piece
+// next to them does not fit in the 168 registers a thread of a 10-warp CTA gets)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -1049,13 +1061,15 @@ static int make_map(CUtensorMap* map, const void* ptr, long long mn, long long k
   return YOTA_OK;
 }
 
-// k-blocks (of 32 K-elements) per accumulation chunk of the compensated mode: 4 = 128 K-elements
-// = 48 truncating accumulations per chunk (YOTA_X3_KCHUNK overrides, in k-blocks).  Measured on
-// B200, C3 at full size against the Float64 oracle: 8 k-blocks 1.17e-5 of max|g| at 28 evals/s
-// (just over the 1e-5 gate), 4 k-blocks 7.0e-6 at 25 evals/s, 2 k-blocks 4.5e-6 at 18.6 evals/s.
-static int x3_kchunk() {
+// k-blocks (of 32 K-elements) per accumulation chunk of the compensated mode (YOTA_X3_KCHUNK
+// overrides).  Measured on B200, C3 at full size against the Float64 oracle, worst error / max|g|:
+//   1-CTA kernel (chunks added to C by the L2, red.global.add.f32: every chunk is a pass over C):
+//     8 k-blocks 1.17e-5 (just over the 1e-5 gate), 4 k-blocks 7.0e-6, 2 k-blocks 4.5e-6 -- default 4;
+//   2-CTA kernel (chunks summed in registers, free): 4 k-blocks 7.0e-6 at 35.2 evals/s, 2 k-blocks
+//     4.5e-6 at 34.7, 1 k-block 3.5e-6 at 34.9 -- default 1.
+static int x3_kchunk(int dflt) {
   const char* e = getenv("YOTA_X3_KCHUNK");
-  const int v = e && *e ? atoi(e) : 4;
+  const int v = e && *e ? atoi(e) : dflt;
   return v < 1 ? 1 : v;
 }
 
@@ -1081,7 +1095,7 @@ static int launch(const GemmArgs& g, const Maps& mp, int sm_count, cudaStream_t 
   p.ldc = g.ldc;
   p.accumulate = g.accumulate;
   p.spread = getenv("YOTA_TMA_SPREAD") ? 1 : 0;
-  p.kchunk = x3_kchunk();
+  p.kchunk = x3_kchunk(4);
   p.pace_ns = getenv("YOTA_X3_PACE_NS") ? atoi(getenv("YOTA_X3_PACE_NS")) : 0;
   p.tsh = nullptr;
   p.tsh_ld = 0;
@@ -1211,8 +1225,14 @@ __device__ __forceinline__ void umma_2sm(uint32_t d_tmem, uint64_t a_desc, uint6
 // (64 KiB per 4.2 MFLOP) is what bounds the kernel once the batch per GPU is small (N = 1024:
 // 520 TFLOP/s at 7.8 TB/s of L2 reads).  An smem stage is then written by TMA loads of BOTH
 // pairs, so empty[s] collects the commits of both pairs' MMA issuers (count MC).
+// Compensated mode: EIGHT epilogue warps (two per TMEM lane quarter, 128 columns each), because the
+// chunks of a tile are summed in REGISTERS -- 128 running sums per thread -- instead of being added
+// to C by the L2 (red.global.add.f32): at one chunk per 128 K-elements that was K / 128 read-modify-
+// write passes over C per GEMM (8.6 GB of L2 atomics for 8192 x 8192 x 4096: the kernel was bound by
+// them, 1.7 ms where three TF32 passes take 1.3).
+constexpr int THREADS_X3 = 320;
 template <bool A_MN, bool B_MN, int EB, int EPI, int ZIN, bool X3, int MC>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(X3 ? THREADS_X3 : THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                 const __grid_constant__ CUtensorMap map_al, const __grid_constant__ CUtensorMap map_bl, const Params p,
                 const __grid_constant__ RegionParams rp) {
@@ -1260,7 +1280,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
     for (int a = 0; a < 2; a++) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 256);
+      mbar_init(&tempty[a], X3 ? 2 * (THREADS_X3 - 64) : 256);  // the epilogue threads of both CTAs
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -1412,12 +1432,88 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         }
       }
     }
+  } else if constexpr (X3) {
+    // ===================== epilogue warps, compensated mode: chunk sums in registers =====================
+    const int q = warp & 3;                // TMEM lane quarter this warp may access
+    const int hc = (warp - EPI_WARP0) >> 2;  // which 128 of the tile's 256 columns
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int kc = p.kchunk, nch = (nkb + kc - 1) / kc;
+    for (int t = pair; t < num_tiles; t += num_pairs) {
+      const long long m = (long long)(t % p.num_m) * (2 * TM) + (long long)rank * TM + q * 32 + lane;
+      const long long tile_n = (long long)(t / p.num_m) * MC + pp;
+      const long long n0 = tile_n * TN2 + hc * (TN2 / 2);
+      using EP = Epilogue<(EPI >= 0 ? EPI : 0), ZIN>;
+      float ebase[EP::NS], eaccs[EP::NO];
+      if constexpr (EPI >= 0) EP::begin_tile(rp, m, n0, p.M, ebase, eaccs, num_tiles <= num_pairs);
+      float sums[TN2 / 2];
+#pragma unroll
+      for (int j = 0; j < TN2 / 2; j++) sums[j] = 0.f;
+      for (int ch = 0; ch < nch; ch++) {
+        mbar_wait(&tfull[acc], acc_phase);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int c = 0; c < TN2 / 32; c++) {
+          uint32_t v[16];
+          const uint32_t taddr = tmem_base + (uint32_t)(acc * TN2 + hc * (TN2 / 2) + c * 16) + ((uint32_t)(q * 32) << 16);
+          tmem_ld16(taddr, v);
+#pragma unroll
+          for (int j = 0; j < 16; j++) sums[c * 16 + j] = __fadd_rn(sums[c * 16 + j], __uint_as_float(v[j]));  // round to nearest
+        }
+        tcgen05_fence_before();
+        mbar_arrive_remote(&tempty[acc], lead);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+      float* crow = p.C + m + n0 * p.ldc;
+#pragma unroll
+      for (int c = 0; c < TN2 / 64; c++) {
+        if constexpr (EPI >= 0) {
+          uint32_t z[32];
+#pragma unroll
+          for (int j = 0; j < 32; j++) z[j] = __float_as_uint(sums[c * 32 + j]);
+          EP::chunk32(rp, z, m, n0 + c * 32, p.M, ebase, eaccs, nullptr, 0, -1, nullptr, nullptr, -1);
+        } else {
+          float* cp = crow + (long long)(c * 32) * p.ldc;
+          if (p.accumulate) {
+#pragma unroll
+            for (int h = 0; h < 4; h++) {  // 8 old values in flight at a time: the 128 sums leave few registers
+              float old[8];
+#pragma unroll
+              for (int j = 0; j < 8; j++) old[j] = __ldcg(cp + (h * 8 + j) * p.ldc);
+#pragma unroll
+              for (int j = 0; j < 8; j++) cp[(h * 8 + j) * p.ldc] = __fadd_rn(sums[c * 32 + h * 8 + j], old[j]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j++) cp[j * p.ldc] = sums[c * 32 + j];
+          }
+        }
+      }
+      if constexpr (EPI >= 0) {
+        // row-sum sinks: the thread holding columns 128..255 of this row hands its partial sums to
+        // the one holding 0..127 (fixed order: left half + right half), which delivers them
+        float* xch = reinterpret_cast<float*>(smem + S::TSH_OFF);  // [NO][128 rows]
+        if (hc == 1) {
+#pragma unroll
+          for (int k = 0; k < EP::NO; k++) xch[k * 128 + q * 32 + lane] = eaccs[k];
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (hc == 0) {
+#pragma unroll
+          for (int k = 0; k < EP::NO; k++) eaccs[k] = __fadd_rn(eaccs[k], xch[k * 128 + q * 32 + lane]);
+          EP::end_tile(rp, m, tile_n, p.M, eaccs, p, reinterpret_cast<unsigned*>(smem + S::BAR_OFF + 200));
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");  // xch is reused by the next tile
+      }
+    }
   } else {
     // ===================== epilogue warps (both CTAs): own 128 rows x 256 columns =====================
     const int q = warp & 3;
     int acc = 0;
     uint32_t acc_phase = 0;
-    const int kc = X3 ? p.kchunk : nkb;
     for (int tk = pair; tk < num_tiles; tk += num_pairs) {
       const int ks = tk / base_tiles, t = tk - ks * base_tiles;
       const long long m = (long long)(t % p.num_m) * (2 * TM) + (long long)rank * TM + q * 32 + lane;
@@ -1428,19 +1524,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       using EP = Epilogue<(EPI >= 0 ? EPI : 0), ZIN>;
       float ebase[EP::NS], eaccs[EP::NO];
       if constexpr (EPI >= 0) EP::begin_tile(rp, m, n0, p.M, ebase, eaccs, num_tiles <= num_pairs);
-     for (int ch = 0; ch < (X3 ? (nkb + kc - 1) / kc : 1); ch++) {
-      const int kb0 = X3 ? ch * kc : 0;
-      // X3: the tile arrives in chunks of k-blocks; every chunk but the first is added to the
-      // partial sums in C, the fused chain runs on the complete sum (C + last chunk)
-      bool add_old = EPI < 0 && p.accumulate && ksplit == 1;
-      bool last = true, red = false;
-      if constexpr (X3) {
-        last = kb0 + kc >= nkb;
-        // chunks are ADDED to C by the L2 (red.global.add.f32, round-to-nearest, nothing read on
-        // the SM side); only the fused chain's last chunk reads the partial sums back
-        red = (EPI < 0 && p.accumulate) || kb0 > 0;
-        add_old = EPI >= 0 && last && kb0 > 0;
-      }
+      const bool add_old = EPI < 0 && p.accumulate && ksplit == 1;
       mbar_wait(&tfull[acc], acc_phase);
       tcgen05_fence_after();
 #pragma unroll 1
@@ -1454,22 +1538,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         }
         const uint32_t taddr = tmem_base + (uint32_t)(acc * TN2 + c * 32) + ((uint32_t)(q * 32) << 16);
         tmem_ld32(taddr, v);
-        if (EPI >= 0 && last) {
-          if constexpr (EPI >= 0) {
-            if (add_old) {
-#pragma unroll
-              for (int j = 0; j < 32; j++) v[j] = __float_as_uint(__uint_as_float(v[j]) + old[j]);
-            }
-            EP::chunk32(rp, v, m, n0 + c * 32, p.M, ebase, eaccs, p.tsh, p.tsh_ld, p.tsh_out,
-                        reinterpret_cast<float4*>(smem + S::TSH_OFF) + q * 256, p.bsh, p.bsh_out);
-          }
+        if constexpr (EPI >= 0) {
+          EP::chunk32(rp, v, m, n0 + c * 32, p.M, ebase, eaccs, p.tsh, p.tsh_ld, p.tsh_out,
+                      reinterpret_cast<float4*>(smem + S::TSH_OFF) + q * 256, p.bsh, p.bsh_out);
         } else {
           float* cp = crow + (long long)(c * 32) * ldc;
-          if (X3 && red) {
-#pragma unroll
-            for (int j = 0; j < 32; j++) atomicAdd(cp + j * ldc, __uint_as_float(v[j]));
-            if (p.pace_ns) __nanosleep(p.pace_ns);
-          } else if (add_old) {
+          if (add_old) {
 #pragma unroll
             for (int j = 0; j < 32; j++) cp[j * ldc] = __uint_as_float(v[j]) + old[j];
           } else {
@@ -1478,16 +1552,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           }
         }
       }
-      if constexpr (EPI >= 0) {
-        if (last) EP::end_tile(rp, m, tile_n, p.M, eaccs, p, reinterpret_cast<unsigned*>(smem + S::BAR_OFF + 200));
-      }
+      if constexpr (EPI >= 0)
+        EP::end_tile(rp, m, tile_n, p.M, eaccs, p, reinterpret_cast<unsigned*>(smem + S::BAR_OFF + 200));
       tcgen05_fence_before();
       mbar_arrive_remote(&tempty[acc], lead);  // the leader's MMA warp waits for both CTAs' epilogues
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
       }
-     }
     }
   }
   tcgen05_fence_before();
@@ -1505,7 +1577,7 @@ static int launch2_mc(const GemmArgs& g, const Maps& mp, int sm_count, cudaStrea
   static int max_clusters = 0;  // co-resident clusters of 2 * MC CTAs the device can hold
   auto kern = gemm_tc2_kernel<A_MN, B_MN, EB, EPI, ZIN, X3, MC>;
   cudaLaunchConfig_t cfg = {};
-  cfg.blockDim = dim3(THREADS);
+  cfg.blockDim = dim3(X3 ? THREADS_X3 : THREADS);
   cfg.dynamicSmemBytes = Smem2T<X3>::TOTAL;
   cfg.stream = s;
   // regular clusters are CTA pairs; MC = 2 prefers clusters of four (two pairs sharing A by
@@ -1542,7 +1614,7 @@ static int launch2_mc(const GemmArgs& g, const Maps& mp, int sm_count, cudaStrea
   p.ldc = g.ldc;
   p.accumulate = g.accumulate;
   p.spread = getenv("YOTA_TMA_SPREAD") ? 1 : 0;
-  p.kchunk = x3_kchunk();
+  p.kchunk = x3_kchunk(1);
   p.pace_ns = getenv("YOTA_X3_PACE_NS") ? atoi(getenv("YOTA_X3_PACE_NS")) : 0;
   p.tsh = g.tsh;
   p.tsh_ld = g.tsh_ld;
