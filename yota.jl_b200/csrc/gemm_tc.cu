@@ -234,7 +234,6 @@ struct Params {
   // round-to-nearest (red.global.add.f32; the tile stays in L2 between chunks), so the truncation
   // bias is bounded by the chunk length instead of K.
   int kchunk;
-  int pace_ns;  // X3: pause of the epilogue warps after each 32-column slice of a chunk's drain
   // fused epilogue with a row-sum sink (db): the CTA that delivers the LAST partial of a 128-row
   // block also reduces the partials (same fixed order as rowsum_finish_kernel) and writes the
   // result -- no separate finisher launch on the critical path.  rs_cnt: one self-resetting
@@ -750,7 +749,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         } else if (X3 && red) {
 #pragma unroll
           for (int j = 0; j < 32; j++) atomicAdd(cp + j * p.ldc, __uint_as_float(v[j]));
-          if (p.pace_ns) __nanosleep(p.pace_ns);
         } else if (add_old) {
 #pragma unroll
           for (int j = 0; j < 32; j++) cp[j * p.ldc] = __uint_as_float(v[j]) + old[j];
@@ -1096,7 +1094,6 @@ static int launch(const GemmArgs& g, const Maps& mp, int sm_count, cudaStream_t 
   p.accumulate = g.accumulate;
   p.spread = getenv("YOTA_TMA_SPREAD") ? 1 : 0;
   p.kchunk = x3_kchunk(4);
-  p.pace_ns = getenv("YOTA_X3_PACE_NS") ? atoi(getenv("YOTA_X3_PACE_NS")) : 0;
   p.tsh = nullptr;
   p.tsh_ld = 0;
   p.tsh_out = -1;
@@ -1615,7 +1612,6 @@ static int launch2_mc(const GemmArgs& g, const Maps& mp, int sm_count, cudaStrea
   p.accumulate = g.accumulate;
   p.spread = getenv("YOTA_TMA_SPREAD") ? 1 : 0;
   p.kchunk = x3_kchunk(1);
-  p.pace_ns = getenv("YOTA_X3_PACE_NS") ? atoi(getenv("YOTA_X3_PACE_NS")) : 0;
   p.tsh = g.tsh;
   p.tsh_ld = g.tsh_ld;
   p.tsh_out = g.tsh_out;
