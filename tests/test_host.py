@@ -181,6 +181,14 @@ def test_planner_c4_slices_are_views_and_accumulation_is_in_place(built, monkeyp
     av_full = [A((1024, 1024)), A((1024, 1024)), A((1024,)), A((1024, 128, 128))]
     desc_full, _ = _plan(cases.make_c4(128), *av_full, flags=ffi.FLAG_GEMM_TF32)
     assert desc_full.count("[K split in 4]") == 2, [l for l in desc_full.splitlines() if "K split" in l]
+    # ... and the forward and backward recurrences (126 + 127 GEMM + epilogue steps) are one persistent launch each
+    marks = [l for l in desc_full.splitlines() if "one persistent launch]" in l]
+    assert len(marks) == 2 and "recurrence of 126 steps" in marks[0] and "recurrence of 127 steps" in marks[1], marks
+    monkeypatch.setenv("YOTA_NO_CHAIN", "1")
+    assert "persistent launch" not in _plan(cases.make_c4(128), *av_full, flags=ffi.FLAG_GEMM_TF32)[0]
+    monkeypatch.delenv("YOTA_NO_CHAIN")
+    # strict FP32 / BF16: no tcgen05 TF32 recurrence kernel
+    assert "persistent launch" not in _plan(cases.make_c4(128), *av_full, flags=0)[0]
     # BF16 / 3xTF32 keep whole-array operand shadows: the loop stays unrolled there and the tape's
     # accumulation is done in place (GEMM C += ..., slice +=) -- also the plan with the pass disabled
     for flags, env in ((ffi.FLAG_GEMM_BF16, None), (0, "1")):
