@@ -172,6 +172,23 @@ def test_planner_c5_gathers_in_the_region_and_scales_in_the_fold(built):
     assert ": getindex ->" in unf and ws_u > 8 << 30
 
 
+def test_planner_forks_small_leaf_steps(built, monkeypatch):
+    """C1 is twelve tiny kernels in a row only because a stream is a row: the loss, db2, dW2, db1, dW1
+    are leaves of the dataflow and are forked onto side streams (parallel branches of the graph);
+    what they read stays allocated until the join.  Big GEMMs (C3) stay in line."""
+    av = [A((128, 784)), A((128,)), A((10, 128)), A((10,)), A((784, 64)), A((10, 64))]
+    desc, (steps, launches, ws, *_r) = _plan(cases.c1_mlp, *av)
+    forked = [l.split(":")[0].strip() for l in desc.splitlines() if "(leaf: on a side stream)" in l]
+    assert forked == ["step 4", "step 5", "step 6", "step 9", "step 10"], desc
+    monkeypatch.setenv("YOTA_NO_FORK", "1")
+    desc0, (_s, _l, ws0, *_r0) = _plan(cases.c1_mlp, *av)
+    assert "side stream" not in desc0 and ws0 <= ws  # longer lifetimes cost a little arena
+    monkeypatch.delenv("YOTA_NO_FORK")
+    av3 = [A((4096, 4096))] * 8 + [A((4096,))] * 8 + [A((4096, 8192))] * 2
+    desc3, _ = _plan(cases.make_c3(8, 8192), *av3, flags=ffi.FLAG_GEMM_TF32)
+    assert all("matmul" not in l for l in desc3.splitlines() if "side stream" in l), desc3
+
+
 def test_planner_c4_slices_are_views_and_accumulation_is_in_place(built, monkeypatch):
     av = [A((1024, 1024)), A((1024, 1024)), A((1024,)), A((1024, 128, 16))]
     desc, (steps, *_r) = _plan(cases.make_c4(16), *av)

@@ -43,6 +43,7 @@ int ctx_ensure_device(yota_ctx* ctx) {
   YOTA_CUDA(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
   YOTA_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   YOTA_CUDA(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+  for (auto& ls : ctx->leaf_streams) YOTA_CUDA(cudaStreamCreateWithFlags(&ls, cudaStreamNonBlocking));
   YOTA_CUDA(cudaEventCreateWithFlags(&ctx->fence_event, cudaEventDisableTiming));
   YOTA_CUDA(cudaEventCreateWithFlags(&ctx->free_event, cudaEventDisableTiming));
   YOTA_CUDA(cudaHostAlloc((void**)&ctx->err_host, 4 * sizeof(long long), cudaHostAllocMapped));
@@ -167,6 +168,7 @@ int yota_shutdown(yota_ctx* ctx) {
     cudaStreamDestroy(ctx->comm_stream);
     cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->side_stream);
+    for (auto ls : ctx->leaf_streams) cudaStreamDestroy(ls);
     cudaEventDestroy(ctx->fence_event);
     if (ctx->free_event) cudaEventDestroy(ctx->free_event);
     for (auto& e : ctx->pending_ar) cudaEventDestroy(e.ev);

@@ -50,6 +50,7 @@ struct yota_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t comm_stream = nullptr;
   cudaStream_t side_stream = nullptr;  // work of a run that depends on its inputs only (index sorts)
+  cudaStream_t leaf_streams[3] = {nullptr, nullptr, nullptr};  // small leaf steps of a run (plan_side_leaves)
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t fence_event = nullptr;
   // size-bucketed free lists (caller-owned buffers come and go every grad() call)

@@ -110,6 +110,7 @@ struct Step {
   bool fused_away = false;  // finisher: performed by the last CTA of the kernel that wrote the partials
   int bsh_make = -1;      // fused-epilogue GEMM (BF16 mode): BF16 shadow it writes itself ...
   int bsh_make_out = -1;  // ... of this store output of the chain
+  int fork = -1;          // small leaf step (plan_side_leaves): runs on a side stream, joined at the end of the sweep
   int unget_launches = 1; // kernels of an ungetindex step (sort passes + fold)
   int chain_len = 0;      // head of a recurrence (plan_recurrence_chains): this many GEMM + epilogue steps
   int chain_head = -1;    // member of a recurrence (the head too): index of its head step
@@ -175,6 +176,8 @@ struct yota_program {
   int region_per_sm = 8;  // CTAs per SM the elementwise regions are sized for (fewer beside side-stream sorts)
   cudaEvent_t presort_fork = nullptr;
   std::vector<cudaEvent_t> presort_join;
+  int n_forks = 0;
+  std::vector<cudaEvent_t> fork_ev, join_ev;
   // where the caller-owned output buffers are touched, and which reductions follow which step
   // (plan_comm; rebuilt after yota_program_set_allreduce)
   struct CommPlan {
@@ -1171,6 +1174,64 @@ static int plan_transposed_shadows(yota_program& P) {
   return YOTA_OK;
 }
 
+// tensors a step reads (as the liveness pass sees them) / writes
+static std::vector<int> step_reads(const yota_program& P, const Step& st) {
+  std::vector<int> r = st.reads;
+  if (st.op >= 0 && st.kind != STEP_ROWSUM_FINISH && st.kind != STEP_SCALAR_FINISH)
+    for (int j = 0; j < P.ops[st.op].n_in; j++) r.push_back(P.ops[st.op].in[j]);
+  return r;
+}
+static std::vector<int> step_writes(const Step& st) {
+  std::vector<int> w = st.writes;
+  if (st.out_tensor >= 0) w.push_back(st.out_tensor);
+  return w;
+}
+
+// A launch-bound program (C1: twelve kernels of a few microseconds, each waiting for the one before)
+// is a chain only because a stream is one: dW, db and the loss are LEAVES of the dataflow -- nothing
+// later reads or rewrites what they produce.  Small leaf steps (finishers, column sums, GEMMs below
+// ~0.5 GFLOP) whose results are program outputs are forked onto side streams right where they stand
+// and joined at the end of the sweep; inside the CUDA graph they are parallel branches, and the
+// critical path is what really depends on what (C1: 12 -> 7 launches deep).  What a forked step
+// reads stays allocated until the join (plan_memory).  Big kernels fill the GPU anyway and stay in
+// line.  YOTA_NO_FORK=1 turns it off; programs that all-reduce are issued in stream order.
+static int plan_side_leaves(yota_program& P) {
+  if (getenv("YOTA_NO_FORK")) return YOTA_OK;
+  const int ns = (int)P.steps.size();
+  int last_launch = -1;
+  for (int s = 0; s < ns; s++)
+    if (P.steps[s].kind != STEP_NOP && !P.steps[s].fused_away) last_launch = s;
+  for (int s = 0; s < ns; s++) {
+    Step& st = P.steps[s];
+    if (st.kind == STEP_NOP || st.fused_away || s == last_launch) continue;
+    bool small = st.kind == STEP_ROWSUM_FINISH || st.kind == STEP_SCALAR_FINISH || st.kind == STEP_COLSUM;
+    if (st.kind == STEP_GEMM && st.epi_region < 0 && st.chain_head < 0 && st.shadow[0] < 0 && st.shadow[1] < 0 &&
+        st.tsh_use[0] < 0 && st.tsh_use[1] < 0) {
+      long long M, N, K, lda, ldb;
+      gemm_dims(P, P.ops[st.op], &M, &N, &K, &lda, &ldb);
+      small = 2.0 * (double)M * (double)N * (double)K <= 5.4e8;
+    }
+    if (!small) continue;
+    const std::vector<int> w = step_writes(st), r = step_reads(P, st);
+    bool leaf = !w.empty();
+    for (int t : w) leaf = leaf && P.T[root_of(P, t)].d.kind == YOTA_T_OUTPUT;  // a caller's buffer: never recycled
+    for (int s2 = s + 1; s2 < ns && leaf; s2++) {
+      const Step& o = P.steps[s2];
+      if (o.kind == STEP_NOP) continue;
+      for (int t2 : step_writes(o)) {  // nobody rewrites what it writes or reads
+        for (int t : w) leaf = leaf && root_of(P, t2) != root_of(P, t);
+        for (int t : r) leaf = leaf && root_of(P, t2) != root_of(P, t);
+      }
+      for (int t2 : step_reads(P, o))  // nobody reads what it writes
+        for (int t : w) leaf = leaf && root_of(P, t2) != root_of(P, t);
+    }
+    if (!leaf) continue;
+    st.fork = P.n_forks++;
+    st.label += " (leaf: on a side stream)";
+  }
+  return YOTA_OK;
+}
+
 // Back-to-back skinny GEMMs (the per-step products of an unrolled recurrence: 1024 x 128 x 1024,
 // ~9 us each, most of it launch latency, prologue and the first TMA round trip) are launched
 // with programmatic stream serialisation: the next grid is scheduled while this one drains, and
@@ -1267,7 +1328,7 @@ static int plan_dependent_launch(yota_program& P) {
   int prev = -1;
   for (size_t s = 0; s < P.steps.size(); s++) {
     Step& st = P.steps[s];
-    if (st.kind == STEP_NOP || st.fused_away) continue;
+    if (st.kind == STEP_NOP || st.fused_away || st.fork >= 0) continue;  // (forked leaves are not in this stream)
     if (st.kind == STEP_GEMM && prev >= 0) {
       st.pdl = true;
       const int a_root = root_of(P, P.ops[st.op].in[0]);
@@ -1298,12 +1359,10 @@ static int plan_memory(yota_program& P) {
   // last use per root tensor
   for (int s = 0; s < ns; s++) {
     const Step& st = P.steps[s];
-    std::vector<int> reads = st.reads;
-    if (st.op >= 0 && st.kind != STEP_ROWSUM_FINISH && st.kind != STEP_SCALAR_FINISH)
-      for (int j = 0; j < P.ops[st.op].n_in; j++) reads.push_back(P.ops[st.op].in[j]);
-    for (int t : reads) {
+    const int until = st.fork >= 0 ? ns - 1 : s;  // a forked leaf may still be reading when the sweep ends
+    for (int t : step_reads(P, st)) {
       TInfo& r = P.T[root_of(P, t)];
-      r.last_step = std::max(r.last_step, s);
+      r.last_step = std::max(r.last_step, until);
     }
   }
   for (size_t t = 0; t < P.T.size(); t++)
@@ -1345,7 +1404,7 @@ static int plan_memory(yota_program& P) {
         Step& fs = P.steps[r.finish_steps[q]];
         fs.ws_off = (long long)fl.alloc(fs.ws_bytes);
         r.ws_off[n_store + q] = fs.ws_off;
-        ws_frees[r.finish_steps[q]].push_back({(size_t)fs.ws_off, fs.ws_bytes});
+        ws_frees[fs.fork >= 0 ? ns - 1 : r.finish_steps[q]].push_back({(size_t)fs.ws_off, fs.ws_bytes});
       }
     } else if ((st.kind == STEP_UNGETINDEX || st.kind == STEP_GEMM) && st.ws_bytes > 0 && st.presort < 0) {
       st.ws_off = (long long)fl.alloc(st.ws_bytes);
@@ -2127,6 +2186,7 @@ extern "C" int yota_program_build(yota_ctx* ctx, const yota_op_desc* ops, int64_
   if ((st = plan_transposed_shadows(P))) return fail(st);
   if ((st = plan_recurrence_chains(P))) return fail(st);
   if ((st = plan_split_k(P))) return fail(st);
+  if ((st = plan_side_leaves(P))) return fail(st);
   if ((st = plan_dependent_launch(P))) return fail(st);
   if ((st = plan_memory(P))) return fail(st);
   P.n_launches = 0;
@@ -2225,6 +2285,8 @@ extern "C" int yota_program_destroy(yota_program* p) {
   for (auto& g : p->graphs)
     if (g.exec) cudaGraphExecDestroy(g.exec);
   for (auto e : p->ar_events) cudaEventDestroy(e);
+  for (auto e : p->fork_ev) cudaEventDestroy(e);
+  for (auto e : p->join_ev) cudaEventDestroy(e);
   if (p->presort_fork) cudaEventDestroy(p->presort_fork);
   for (auto e : p->presort_join) cudaEventDestroy(e);
   free_adam_state(p);
@@ -2733,6 +2795,7 @@ static int run_all_steps(yota_program& P, cudaStream_t s, bool with_comm, Timeli
   const int reserve = with_comm ? comm_reserved_sms(ctx) : 0;
   bool in_flight = false;
   int chain_done_until = -1;  // steps of a recurrence up to here were executed by their head's persistent launch
+  std::vector<int> forked;    // leaves running on side streams
   size_t ev = 0;
   // Buckets: outputs finished by a step wait until at least kBucketBytes are pending (a
   // layer's 16 KiB bias gradient rides with the next weight gradient instead of paying a
@@ -2751,8 +2814,27 @@ static int run_all_steps(yota_program& P, cudaStream_t s, bool with_comm, Timeli
       if (head_gemms > 0) head_gemms--;
     }
     const bool launches = st.kind != STEP_NOP && !st.fused_away;
-    if (tl && launches) YOTA_TRY(tl->open(st.label, s));
+    const bool leaf = st.fork >= 0 && !with_comm;
+    if (tl && launches && !leaf) YOTA_TRY(tl->open(st.label, s));
     if (st.presort >= 0) YOTA_CUDA(cudaStreamWaitEvent(s, P.presort_join[st.presort], 0));
+    if (leaf) {  // small leaf: beside the sweep, joined after the last step
+      while ((int)P.fork_ev.size() < P.n_forks) {
+        cudaEvent_t a, b;
+        YOTA_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        YOTA_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        P.fork_ev.push_back(a);
+        P.join_ev.push_back(b);
+      }
+      cudaStream_t lane = ctx->leaf_streams[st.fork % 3];
+      YOTA_CUDA(cudaEventRecord(P.fork_ev[st.fork], s));
+      YOTA_CUDA(cudaStreamWaitEvent(lane, P.fork_ev[st.fork], 0));
+      if (tl && launches) YOTA_TRY(tl->open(st.label, lane));
+      YOTA_TRY(run_step(P, st, lane));
+      if (tl && launches) YOTA_TRY(tl->close(lane));
+      YOTA_CUDA(cudaEventRecord(P.join_ev[st.fork], lane));
+      forked.push_back(st.fork);
+      continue;
+    }
     if (st.chain_len > 0) {  // head of a recurrence: one persistent launch for all its steps, if they line up
       // (not when a member is where a bound output is first touched or all-reduced: those waits and
       // launches are tied to the member's own place in the sweep)
@@ -2806,6 +2888,7 @@ static int run_all_steps(yota_program& P, cudaStream_t s, bool with_comm, Timeli
     }
   }
   ctx->sm_reserved = 0;
+  for (int k : forked) YOTA_CUDA(cudaStreamWaitEvent(s, P.join_ev[k], 0));
   if (with_comm && getenv("YOTA_AR_JOIN")) YOTA_TRY(ctx_join_comm(ctx, s));  // A/B: the round-1 behaviour
   // update!(param, grad) for the marked pairs: after every reader of the parameter in this sweep
   // and after its gradient has been summed over ranks (src/update.jl:42-49, x .= x .- lr .* gx)
