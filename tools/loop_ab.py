@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""evals/s of one workload in the graph-replayed loop (the product path): python tools/c5_ab.py [steps [workload [gemm mode]]]
+"""evals/s of one workload in the graph-replayed loop (the product path): python tools/loop_ab.py [steps [workload [gemm mode]]]
 Used for A/B runs through environment switches (YOTA_NO_PRESORT, YOTA_PRESORT_REGION_PER_SM)."""
 import os
 import sys
