@@ -13,3 +13,15 @@ for w in c4 c1; do
   python -c "
 import json;d=json.loads(open('gpurun_out/bench_$w.json').read().strip().splitlines()[-1]);print(d['value'],d['ms_per_step'],d['e2e']['value'],d['gpu_launches'],d.get('roofline',{}).get('frac'))"
 done
+# launch list of the C3 loop with the final code (after the bench above has exited 0 without ncu)
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/c3_launches_final.csv python bench.py --steps 2 --warmup 1 --quick > gpurun_out/c3_ncu.log 2>&1; echo "ncu c3 rc=$?"
+python - <<'PY'
+import csv, collections
+rows=[r for r in csv.reader(open('gpurun_out/c3_launches_final.csv')) if len(r)>5]
+hdr=rows[0]; ki=hdr.index('Kernel Name'); vi=hdr.index('Metric Value')
+agg=collections.OrderedDict()
+for r in rows[1:]:
+    k=r[ki][:80]; v=float(r[vi].replace(',',''))/1e3
+    a=agg.setdefault(k,[0,0.0]); a[0]+=1; a[1]+=v
+for k,a in agg.items(): print(f"{a[0]:4d} x avg {a[1]/a[0]:8.1f} us  {k}")
+PY
