@@ -788,9 +788,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // Steps are ordered through global counters, one per output tile: each of the leader's 128 epilogue
 // threads adds 1 (release) after it stored its part of h_i; a producer whose K-slice covers rows
 // [r0, r1) of h_i polls the counters of the tiles holding those rows (acquire) until they show
-// 128 (i + 1), then crosses into the
-// async proxy (fence.proxy.async) before the TMA loads.  All clusters are co-resident (the host
-// checks), nothing else on the device waits for this kernel while it spins.
+// 128 (i + 1), then crosses into the async proxy (fence.proxy.async) before the TMA loads.  All
+// clusters are co-resident (the host checks), nothing else on the device waits for this kernel
+// while it spins, and a poll that never succeeds gives up after ~1 s (wait_step_flag).
 // Operands advance per step by whole columns: B tile column b_col0 + i * b_dcol of one tensor map
 // over the container of all h_i; the chain's FULL operands and stores by e_dcol columns (folded
 // into the column argument of the epilogue -- ROWVEC / SCALAR operands do not move).
@@ -798,8 +798,8 @@ struct ChainParams {
   int nsteps;
   int b_col0, b_dcol;
   long long e_dcol;
-  unsigned* flags;
-  long long* err;  // err[3] = 1: a flag did not arrive (reported by the next synchronising call)
+  unsigned* flags;  // one counter per output tile, zeroed by the host before the launch
+  long long* err;  // err[3] = 1: a counter did not arrive (reported by the next synchronising call)
   // diagnostics (YOTA_CHAIN_TRACE=1, tools/chain_trace.py): %globaltimer stamps of the cluster of tile 0,
   // [step][8]: 0 flags seen, 1 B requested, 2 products done (leader), 3 products done (rank 1),
   // 4 partial sums sent (rank 1), 5 partial sums in (leader), 6 stored, 7 published
