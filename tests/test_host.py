@@ -172,6 +172,19 @@ def test_planner_c5_gathers_in_the_region_and_scales_in_the_fold(built):
     assert ": getindex ->" in unf and ws_u > 8 << 30
 
 
+def test_k_split_only_where_tiles_are_few(built):
+    """The K split of the 2-CTA kernel is for contractions with few 256 x 256 output tiles and a long
+    K; the C3 shapes -- whole batch or an eighth of it (8 GPUs) -- have 64-256 tiles and stay whole."""
+    for batch in (8192, 1024):
+        av = [A((4096, 4096))] * 8 + [A((4096,))] * 8 + [A((4096, batch))] * 2
+        desc, _ = _plan(cases.make_c3(8, batch), *av, flags=ffi.FLAG_GEMM_TF32)
+        assert "K split" not in desc and "persistent launch" not in desc, batch
+    f = lambda W, X: jl.sum(jl.tanh(W @ X))  # dW = dZ * X': 512 x 256 x 8192 -> 2 tiles
+    desc, _ = _plan(f, A((512, 256)), A((256, 8192)), flags=ffi.FLAG_GEMM_TF32)
+    assert desc.count("[K split in 4]") == 1, desc
+    assert "K split" not in _plan(f, A((512, 256)), A((256, 8192)), flags=0)[0]  # strict FP32: FFMA kernel
+
+
 def test_planner_forks_small_leaf_steps(built, monkeypatch):
     """C1 is twelve tiny kernels in a row only because a stream is a row: the loss, db2, dW2, db1, dW1
     are leaves of the dataflow and are forked onto side streams (parallel branches of the graph);
